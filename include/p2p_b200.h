@@ -1,0 +1,125 @@
+/* p2p_b200.h -- native C-ABI of the B200 near-field P2P library (libp2p_b200.so).
+ *
+ * The library replaces the body of the reference's GPU path behind
+ *   1_Indexing/inc/photoNs_CUDA.cuh:24-33 and 2_Redundant/inc/photoNs_CUDA.cuh:28-51
+ * (those exact symbols are exported by the compat shims, see photoNs_CUDA_indexing.h /
+ * photoNs_CUDA_redundant.h in this directory).  The native API below carries what those
+ * signatures cannot: the PM split radius r_s (never reaches the device in the reference, SURVEY
+ * defect D4), persistent device-resident particles, ghost (halo / periodic image) leaves, a
+ * device CSR of the (target leaf, source leaf) list and per-PARTICLE reduced accelerations.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns 0 on
+ * success, a negative p2p_status on failure (p2p_last_error() gives the text); nothing is printed
+ * unless P2P_B200_VERBOSE is set.  Calls on one context must be serialised by the caller (the
+ * reference drives its GPU from one worker thread, 1_Indexing/src/fmm.c:390); every entry point
+ * sets the context's device first, so it may be called from any host thread.
+ *
+ * Data model
+ *   particles : float4 {x*s, y*s, z*s, mass} on device, s = power of two chosen from r_s so that
+ *               scaling is exact; local particles [0, npart) then ghost particles.
+ *   leaves    : {first particle, count}; local leaves [0, nleaf) (targets AND sources), then ghost
+ *               leaves (sources only: halo leaves of other domains and periodic images, already
+ *               displaced by the sender exactly as 1_Indexing/src/remotes.c:360-366 does).
+ *   tasks     : (target leaf, source leaf) int32 pairs in any order, as walk_task_p2p emits them
+ *               (1_Indexing/src/fmm.c:402-534: ts[] = source, tt[] = target); packed on device into
+ *               CSR rows per target leaf with ascending source ids.
+ *   result    : acc[i] += sum over listed leaf pairs of  m * dx / max(r, eps)^3 * g(r / 2 r_s),
+ *               g(u) = erfc(u) + 2/sqrt(pi) u exp(-u^2)  (2_Redundant/src/photoNs_CUDA.cu:432-450),
+ *               g = 1 when r_s <= 0 (the plain kernel, 1_Indexing/src/photoNs_CUDA.cu:342-354).
+ *               G is not applied (1_Indexing/src/photoNs.c:161 applies it in the kick).
+ */
+#ifndef P2P_B200_H
+#define P2P_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p2p_ctx p2p_ctx;
+
+enum p2p_status {
+    P2P_OK = 0,
+    P2P_ERR_CUDA = -1,      /* a CUDA runtime call failed (same code the reference returns) */
+    P2P_ERR_ARG = -2,       /* bad argument (null pointer, negative size, leaf larger than P2P_MAX_LEAF) */
+    P2P_ERR_STATE = -3,     /* call order violated (e.g. compute before build_csr) */
+    P2P_ERR_NODEVICE = -4   /* no CUDA device / driver: there is NO CPU fallback */
+};
+
+#define P2P_MAX_LEAF 32     /* largest TARGET leaf occupancy the kernels accept (ghost source leaves: 512) */
+
+/* kernel variants, selectable for the ncu comparisons (default P2P_KERNEL_AUTO) */
+enum p2p_kernel_variant {
+    P2P_KERNEL_AUTO = 0,
+    P2P_KERNEL_SCALAR = 1,  /* one FP32 op per instruction */
+    P2P_KERNEL_PACKED = 2   /* fma.rn.f32x2 on target pairs (sm_100a FFMA2) */
+};
+
+const char* p2p_last_error(void);
+int p2p_device_count(void);
+
+int p2p_create(p2p_ctx** ctx, int device);
+int p2p_destroy(p2p_ctx* ctx);
+
+/* mass: particle mass used when per-particle masses are not supplied (MASSPART);
+ * eps: SoftenScale; rs: splitRadius, <= 0 selects the plain (untruncated) kernel. */
+int p2p_set_physics(p2p_ctx* ctx, double mass, double eps, double rs);
+int p2p_set_kernel_variant(p2p_ctx* ctx, int variant);
+/* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
+int p2p_set_stream(p2p_ctx* ctx, void* cuda_stream);
+
+/* Local particles in tree order.  pos: npart rows of 3 doubles, consecutive rows `stride_doubles`
+ * apart (3 for a packed array, 12 for the reference's Body AoS, 1_Indexing/inc/typesdef.h:48-57).
+ * Also zeroes the accelerations.  Local leaves: leaf_npart/leaf_ipart as in Pack
+ * (1_Indexing/inc/typesdef.h:38-46); empty leaves are legal. */
+int p2p_upload_particles(p2p_ctx* ctx, const double* pos, int64_t stride_doubles, int64_t npart);
+int p2p_upload_leaves(p2p_ctx* ctx, const int* leaf_npart, const int* leaf_ipart, int nleaf);
+
+/* Ghost sources.  Appends nbody displaced bodies (rows of 3 doubles, stride as above; the
+ * reference's RemoteBody has stride 4) and nleaf ghost leaves {start (relative to this batch),
+ * count}.  Returns the id of the first new leaf in *first_leaf_id.  p2p_clear_ghosts drops all. */
+int p2p_append_ghosts(p2p_ctx* ctx, const double* pos, int64_t stride_doubles, int64_t nbody, const int* start,
+                      const int* count, int nleaf, int* first_leaf_id);
+/* same, bodies already on the device as float4 {x, y, z, mass} in UNSCALED units (NCCL halo buffers) */
+int p2p_append_ghosts_device(p2p_ctx* ctx, const void* d_xyzm, int64_t nbody, const int* start, const int* count,
+                             int nleaf, int* first_leaf_id);
+int p2p_clear_ghosts(p2p_ctx* ctx);
+
+/* Task list.  tt = target leaf ids (local), ts = source leaf ids; source_offset is added to every
+ * ts (0 for local lists, *first_leaf_id for a ghost batch whose ids are batch-relative). */
+int p2p_clear_tasks(p2p_ctx* ctx);
+int p2p_append_tasks(p2p_ctx* ctx, const int* tt, const int* ts, int64_t ntask, int source_offset);
+/* interleaved {target, source} pairs, the reference's interactions_data layout (1_Indexing/src/fmm.c:873-877) */
+int p2p_append_tasks_interleaved(p2p_ctx* ctx, const int* ts_pairs, int64_t ntask, int source_offset);
+int p2p_build_csr(p2p_ctx* ctx);
+
+/* Launch the force kernel over the whole CSR (asynchronous on the context's stream). */
+int p2p_compute(p2p_ctx* ctx);
+int p2p_zero_acc(p2p_ctx* ctx);
+int p2p_synchronize(p2p_ctx* ctx);
+
+/* acc: npart rows of 3 doubles `stride_doubles` apart; accumulate != 0 does acc += result
+ * (the reference's update loop, 1_Indexing/src/fmm.c:895-908), else acc = result. */
+int p2p_download_acc(p2p_ctx* ctx, double* acc, int64_t stride_doubles, int accumulate);
+
+int p2p_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
+/* copies of the device CSR for parity tests: row_ptr[nleaf+1] (int64), col[ntask] (int32) */
+int p2p_download_csr(p2p_ctx* ctx, int64_t* row_ptr, int* col);
+/* milliseconds spent by the last p2p_compute / p2p_build_csr launch sequence (CUDA events) */
+int p2p_last_timings(p2p_ctx* ctx, float* ms_compute, float* ms_csr);
+
+/* One-call convenience used by the compat shims and the e2e benchmark: host buffers in, host
+ * accelerations out (H2D, CSR, kernel, D2H all inside).  Ghost arguments may be NULL / 0. */
+int p2p_step_host(p2p_ctx* ctx, const double* pos, int64_t pos_stride, int64_t npart, const int* leaf_npart,
+                  const int* leaf_ipart, int nleaf, const int* tt, const int* ts, int64_t ntask, double* acc,
+                  int64_t acc_stride, int accumulate);
+
+/* raw device pointers for plumbing layers that keep data on the GPU (torch / NCCL) */
+void* p2p_device_particles(p2p_ctx* ctx);   /* float4[npart + nghost], scaled */
+void* p2p_device_acc(p2p_ctx* ctx);         /* float4[npart], unscaled accelerations in .xyz */
+double p2p_position_scale(p2p_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

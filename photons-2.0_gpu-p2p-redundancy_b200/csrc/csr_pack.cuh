@@ -1,0 +1,195 @@
+// csr_pack.cuh -- interaction-list packing on the device.
+//
+// The reference re-packs and re-uploads per call: Indexing ships {t,s} pairs plus a padded
+// [leaf][maxParts][3] fp64 position array (1_Indexing/src/fmm.c:851-877), Redundant ships a private
+// copy of both leaves' particles per task (2_Redundant/src/fmm.c:812-838).  Here the walk's
+// (target, source) pairs are turned ONCE per step into a CSR over target leaves:
+//   count -> exclusive scan -> scatter -> per-row ascending sort of the source ids
+// (the sort makes the row order, hence the FP32 summation order, independent of atomics timing and
+// gives the staging copies ascending addresses).  All kernels are HBM-bound integer work.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+namespace p2p {
+
+__global__ void csr_count_kernel(const int* __restrict__ tt, long long n, unsigned int* __restrict__ cnt) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) atomicAdd(cnt + tt[i], 1u);
+}
+
+// three-phase exclusive scan of unsigned counts into 64-bit offsets
+constexpr int kScanTile = 2048;  // items per block (256 threads x 8)
+
+__global__ void __launch_bounds__(256) scan_tile_sums_kernel(const unsigned int* __restrict__ cnt, int n,
+                                                             unsigned long long* __restrict__ tile_sum) {
+    __shared__ unsigned long long red[8];
+    const int base = blockIdx.x * kScanTile;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int i = base + k * 256 + threadIdx.x;
+        if (i < n) s += cnt[i];
+    }
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(unsigned long long* __restrict__ tile_sum, int ntile) {
+    // single block, serial over chunks of 1024 tiles (ntile <= a few thousand)
+    __shared__ unsigned long long sh[1024];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntile; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned long long v = i < ntile ? tile_sum[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            unsigned long long o = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += o;
+            __syncthreads();
+        }
+        unsigned long long incl = sh[threadIdx.x];
+        if (i < ntile) tile_sum[i] = carry + incl - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(const unsigned int* __restrict__ cnt, int n,
+                                                         const unsigned long long* __restrict__ tile_off,
+                                                         long long* __restrict__ row_ptr,
+                                                         unsigned long long* __restrict__ cursor) {
+    __shared__ unsigned long long wsum[8];
+    const int base = blockIdx.x * kScanTile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // thread owns 8 consecutive items
+    unsigned int v[8];
+    unsigned long long s = 0;
+    const int i0 = base + threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = (i0 + k < n) ? cnt[i0 + k] : 0u; s += v[k]; }
+    unsigned long long incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    unsigned long long off = tile_off[blockIdx.x];
+    for (int k = 0; k < w; k++) off += wsum[k];
+    unsigned long long run = off + incl - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (i0 + k < n) { row_ptr[i0 + k] = (long long)run; cursor[i0 + k] = run; }
+        run += v[k];
+    }
+    if (i0 <= n - 1 && n - 1 < i0 + 8) row_ptr[n] = (long long)run;  // owner of the last item closes the array
+}
+
+__global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n,
+                                   unsigned long long* __restrict__ cursor, int* __restrict__ col) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long p = atomicAdd(cursor + tt[i], 1ull);
+        col[p] = ts[i];
+    }
+}
+
+// one warp per row: bitonic sort of the row's source ids in shared memory (rows up to kSortCap)
+constexpr int kSortCap = 2048;
+
+__global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __restrict__ row_ptr, int nrow,
+                                                            int* __restrict__ col, unsigned int* __restrict__ unsorted) {
+    __shared__ int sh[4][kSortCap];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int* a = sh[w];
+    for (int row = blockIdx.x * 4 + w; row < nrow; row += gridDim.x * 4) {
+        const long long b = row_ptr[row];
+        const int len = (int)(row_ptr[row + 1] - b);
+        if (len <= 1) continue;
+        if (len > kSortCap) { if (lane == 0) atomicAdd(unsorted, 1u); continue; }
+        int m = 1;
+        while (m < len) m <<= 1;
+        for (int i = lane; i < m; i += 32) a[i] = i < len ? col[b + i] : INT_MAX;
+        __syncwarp();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < m; i += 32) {
+                    int p = i ^ j;
+                    if (p > i) {
+                        int x = a[i], y = a[p];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { a[i] = y; a[p] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < len; i += 32) col[b + i] = a[i];
+        __syncwarp();
+    }
+}
+
+// sum over tasks of n_t * n_s: the pair-interaction count of the metric
+__global__ void __launch_bounds__(256) pair_count_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col,
+                                                         const int2* __restrict__ leaf, int nrow,
+                                                         unsigned long long* __restrict__ npairs) {
+    unsigned long long s = 0;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int row = warp; row < nrow; row += nwarp) {
+        const long long b = row_ptr[row], e = row_ptr[row + 1];
+        const unsigned long long nt = (unsigned long long)leaf[row].y;
+        unsigned long long ns = 0;
+        for (long long i = b + lane; i < e; i += 32) ns += (unsigned long long)leaf[col[i]].y;
+        s += nt * ns;
+    }
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0 && s) atomicAdd(npairs, s);
+}
+
+// fp64 AoS host layout (staged through pinned memory) -> scaled float4 {x,y,z,m}
+__global__ void pack_particles_kernel(const double* __restrict__ xyz, long long n, double scale, float mass,
+                                      float4* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4((float)(xyz[3 * i] * scale), (float)(xyz[3 * i + 1] * scale),
+                                    (float)(xyz[3 * i + 2] * scale), mass);
+}
+__global__ void rescale_particles_kernel(const float4* __restrict__ in, long long n, float scale, float4* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { float4 p = in[i]; out[i] = make_float4(p.x * scale, p.y * scale, p.z * scale, p.w); }
+}
+__global__ void leaves_pack_kernel(const int* __restrict__ start, const int* __restrict__ count, int n, int start_off,
+                                   int2* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_int2(start[i] + start_off, count[i]);
+}
+__global__ void add_offset_kernel(int* __restrict__ v, long long n, int off) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) v[i] += off;
+}
+__global__ void deinterleave_kernel(const int* __restrict__ pairs, long long n, int off, int* __restrict__ tt,
+                                    int* __restrict__ ts) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { tt[i] = pairs[2 * i]; ts[i] = pairs[2 * i + 1] + off; }
+}
+__global__ void acc_to_f64_kernel(const float4* __restrict__ acc, long long n, double* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { float4 a = acc[i]; out[3 * i] = a.x; out[3 * i + 1] = a.y; out[3 * i + 2] = a.z; }
+}
+
+}  // namespace p2p

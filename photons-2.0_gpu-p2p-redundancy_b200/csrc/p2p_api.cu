@@ -1,0 +1,562 @@
+// p2p_api.cu -- native C-ABI (include/p2p_b200.h) over the sm_100a kernels.
+// Host-side state is one context per device; device buffers are grow-only and persist across steps
+// (the reference allocates once, sized from the first step, and never re-sizes: SURVEY defect D16).
+// There is NO CPU fallback: without a device every call that needs one returns P2P_ERR_NODEVICE.
+#include "../../include/p2p_b200.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "csr_pack.cuh"
+#include "p2p_gcoef.h"
+#include "p2p_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_verbose = -1;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    if (g_verbose < 0) g_verbose = getenv("P2P_B200_VERBOSE") ? 1 : 0;
+    if (g_verbose) fprintf(stderr, "[p2p_b200] error %d: %s\n", code, g_err);
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? P2P_ERR_NODEVICE : P2P_ERR_CUDA, \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);       \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n, cudaStream_t st, size_t keep = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct p2p_ctx {
+    int device = 0;
+    int num_sm = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double mass = 1.0, eps = 0.0, rs = 0.0, scale = 1.0;
+    double part_scale = 0.0;   // scale the resident particles were packed with (0: none resident)
+    int variant = P2P_KERNEL_AUTO;
+    long long npart = 0, nghost = 0, ntask = 0, npairs = -1;
+    int nleaf = 0, nghostleaf = 0, max_target_leaf = 0;
+    bool csr_valid = false;
+    DevBuf<float4> part, acc;
+    DevBuf<int2> leaf;
+    DevBuf<int> tt, ts, col, itmp;
+    DevBuf<long long> row_ptr;
+    DevBuf<unsigned int> cnt;
+    DevBuf<unsigned long long> cursor, tile;
+    DevBuf<unsigned char> stage;
+    unsigned int* d_counter = nullptr;      // [0] row scheduler, [1] unsorted rows
+    unsigned long long* d_npairs = nullptr;
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    float ms_compute = 0.f, ms_csr = 0.f;
+    bool timed_compute = false, timed_csr = false;
+};
+
+namespace {
+
+int use(p2p_ctx* c) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+#define USE(c)               \
+    do {                     \
+        int r__ = use(c);    \
+        if (r__) return r__; \
+    } while (0)
+
+double pick_scale(double rs) {
+    if (!(rs > 0.0)) return 1.0;
+    return exp2(round(log2(1.0 / (2.0 * rs))));
+}
+
+int pinned(p2p_ctx* c, size_t bytes, void** out) {
+    if (bytes > c->h_pinned_bytes) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        c->h_pinned = nullptr;
+        c->h_pinned_bytes = 0;
+        CU(cudaMallocHost(&c->h_pinned, bytes));
+        c->h_pinned_bytes = bytes;
+    }
+    *out = c->h_pinned;
+    return 0;
+}
+
+// host rows of 3 doubles (stride in doubles) -> device float4 at dst[0..n)
+int upload_xyz(p2p_ctx* c, const double* pos, long long stride, long long n, float4* dst) {
+    if (n == 0) return 0;
+    CU(c->stage.reserve((size_t)n * 24, c->stream));
+    if (stride == 3) {
+        CU(cudaMemcpyAsync(c->stage.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int B = 256;
+    p2p::pack_particles_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(
+        reinterpret_cast<const double*>(c->stage.p), n, c->scale, (float)c->mass, dst);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int upload_ints(p2p_ctx* c, const int* a, const int* b, long long n, int** da, int** db) {
+    // two int arrays through one staging buffer
+    CU(c->itmp.reserve((size_t)(2 * n + 2), c->stream));
+    *da = c->itmp.p;
+    *db = c->itmp.p + n;
+    if (n) {
+        CU(cudaMemcpyAsync(*da, a, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(*db, b, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+template <int TT, bool TRUNC, bool PACKED>
+int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
+    auto kern = p2p::p2p_rows_kernel<TT, TRUNC, false, PACKED>;
+    const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT>);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) return fail(P2P_ERR_CUDA, "force kernel does not fit on an SM (smem %d)", smem);
+    long long want = ((long long)P.nrow + 3) / 4;
+    int grid = (int)std::min<long long>((long long)c->num_sm * per_sm, std::max<long long>(want, 1));
+    kern<<<grid, 128, smem, c->stream>>>(P);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <bool TRUNC, bool PACKED>
+int launch_tt(p2p_ctx* c, const p2p::KernelParams& P) {
+    if (c->max_target_leaf <= 8) return launch_rows<8, TRUNC, PACKED>(c, P);
+    if (c->max_target_leaf <= 16) return launch_rows<16, TRUNC, PACKED>(c, P);
+    return launch_rows<32, TRUNC, PACKED>(c, P);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* p2p_last_error(void) { return g_err; }
+
+int p2p_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int p2p_create(p2p_ctx** out, int device) {
+    if (!out) return fail(P2P_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(P2P_ERR_NODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(P2P_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(P2P_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    p2p_ctx* c = new p2p_ctx();
+    c->device = device;
+    c->num_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMalloc(&c->d_counter, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_npairs, sizeof(unsigned long long)));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->ev2));
+    CU(cudaEventCreate(&c->ev3));
+    *out = c;
+    return 0;
+}
+
+int p2p_destroy(p2p_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->part.release(); c->acc.release(); c->leaf.release(); c->tt.release(); c->ts.release(); c->col.release();
+    c->itmp.release(); c->row_ptr.release(); c->cnt.release(); c->cursor.release(); c->tile.release(); c->stage.release();
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_npairs) cudaFree(c->d_npairs);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int p2p_set_physics(p2p_ctx* c, double mass, double eps, double rs) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    if (!(eps >= 0.0) || !isfinite(mass)) return fail(P2P_ERR_ARG, "bad physics (mass %g eps %g)", mass, eps);
+    c->mass = mass; c->eps = eps; c->rs = rs;
+    c->scale = pick_scale(rs);
+    return 0;
+}
+
+int p2p_set_kernel_variant(p2p_ctx* c, int v) {
+    if (!c || v < 0 || v > 2) return fail(P2P_ERR_ARG, "bad kernel variant");
+    c->variant = v;
+    return 0;
+}
+
+int p2p_set_stream(p2p_ctx* c, void* s) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int p2p_upload_particles(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart) {
+    USE(c);
+    if (npart < 0 || (npart && !pos) || stride < 3) return fail(P2P_ERR_ARG, "bad particle array");
+    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false;
+    CU(c->part.reserve((size_t)npart + 1, c->stream));
+    CU(c->acc.reserve((size_t)npart + 1, c->stream));
+    int r = upload_xyz(c, pos, stride, npart, c->part.p);
+    if (r) return r;
+    c->part_scale = c->scale;
+    CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), c->stream));
+    return 0;
+}
+
+int p2p_upload_leaves(p2p_ctx* c, const int* leaf_npart, const int* leaf_ipart, int nleaf) {
+    USE(c);
+    if (nleaf < 0 || (nleaf && (!leaf_npart || !leaf_ipart))) return fail(P2P_ERR_ARG, "bad leaf arrays");
+    int mx = 0;
+    for (int i = 0; i < nleaf; i++) {
+        if (leaf_npart[i] < 0 || leaf_ipart[i] < 0 || (long long)leaf_ipart[i] + leaf_npart[i] > c->npart)
+            return fail(P2P_ERR_ARG, "leaf %d {npart %d, ipart %d} outside the %lld uploaded particles", i, leaf_npart[i],
+                        leaf_ipart[i], c->npart);
+        mx = std::max(mx, leaf_npart[i]);
+    }
+    if (mx > P2P_MAX_LEAF) return fail(P2P_ERR_ARG, "leaf occupancy %d exceeds P2P_MAX_LEAF %d", mx, P2P_MAX_LEAF);
+    c->nleaf = nleaf; c->nghostleaf = 0; c->nghost = 0; c->max_target_leaf = mx; c->csr_valid = false;
+    CU(c->leaf.reserve((size_t)nleaf + 1, c->stream));
+    int *dc, *ds;
+    int r = upload_ints(c, leaf_npart, leaf_ipart, nleaf, &dc, &ds);
+    if (r) return r;
+    if (nleaf) {
+        p2p::leaves_pack_kernel<<<(nleaf + 255) / 256, 256, 0, c->stream>>>(ds, dc, nleaf, 0, c->leaf.p);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int append_ghost_leaves(p2p_ctx* c, const int* start, const int* count, int nleaf, long long nbody, int* first_id) {
+    for (int i = 0; i < nleaf; i++) {
+        if (count[i] < 0 || start[i] < 0 || (long long)start[i] + count[i] > nbody)
+            return fail(P2P_ERR_ARG, "ghost leaf %d {start %d, count %d} outside the batch of %lld bodies", i, start[i],
+                        count[i], nbody);
+        if (count[i] > p2p::kStageParticles) return fail(P2P_ERR_ARG, "ghost leaf %d too large (%d)", i, count[i]);
+    }
+    const int first = c->nleaf + c->nghostleaf;
+    CU(c->leaf.reserve((size_t)first + nleaf + 1, c->stream, (size_t)first));
+    int *ds, *dc;
+    int r = upload_ints(c, start, count, nleaf, &ds, &dc);
+    if (r) return r;
+    if (nleaf) {
+        p2p::leaves_pack_kernel<<<(nleaf + 255) / 256, 256, 0, c->stream>>>(ds, dc, nleaf, (int)(c->npart + c->nghost),
+                                                                             c->leaf.p + first);
+        CU(cudaGetLastError());
+    }
+    if (first_id) *first_id = first;
+    c->nghostleaf += nleaf;
+    c->nghost += nbody;
+    c->csr_valid = false;
+    return 0;
+}
+
+int p2p_append_ghosts(p2p_ctx* c, const double* pos, int64_t stride, int64_t nbody, const int* start, const int* count,
+                      int nleaf, int* first_leaf_id) {
+    USE(c);
+    if (nbody < 0 || nleaf < 0 || (nbody && !pos) || (nleaf && (!start || !count)) || stride < 3)
+        return fail(P2P_ERR_ARG, "bad ghost batch");
+    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "upload particles after p2p_set_physics");
+    const long long base = c->npart + c->nghost;
+    CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
+    int r = upload_xyz(c, pos, stride, nbody, c->part.p + base);
+    if (r) return r;
+    return append_ghost_leaves(c, start, count, nleaf, nbody, first_leaf_id);
+}
+
+int p2p_append_ghosts_device(p2p_ctx* c, const void* d_xyzm, int64_t nbody, const int* start, const int* count, int nleaf,
+                             int* first_leaf_id) {
+    USE(c);
+    if (nbody < 0 || nleaf < 0 || (nbody && !d_xyzm) || (nleaf && (!start || !count))) return fail(P2P_ERR_ARG, "bad ghost batch");
+    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "upload particles after p2p_set_physics");
+    const long long base = c->npart + c->nghost;
+    CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
+    if (nbody) {
+        p2p::rescale_particles_kernel<<<(unsigned)((nbody + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const float4*>(d_xyzm), nbody, (float)c->scale, c->part.p + base);
+        CU(cudaGetLastError());
+    }
+    return append_ghost_leaves(c, start, count, nleaf, nbody, first_leaf_id);
+}
+
+int p2p_clear_ghosts(p2p_ctx* c) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false;
+    return 0;
+}
+
+int p2p_clear_tasks(p2p_ctx* c) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    c->ntask = 0; c->csr_valid = false; c->npairs = -1;
+    return 0;
+}
+
+static int check_tasks(p2p_ctx* c, const int* tt, const int* ts, long long n, int step, int off) {
+    const int nsrc = c->nleaf + c->nghostleaf;
+    for (long long i = 0; i < n; i++) {
+        int t = tt[i * step], s = ts[i * step] + off;
+        if (t < 0 || t >= c->nleaf || s < 0 || s >= nsrc)
+            return fail(P2P_ERR_ARG, "task %lld = (target %d, source %d) outside [0,%d) x [0,%d)", i, t, s, c->nleaf, nsrc);
+    }
+    return 0;
+}
+
+int p2p_append_tasks(p2p_ctx* c, const int* tt, const int* ts, int64_t n, int off) {
+    USE(c);
+    if (n < 0 || (n && (!tt || !ts))) return fail(P2P_ERR_ARG, "bad task arrays");
+    int r = check_tasks(c, tt, ts, n, 1, off);
+    if (r) return r;
+    CU(c->tt.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
+    CU(c->ts.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
+    if (n) {
+        CU(cudaMemcpyAsync(c->tt.p + c->ntask, tt, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->ts.p + c->ntask, ts, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (off) {
+            p2p::add_offset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->ts.p + c->ntask, n, off);
+            CU(cudaGetLastError());
+        }
+    }
+    c->ntask += n; c->csr_valid = false;
+    return 0;
+}
+
+int p2p_append_tasks_interleaved(p2p_ctx* c, const int* pairs, int64_t n, int off) {
+    USE(c);
+    if (n < 0 || (n && !pairs)) return fail(P2P_ERR_ARG, "bad task array");
+    int r = check_tasks(c, pairs, pairs + 1, n, 2, off);
+    if (r) return r;
+    CU(c->tt.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
+    CU(c->ts.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
+    if (n) {
+        CU(c->itmp.reserve((size_t)(2 * n), c->stream));
+        CU(cudaMemcpyAsync(c->itmp.p, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        p2p::deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->itmp.p, n, off, c->tt.p + c->ntask,
+                                                                                    c->ts.p + c->ntask);
+        CU(cudaGetLastError());
+    }
+    c->ntask += n; c->csr_valid = false;
+    return 0;
+}
+
+int p2p_build_csr(p2p_ctx* c) {
+    USE(c);
+    const int nrow = c->nleaf;
+    const long long n = c->ntask;
+    CU(cudaEventRecord(c->ev2, c->stream));
+    CU(c->row_ptr.reserve((size_t)nrow + 2, c->stream));
+    CU(c->cnt.reserve((size_t)nrow + 1, c->stream));
+    CU(c->cursor.reserve((size_t)nrow + 1, c->stream));
+    CU(c->col.reserve((size_t)n + 1, c->stream));
+    const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
+    CU(c->tile.reserve((size_t)ntile + 1, c->stream));
+    CU(cudaMemsetAsync(c->cnt.p, 0, ((size_t)nrow + 1) * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned int), c->stream));
+    CU(cudaMemsetAsync(c->d_npairs, 0, sizeof(unsigned long long), c->stream));
+    if (nrow == 0) {
+        CU(cudaMemsetAsync(c->row_ptr.p, 0, sizeof(long long), c->stream));
+    } else {
+        const int G = c->num_sm * 8;
+        if (n) {
+            p2p::csr_count_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, n, c->cnt.p);
+            CU(cudaGetLastError());
+        }
+        p2p::scan_tile_sums_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p);
+        p2p::scan_tile_offsets_kernel<<<1, 1024, 0, c->stream>>>(c->tile.p, ntile);
+        p2p::scan_apply_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p, c->row_ptr.p, c->cursor.p);
+        CU(cudaGetLastError());
+        if (n) {
+            p2p::csr_scatter_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, c->cursor.p, c->col.p);
+            p2p::csr_sort_rows_kernel<<<G, 128, 0, c->stream>>>(c->row_ptr.p, nrow, c->col.p, c->d_counter + 1);
+            p2p::pair_count_kernel<<<G, 256, 0, c->stream>>>(c->row_ptr.p, c->col.p, c->leaf.p, nrow, c->d_npairs);
+            CU(cudaGetLastError());
+        }
+    }
+    CU(cudaEventRecord(c->ev3, c->stream));
+    c->timed_csr = true;
+    c->csr_valid = true;
+    c->npairs = -1;
+    return 0;
+}
+
+int p2p_compute(p2p_ctx* c) {
+    USE(c);
+    if (!c->csr_valid) return fail(P2P_ERR_STATE, "p2p_compute before p2p_build_csr");
+    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "particles were uploaded before p2p_set_physics changed r_s");
+    if (c->max_target_leaf > 32) return fail(P2P_ERR_ARG, "target leaves above 32 particles are not supported by this build");
+    p2p::KernelParams P;
+    memset(&P, 0, sizeof P);
+    P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.acc = c->acc.p;
+    P.counter = c->d_counter; P.nrow = c->nleaf;
+    const double s = c->scale;
+    P.eps2 = (float)((c->eps * s) * (c->eps * s));
+    const bool trunc = c->rs > 0.0;
+    if (trunc) {
+        const double kappa = 1.0 / (2.0 * c->rs * s);
+        P.nlog2e_k2 = (float)(-1.4426950408889634 * kappa * kappa);
+        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] * pow(kappa, j + 2));
+        P.far_coord = (float)(24.0 / kappa);
+    } else {
+        P.far_coord = 1.0e18f;
+    }
+    P.out_scale = (float)(s * s * c->mass);
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    int r = 0;
+    if (c->nleaf > 0 && c->ntask > 0) {
+        const bool packed = c->variant == P2P_KERNEL_PACKED;
+        if (trunc) r = packed ? launch_tt<true, true>(c, P) : launch_tt<true, false>(c, P);
+        else r = packed ? launch_tt<false, true>(c, P) : launch_tt<false, false>(c, P);
+    }
+    if (r) return r;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed_compute = true;
+    return 0;
+}
+
+int p2p_zero_acc(p2p_ctx* c) {
+    USE(c);
+    if (c->npart) CU(cudaMemsetAsync(c->acc.p, 0, (size_t)c->npart * sizeof(float4), c->stream));
+    return 0;
+}
+
+int p2p_synchronize(p2p_ctx* c) {
+    USE(c);
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int p2p_download_acc(p2p_ctx* c, double* acc, int64_t stride, int accumulate) {
+    USE(c);
+    if ((c->npart && !acc) || stride < 3) return fail(P2P_ERR_ARG, "bad acc array");
+    const long long n = c->npart;
+    if (n == 0) return 0;
+    void* hp;
+    int r = pinned(c, (size_t)n * sizeof(float4), &hp);
+    if (r) return r;
+    CU(cudaMemcpyAsync(hp, c->acc.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const float4* a = reinterpret_cast<const float4*>(hp);
+    if (accumulate) {
+        for (long long i = 0; i < n; i++) { double* d = acc + i * stride; d[0] += a[i].x; d[1] += a[i].y; d[2] += a[i].z; }
+    } else {
+        for (long long i = 0; i < n; i++) { double* d = acc + i * stride; d[0] = a[i].x; d[1] = a[i].y; d[2] = a[i].z; }
+    }
+    return 0;
+}
+
+int p2p_counts(p2p_ctx* c, int64_t* ntask, int64_t* npairs) {
+    USE(c);
+    if (ntask) *ntask = c->ntask;
+    if (npairs) {
+        if (!c->csr_valid) return fail(P2P_ERR_STATE, "pair count needs p2p_build_csr");
+        if (c->npairs < 0) {
+            unsigned long long v = 0;
+            CU(cudaMemcpyAsync(&v, c->d_npairs, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->npairs = (long long)v;
+        }
+        *npairs = c->npairs;
+    }
+    return 0;
+}
+
+int p2p_download_csr(p2p_ctx* c, int64_t* row_ptr, int* col) {
+    USE(c);
+    if (!c->csr_valid) return fail(P2P_ERR_STATE, "no CSR built");
+    if (row_ptr) CU(cudaMemcpyAsync(row_ptr, c->row_ptr.p, ((size_t)c->nleaf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (col && c->ntask) CU(cudaMemcpyAsync(col, c->col.p, (size_t)c->ntask * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int p2p_last_timings(p2p_ctx* c, float* ms_compute, float* ms_csr) {
+    USE(c);
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->timed_compute) CU(cudaEventElapsedTime(&c->ms_compute, c->ev0, c->ev1));
+    if (c->timed_csr) CU(cudaEventElapsedTime(&c->ms_csr, c->ev2, c->ev3));
+    if (ms_compute) *ms_compute = c->ms_compute;
+    if (ms_csr) *ms_csr = c->ms_csr;
+    return 0;
+}
+
+int p2p_step_host(p2p_ctx* c, const double* pos, int64_t pos_stride, int64_t npart, const int* leaf_npart,
+                  const int* leaf_ipart, int nleaf, const int* tt, const int* ts, int64_t ntask, double* acc,
+                  int64_t acc_stride, int accumulate) {
+    int r;
+    if ((r = p2p_upload_particles(c, pos, pos_stride, npart))) return r;
+    if ((r = p2p_upload_leaves(c, leaf_npart, leaf_ipart, nleaf))) return r;
+    if ((r = p2p_clear_tasks(c))) return r;
+    if ((r = p2p_append_tasks(c, tt, ts, ntask, 0))) return r;
+    if ((r = p2p_build_csr(c))) return r;
+    if ((r = p2p_compute(c))) return r;
+    return p2p_download_acc(c, acc, acc_stride, accumulate);
+}
+
+void* p2p_device_particles(p2p_ctx* c) { return c ? c->part.p : nullptr; }
+void* p2p_device_acc(p2p_ctx* c) { return c ? c->acc.p : nullptr; }
+double p2p_position_scale(p2p_ctx* c) { return c ? c->scale : 0.0; }
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""ctypes binding of lib/libp2p_b200.so (native C-ABI, include/p2p_b200.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libp2p_b200.so")
+
+KERNEL_AUTO, KERNEL_SCALAR, KERNEL_PACKED = 0, 1, 2
+
+
+class P2PError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"p2p_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build_library(force=False):
+    """Compile the sm_100a libraries in-tree (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", PKG_DIR, "clean"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", PKG_DIR, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_int64)
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise P2PError(-4, f"{LIB_PATH} is not built (run __graft_entry__.build() or make -C {PKG_DIR}); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.p2p_last_error.restype = C.c_char_p
+    L.p2p_device_particles.restype = C.c_void_p
+    L.p2p_device_acc.restype = C.c_void_p
+    L.p2p_position_scale.restype = C.c_double
+    L.p2p_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    for name in ("p2p_destroy", "p2p_clear_ghosts", "p2p_clear_tasks", "p2p_build_csr", "p2p_compute", "p2p_zero_acc",
+                 "p2p_synchronize"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.p2p_set_physics.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.p2p_set_kernel_variant.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.p2p_upload_particles.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64]
+    L.p2p_upload_leaves.argtypes = [C.c_void_p, _ip, _ip, C.c_int]
+    L.p2p_append_ghosts.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _ip]
+    L.p2p_append_ghosts_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, _ip, _ip, C.c_int, _ip]
+    L.p2p_append_tasks.argtypes = [C.c_void_p, _ip, _ip, C.c_int64, C.c_int]
+    L.p2p_append_tasks_interleaved.argtypes = [C.c_void_p, _ip, C.c_int64, C.c_int]
+    L.p2p_download_acc.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int]
+    L.p2p_counts.argtypes = [C.c_void_p, _lp, _lp]
+    L.p2p_download_csr.argtypes = [C.c_void_p, _lp, _ip]
+    L.p2p_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.p2p_step_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _ip, _ip, C.c_int64, _dp,
+                                C.c_int64, C.c_int]
+    L.p2p_device_particles.argtypes = [C.c_void_p]
+    L.p2p_device_acc.argtypes = [C.c_void_p]
+    L.p2p_position_scale.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def device_count():
+    return int(load_library().p2p_device_count())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class P2PContext:
+    """One device context: persistent particles, leaves, ghost leaves, CSR task list, accelerations."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        self._chk(self._L.p2p_create(C.byref(h), int(device)))
+        self._h = h
+        self.npart = 0
+        self.nleaf = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise P2PError(rc, self._L.p2p_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.p2p_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_physics(self, mass, eps, rs):
+        self._chk(self._L.p2p_set_physics(self._h, float(mass), float(eps), float(rs)))
+
+    def set_kernel_variant(self, v):
+        self._chk(self._L.p2p_set_kernel_variant(self._h, int(v)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self._L.p2p_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def upload_particles(self, pos):
+        pos = _f64(pos)
+        assert pos.ndim == 2 and pos.shape[1] >= 3
+        self._chk(self._L.p2p_upload_particles(self._h, pos.ctypes.data_as(_dp), pos.shape[1], pos.shape[0]))
+        self.npart = pos.shape[0]
+
+    def upload_leaves(self, leaf_npart, leaf_ipart):
+        n, i = _i32(leaf_npart), _i32(leaf_ipart)
+        self._chk(self._L.p2p_upload_leaves(self._h, n.ctypes.data_as(_ip), i.ctypes.data_as(_ip), len(n)))
+        self.nleaf = len(n)
+
+    def append_ghosts(self, pos, start, count):
+        pos = _f64(pos).reshape(-1, 3) if np.size(pos) else np.zeros((0, 3))
+        s, c = _i32(start), _i32(count)
+        first = C.c_int()
+        self._chk(self._L.p2p_append_ghosts(self._h, pos.ctypes.data_as(_dp), 3, pos.shape[0], s.ctypes.data_as(_ip),
+                                            c.ctypes.data_as(_ip), len(s), C.byref(first)))
+        return first.value
+
+    def append_ghosts_device(self, dev_ptr, nbody, start, count):
+        s, c = _i32(start), _i32(count)
+        first = C.c_int()
+        self._chk(self._L.p2p_append_ghosts_device(self._h, C.c_void_p(dev_ptr), int(nbody), s.ctypes.data_as(_ip),
+                                                   c.ctypes.data_as(_ip), len(s), C.byref(first)))
+        return first.value
+
+    def clear_ghosts(self):
+        self._chk(self._L.p2p_clear_ghosts(self._h))
+
+    def clear_tasks(self):
+        self._chk(self._L.p2p_clear_tasks(self._h))
+
+    def append_tasks(self, tt, ts, source_offset=0):
+        tt, ts = _i32(tt), _i32(ts)
+        assert len(tt) == len(ts)
+        self._chk(self._L.p2p_append_tasks(self._h, tt.ctypes.data_as(_ip), ts.ctypes.data_as(_ip), len(tt),
+                                           int(source_offset)))
+
+    def append_tasks_interleaved(self, pairs, source_offset=0):
+        pairs = _i32(pairs).reshape(-1, 2)
+        self._chk(self._L.p2p_append_tasks_interleaved(self._h, pairs.ctypes.data_as(_ip), pairs.shape[0],
+                                                       int(source_offset)))
+
+    def build_csr(self):
+        self._chk(self._L.p2p_build_csr(self._h))
+
+    def compute(self):
+        self._chk(self._L.p2p_compute(self._h))
+
+    def zero_acc(self):
+        self._chk(self._L.p2p_zero_acc(self._h))
+
+    def synchronize(self):
+        self._chk(self._L.p2p_synchronize(self._h))
+
+    def download_acc(self, out=None, accumulate=False):
+        if out is None:
+            out = np.zeros((self.npart, 3))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape[0] == self.npart
+        self._chk(self._L.p2p_download_acc(self._h, out.ctypes.data_as(_dp), out.shape[1], 1 if accumulate else 0))
+        return out
+
+    def counts(self):
+        nt, npairs = C.c_int64(), C.c_int64()
+        self._chk(self._L.p2p_counts(self._h, C.byref(nt), C.byref(npairs)))
+        return nt.value, npairs.value
+
+    def download_csr(self):
+        nt, _ = self.counts()
+        row = np.zeros(self.nleaf + 1, np.int64)
+        col = np.zeros(max(nt, 1), np.int32)
+        self._chk(self._L.p2p_download_csr(self._h, row.ctypes.data_as(_lp), col.ctypes.data_as(_ip)))
+        return row, col[:nt]
+
+    def last_timings(self):
+        a, b = C.c_float(), C.c_float()
+        self._chk(self._L.p2p_last_timings(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def step_host(self, pos, leaf_npart, leaf_ipart, tt, ts, acc=None, accumulate=False):
+        """Host buffers in, host accelerations out (H2D + CSR + kernel + D2H)."""
+        pos = _f64(pos)
+        n, i, tt, ts = _i32(leaf_npart), _i32(leaf_ipart), _i32(tt), _i32(ts)
+        if acc is None:
+            acc = np.zeros((pos.shape[0], 3))
+        self._chk(self._L.p2p_step_host(self._h, pos.ctypes.data_as(_dp), pos.shape[1], pos.shape[0],
+                                        n.ctypes.data_as(_ip), i.ctypes.data_as(_ip), len(n), tt.ctypes.data_as(_ip),
+                                        ts.ctypes.data_as(_ip), len(tt), acc.ctypes.data_as(_dp), acc.shape[1],
+                                        1 if accumulate else 0))
+        self.npart, self.nleaf = pos.shape[0], len(n)
+        return acc
+
+    @property
+    def device_particles_ptr(self):
+        return self._L.p2p_device_particles(self._h)
+
+    @property
+    def device_acc_ptr(self):
+        return self._L.p2p_device_acc(self._h)
+
+    @property
+    def position_scale(self):
+        return self._L.p2p_position_scale(self._h)
