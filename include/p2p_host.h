@@ -1,0 +1,88 @@
+/* p2p_host.h -- host-side producers of the P2P path (libp2p_host.so, plain C-ABI, no CUDA).
+ *
+ * These are the B200 build's own implementations of the reference host functions that feed the
+ * GPU path; list parity (bit-exact trees, identical task sequences) is tested against the oracle
+ * and the compiled reference.  Names follow the reference:
+ *
+ *   p2p_build_localtree     build_localtree + bksort_inplace/build_kdtree/center_kdtree
+ *                           (1_Indexing/src/fmm.c:29-263) -- subtree-parallel, same ids/boxes
+ *   p2p_walk_task_p2p       walk_task_p2p from (first_node, first_node) (1_Indexing/src/fmm.c:402-534)
+ *                           -- frontier-parallel, emits the SAME SEQUENCE of (target, source) pairs
+ *   p2p_prepare_sendtree    prepare_sendtree2 (1_Indexing/src/remotes.c:337-446)
+ *   p2p_walk_task_p2p_ext   walk_task_p2p_ext from (first_node, 0) (1_Indexing/src/remotes.c:141-317)
+ *   p2p_domain_*            setup_domain_index (1_Indexing/src/initial.c:204-228), domain_initialize
+ *                           (1_Indexing/src/domains.c:401-469), center_toptree (1_Indexing/src/toptree.c:150-182),
+ *                           prepare_body_inOrderOf_domain (1_Indexing/src/domains.c:163-296)
+ *
+ * All functions return 0 / a count on success and a negative value on failure.
+ */
+#ifndef P2P_HOST_H
+#define P2P_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct p2p_tree p2p_tree;
+
+/* A view of the tree arrays in the reference's layout: leaves are ids [first_leaf, first_leaf+nleaf),
+ * nodes [first_node, first_node+nnode); `son` holds global ids (I/src/fmm.c:199-212). */
+typedef struct {
+    int npart, maxleaf, nleaf, nnode, nleaf_cap, nnode_cap, first_leaf, first_node;
+    const int* leaf_npart;      /* [nleaf] */
+    const int* leaf_ipart;      /* [nleaf] */
+    const double* leaf_center;  /* [nleaf][3] */
+    const double* leaf_width;   /* [nleaf][3] */
+    const int* node_npart;      /* [nnode] */
+    const int* node_son;        /* [nnode][2] */
+    const double* node_split;   /* [nnode] */
+    const double* node_center;  /* [nnode][3] */
+    const double* node_width;   /* [nnode][3] */
+} p2p_tree_view;
+
+/* Builds the local kd-tree over `npart` records.  Each record is `stride_doubles` doubles whose
+ * first three are the position (3 = packed positions, 12 = the reference's Body); whole records
+ * and the optional payload are permuted in place exactly as the reference permutes part[].
+ * bdl/bdr: domain box; direct_start: first split dimension (direct_local_start). */
+int p2p_build_localtree(p2p_tree** out, double* records, int64_t stride_doubles, int64_t* payload, int npart,
+                        int maxleaf, const double bdl[3], const double bdr[3], int direct_start, int nthreads);
+void p2p_tree_free(p2p_tree* t);
+int p2p_tree_get(const p2p_tree* t, p2p_tree_view* view);
+
+/* Local dual-tree walk.  On success *tt / *ts point to library-owned arrays of *ntask 0-based leaf
+ * indices (target, source) in the reference's traversal order; release with p2p_host_free. */
+int p2p_walk_task_p2p(const p2p_tree* t, double theta, double rcut, int nthreads, int** tt, int** ts, int64_t* ntask);
+
+/* Pruned image of the local tree for one target domain box and displacement (the halo a peer
+ * needs).  The image is the reference's RemoteNode/RemoteBody content (1_Indexing/inc/photoNs.h:202-214). */
+typedef struct {
+    int nnode, nbody;
+    int* npart;        /* [nnode] */
+    int* son;          /* [nnode][2]: leaves: {first body, end body}; pruned nodes: {-1,-1} */
+    double* center;    /* [nnode][3] (displaced) */
+    double* width;     /* [nnode][3] */
+    double* body;      /* [nbody][3] (displaced) */
+} p2p_image;
+int p2p_prepare_sendtree(const p2p_tree* t, const double* records, int64_t stride_doubles, const double tcenter[3],
+                         const double twidth[3], const double displace[3], double theta, double rcut, p2p_image* img);
+void p2p_image_free(p2p_image* img);
+
+/* Walk of the local tree against a received image: tt = 0-based local leaf, ts = image node index. */
+int p2p_walk_task_p2p_ext(const p2p_tree* t, const p2p_image* img, double theta, double rcut, int nthreads, int** tt,
+                          int** ts, int64_t* ntask);
+
+void p2p_host_free(void* p);
+
+/* Domain decomposition over P ranks (rank kd-tree in heap order, 2P-1 nodes). */
+int p2p_domain_of_rank(int nproc, int rank);
+int p2p_domain_setup(int nproc, double box, double* split, double* center, double* width, int* direct_of_node);
+/* routes records in place; sendcount[r] = number of records bound for rank r, stored contiguously in rank order */
+int p2p_domain_route(int nproc, const double* split, double* records, int64_t stride_doubles, int64_t* payload,
+                     int64_t npart, int* sendcount);
+
+int p2p_host_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -13,6 +13,7 @@
  *   a sequence of records  [u32 name_len][name][u32 dtype: 0=i32 1=f64 2=i64][u64 count][payload].
  */
 #define _GNU_SOURCE
+#include <signal.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -209,11 +210,19 @@ int main(int argc, char** argv) {
     fclose(f);
     stub_mpi_init(nproc);
     if (nproc == 1) return run_rank(0, 1, pos, ntot, box, maxleaf, nside, theta, do_ext, argv[9]);
+    pid_t pids[64];
     for (int r = 0; r < nproc; r++) {
-        pid_t p = fork();
-        if (p == 0) _exit(run_rank(r, nproc, pos, ntot, box, maxleaf, nside, theta, do_ext, argv[9]));
+        pids[r] = fork();
+        if (pids[r] == 0) _exit(run_rank(r, nproc, pos, ntot, box, maxleaf, nside, theta, do_ext, argv[9]));
     }
     int rc = 0, st;
-    while (wait(&st) > 0) if (!WIFEXITED(st) || WEXITSTATUS(st)) rc = 5;
+    while (wait(&st) > 0) {
+        if (!WIFEXITED(st) || WEXITSTATUS(st)) {
+            /* a rank died (the reference overruns its fixed halo buffers on very unbalanced inputs):
+             * its peers would wait for it forever, so stop them */
+            rc = 5;
+            for (int r = 0; r < nproc; r++) kill(pids[r], SIGKILL);
+        }
+    }
     return rc;
 }

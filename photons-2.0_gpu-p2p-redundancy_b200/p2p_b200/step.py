@@ -1,0 +1,109 @@
+"""The short-range P2P step on one rank: tree -> lists (+ periodic-image / halo ghosts) -> device.
+
+Mirrors the reference's fmm_prepare / fmm_task / fmm_ext sequence for the P2P part
+(1_Indexing/src/photoNs.c:97-123, 1_Indexing/src/fmm.c:947-1024,1026-1145) with the intended
+semantics: every local task once (the zero-shift self exchange of SURVEY defect D6 is not
+repeated), sources of the 26 periodic images and of other domains as displaced ghost leaves."""
+import time
+
+import numpy as np
+
+from . import host
+from .binding import P2PContext
+
+SHIFTS = [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) if (i, j, k) != (0, 0, 0)]
+"""The 26 periodic displacements in the order 1_Indexing/src/fmm.c:1084-1106 issues them."""
+
+
+class HostLists:
+    """Everything the device needs for one rank, produced on the host."""
+
+    def __init__(self):
+        self.tree = None
+        self.tt = self.ts = None                 # local tasks
+        self.ghost_pos = np.zeros((0, 3))        # displaced ghost bodies
+        self.ghost_start = np.zeros(0, np.int32)
+        self.ghost_count = np.zeros(0, np.int32)
+        self.gtt = np.zeros(0, np.int32)         # ghost tasks: target leaf, ghost leaf (batch-relative id)
+        self.gts = np.zeros(0, np.int32)
+        self.timings = {}
+
+
+def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, domain_box=None, direct_start=0):
+    """Single-rank producer: local tree + local list + (optionally) the 26 periodic-image ghost lists."""
+    rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
+    out = HostLists()
+    t0 = time.perf_counter()
+    bdl, bdr = ([0.0] * 3, [box] * 3) if domain_box is None else domain_box
+    T = host.LocalTree(pos, maxleaf, bdl, bdr, direct_start, nthreads)
+    t1 = time.perf_counter()
+    out.tree = T
+    out.tt, out.ts = T.walk_task_p2p(theta, rcut, nthreads)
+    t2 = time.perf_counter()
+    if periodic:
+        gp, gs, gc, gtt, gts = [], [], [], [], []
+        nbody = nleaf = 0
+        for sh in SHIFTS:
+            disp = np.array(sh, np.float64) * box
+            img = T.prepare_sendtree(T.node_center[0], T.node_width[0], disp, theta, rcut)
+            tt, ts = T.walk_task_p2p_ext(img, theta, rcut, nthreads)
+            if len(tt) == 0:
+                continue
+            # compact: only image leaves that are actually referenced become ghost leaves
+            used, inv = np.unique(ts, return_inverse=True)
+            cnt = img.npart[used]
+            st = img.son[used, 0]
+            sel = np.concatenate([np.arange(s, s + c) for s, c in zip(st, cnt)]) if len(used) else np.zeros(0, np.int64)
+            gp.append(img.body[sel])
+            gs.append(nbody + np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32))
+            gc.append(cnt.astype(np.int32))
+            gtt.append(tt)
+            gts.append((nleaf + inv).astype(np.int32))
+            nbody += int(cnt.sum())
+            nleaf += len(used)
+        if gp:
+            out.ghost_pos = np.concatenate(gp)
+            out.ghost_start = np.concatenate(gs).astype(np.int32)
+            out.ghost_count = np.concatenate(gc).astype(np.int32)
+            out.gtt = np.concatenate(gtt).astype(np.int32)
+            out.gts = np.concatenate(gts).astype(np.int32)
+    t3 = time.perf_counter()
+    out.timings = dict(build_s=t1 - t0, walk_s=t2 - t1, images_s=t3 - t2)
+    out.params = dict(rs=rs, rcut=rcut, eps=eps)
+    return out
+
+
+class ShortRangeStep:
+    """Device side of the step for one rank."""
+
+    def __init__(self, device=0, variant=0):
+        self.ctx = P2PContext(device)
+        self.ctx.set_kernel_variant(variant)
+
+    def upload(self, lists, mass, truncated=True):
+        T, c = lists.tree, self.ctx
+        prm = lists.params
+        c.set_physics(mass, prm["eps"], prm["rs"] if truncated else 0.0)
+        c.upload_particles(T.pos)
+        c.upload_leaves(T.leaf_npart, T.leaf_ipart)
+        c.clear_tasks()
+        c.append_tasks(lists.tt, lists.ts)
+        if len(lists.gtt):
+            first = c.append_ghosts(lists.ghost_pos, lists.ghost_start, lists.ghost_count)
+            c.append_tasks(lists.gtt, lists.gts, source_offset=first)
+        c.build_csr()
+
+    def compute(self):
+        self.ctx.compute()
+
+    def download(self, lists):
+        """Accelerations in the ORIGINAL particle order."""
+        a = self.ctx.download_acc()
+        out = np.empty_like(a)
+        out[lists.tree.perm] = a
+        return out
+
+    def run(self, lists, mass, truncated=True):
+        self.upload(lists, mass, truncated)
+        self.compute()
+        return self.download(lists)

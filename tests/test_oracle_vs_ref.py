@@ -1,0 +1,68 @@
+"""Bit-exact comparison of the oracle with the reference's own host code, run through
+oracle/_ref/ref_lists (built from /root/reference by oracle/Makefile; travels to the GPU box prebuilt).
+Skipped when that binary is absent."""
+import numpy as np
+import pytest
+from conftest import DEMO_BOX, DEMO_NSIDE, THETA
+
+import flow
+import oracle
+import refrun
+
+pytestmark = pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_lists not built (no /root/reference)")
+
+
+def _compare(pos, box, maxleaf, nside, nproc):
+    rr = refrun.run(pos, box, maxleaf, nside, THETA, do_ext=True, nproc=nproc, timeout=120)
+    oo = flow.short_range_lists(pos, box, maxleaf, nside, THETA, nproc, True, True)
+    for r, o in zip(rr, oo):
+        T = o["tree"]
+        assert np.array_equal(o["orig_index"], r["part_orig_index"])
+        assert np.array_equal(T.pos, r["part_pos"].reshape(-1, 3))
+        nl = r["leaf_npart_ipart"].reshape(-1, 2)
+        lcw = r["leaf_center_width"].reshape(-1, 6)
+        assert np.array_equal(T.leaf_npart[:T.nleaf], nl[:, 0]) and np.array_equal(T.leaf_ipart[:T.nleaf], nl[:, 1])
+        assert np.array_equal(T.leaf_center[:T.nleaf], lcw[:, :3]) and np.array_equal(T.leaf_width[:T.nleaf], lcw[:, 3:])
+        nn = r["node_npart_son"].reshape(-1, 3)
+        ncw = r["node_center_width_split"].reshape(-1, 7)
+        assert np.array_equal(T.node_npart[:T.nnode], nn[:, 0]) and np.array_equal(T.node_son[:T.nnode], nn[:, 1:])
+        assert np.array_equal(T.node_center[:T.nnode], ncw[:, :3]) and np.array_equal(T.node_width[:T.nnode], ncw[:, 3:6])
+        assert np.array_equal(T.node_split[:T.nnode], ncw[:, 6])
+        rts = r["local_tasks_ts"].reshape(-1, 2)
+        assert np.array_equal(o["local"][0], rts[:, 0]) and np.array_equal(o["local"][1], rts[:, 1])   # same ORDER
+        assert int(r["n_remote_calls"][0]) == len(o["remote"])
+        for c, rem in enumerate(o["remote"], 1):
+            assert np.array_equal(rem["shift"], r[f"remote{c}_shift"])
+            rn = r[f"remote{c}_node_npart_son"].reshape(-1, 3)
+            rc = r[f"remote{c}_node_center_width"].reshape(-1, 6)
+            assert np.array_equal(rem["image"]["npart"], rn[:, 0]) and np.array_equal(rem["image"]["son"], rn[:, 1:])
+            assert np.array_equal(rem["image"]["center"], rc[:, :3]) and np.array_equal(rem["image"]["width"], rc[:, 3:])
+            assert np.array_equal(rem["image"]["body"], r[f"remote{c}_body_pos"].reshape(-1, 3))
+            rts = r[f"remote{c}_tasks_ts"].reshape(-1, 2)
+            assert np.array_equal(rem["tt"], rts[:, 0]) and np.array_equal(rem["ts"], rts[:, 1] + T.first_leaf)
+
+
+@pytest.mark.parametrize("maxleaf,nproc", [(8, 1), (16, 1), (32, 1), (16, 2), (16, 4), (16, 8), (8, 4)])
+def test_demo_ic(demo_pos, maxleaf, nproc):
+    _compare(demo_pos, DEMO_BOX, maxleaf, DEMO_NSIDE, nproc)
+
+
+@pytest.mark.parametrize("kind,seed,n,maxleaf,nproc", [("clumpy", 1, 5000, 16, 1), ("clumpy", 2, 20000, 8, 2),
+                                                         ("uniform", 3, 30000, 32, 4), ("uniform", 4, 12000, 4, 3)])
+def test_random_inputs(kind, seed, n, maxleaf, nproc):
+    """Clumpy input with duplicate coordinates exercises ties at the mean split and empty leaves.
+    (Strongly unbalanced inputs on P > 2 ranks overrun the reference's fixed-size halo buffers --
+    lenExBody = NPART*1.5 of the LOCAL rank, 1_Indexing/src/fmm.c:1043-1050 -- and crash it, so the
+    multi-rank cases use uniform inputs.)"""
+    rng = np.random.default_rng(seed)
+    box = 1000.0
+    if kind == "clumpy":
+        centers = rng.uniform(0, box, (12, 3))
+        pos = centers[rng.integers(0, 12, n)] + rng.normal(0, 25.0, (n, 3))
+        pos[: n // 50] = pos[n // 50: 2 * (n // 50)]            # exact duplicates
+        pos[:, 0][: n // 20] = np.round(pos[:, 0][: n // 20])   # many equal x coordinates
+        pos %= box
+    else:
+        pos = rng.uniform(0, box, (n, 3))
+    pos = pos.astype(np.float32).astype(np.float64)
+    _compare(pos, box, maxleaf, 16, nproc)
