@@ -15,8 +15,10 @@
  * sets the context's device first, so it may be called from any host thread.
  *
  * Data model
- *   particles : float4 {x*s, y*s, z*s, mass} on device, s = power of two chosen from r_s so that
- *               scaling is exact; local particles [0, npart) then ghost particles.
+ *   particles : int4 {xi, yi, zi, mass bits} on device: 32-bit fixed-point coordinates over the box
+ *               given to p2p_set_box (resolution extent / 2^32 whatever the box size; coordinate
+ *               differences wrap to the minimal image, so periodic-image and halo sources may be
+ *               passed displaced or not); local particles [0, npart) then ghost particles.
  *   leaves    : {first particle, count}; local leaves [0, nleaf) (targets AND sources), then ghost
  *               leaves (sources only: halo leaves of other domains and periodic images, already
  *               displaced by the sender exactly as 1_Indexing/src/remotes.c:360-366 does).
@@ -65,6 +67,14 @@ int p2p_destroy(p2p_ctx* ctx);
  * eps: SoftenScale; rs: splitRadius, <= 0 selects the plain (untruncated) kernel. */
 int p2p_set_physics(p2p_ctx* ctx, double mass, double eps, double rs);
 int p2p_set_kernel_variant(p2p_ctx* ctx, int variant);
+/* Coordinate frame of the fixed-point positions: x in [origin, origin + extent) per axis, periodic
+ * with period `extent` (pass the simulation box for periodic runs; any target-source separation
+ * the lists imply must stay below extent / 2 per axis).  Must precede p2p_upload_particles.
+ * If never called, the box is derived from the uploaded particles (bounding cube, doubled). */
+int p2p_set_box(p2p_ctx* ctx, const double origin[3], double extent);
+/* kernel tuning knobs for the ncu sweeps: targets per pass (8/16/32), sources per lane (1/2),
+ * min resident blocks per SM (2..4); 0 keeps the default of that knob */
+int p2p_set_tuning(p2p_ctx* ctx, int targets_per_pass, int sources_per_lane, int min_blocks);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
 int p2p_set_stream(p2p_ctx* ctx, void* cuda_stream);
 
@@ -80,7 +90,7 @@ int p2p_upload_leaves(p2p_ctx* ctx, const int* leaf_npart, const int* leaf_ipart
  * count}.  Returns the id of the first new leaf in *first_leaf_id.  p2p_clear_ghosts drops all. */
 int p2p_append_ghosts(p2p_ctx* ctx, const double* pos, int64_t stride_doubles, int64_t nbody, const int* start,
                       const int* count, int nleaf, int* first_leaf_id);
-/* same, bodies already on the device as float4 {x, y, z, mass} in UNSCALED units (NCCL halo buffers) */
+/* same, bodies already on the device as float4 {x, y, z, mass} in simulation units (NCCL halo buffers) */
 int p2p_append_ghosts_device(p2p_ctx* ctx, const void* d_xyzm, int64_t nbody, const int* start, const int* count,
                              int nleaf, int* first_leaf_id);
 int p2p_clear_ghosts(p2p_ctx* ctx);
@@ -115,9 +125,8 @@ int p2p_step_host(p2p_ctx* ctx, const double* pos, int64_t pos_stride, int64_t n
                   int64_t acc_stride, int accumulate);
 
 /* raw device pointers for plumbing layers that keep data on the GPU (torch / NCCL) */
-void* p2p_device_particles(p2p_ctx* ctx);   /* float4[npart + nghost], scaled */
-void* p2p_device_acc(p2p_ctx* ctx);         /* float4[npart], unscaled accelerations in .xyz */
-double p2p_position_scale(p2p_ctx* ctx);
+void* p2p_device_particles(p2p_ctx* ctx);   /* int4[npart + nghost], fixed-point */
+void* p2p_device_acc(p2p_ctx* ctx);         /* float4[npart], accelerations in .xyz */
 
 #ifdef __cplusplus
 }

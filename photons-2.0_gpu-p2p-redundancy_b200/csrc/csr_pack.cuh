@@ -162,16 +162,29 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
     if (lane == 0 && s) atomicAdd(npairs, s);
 }
 
-// fp64 AoS host layout (staged through pinned memory) -> scaled float4 {x,y,z,m}
-__global__ void pack_particles_kernel(const double* __restrict__ xyz, long long n, double scale, float mass,
-                                      float4* __restrict__ out) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_float4((float)(xyz[3 * i] * scale), (float)(xyz[3 * i + 1] * scale),
-                                    (float)(xyz[3 * i + 2] * scale), mass);
+// 32-bit fixed-point coordinate over the (padded) box: q = round((x - origin) * 2^32 / extent) mod 2^32.
+// Differences of two such coordinates wrap to the minimal image, so displaced (periodic image /
+// halo) copies of a particle map to the same value as the original.
+__device__ __forceinline__ int to_fixed(double x, double origin, double inv_step) {
+    const long long q = __double2ll_rn((x - origin) * inv_step);
+    return (int)(unsigned int)(q & 0xffffffffLL);
 }
-__global__ void rescale_particles_kernel(const float4* __restrict__ in, long long n, float scale, float4* __restrict__ out) {
+// fp64 xyz rows (staged in device memory) -> int4 {xi, yi, zi, mass bits}
+__global__ void pack_particles_kernel(const double* __restrict__ xyz, long long n, double ox, double oy, double oz,
+                                      double inv_step, float mass, int4* __restrict__ out) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) { float4 p = in[i]; out[i] = make_float4(p.x * scale, p.y * scale, p.z * scale, p.w); }
+    if (i < n) out[i] = make_int4(to_fixed(xyz[3 * i], ox, inv_step), to_fixed(xyz[3 * i + 1], oy, inv_step),
+                                  to_fixed(xyz[3 * i + 2], oz, inv_step), __float_as_int(mass));
+}
+// float4 {x, y, z, m} already on the device (NCCL halo buffers) -> int4
+__global__ void pack_particles_f4_kernel(const float4* __restrict__ in, long long n, double ox, double oy, double oz,
+                                         double inv_step, int4* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float4 p = in[i];
+        out[i] = make_int4(to_fixed((double)p.x, ox, inv_step), to_fixed((double)p.y, oy, inv_step),
+                           to_fixed((double)p.z, oz, inv_step), __float_as_int(p.w));
+    }
 }
 __global__ void leaves_pack_kernel(const int* __restrict__ start, const int* __restrict__ count, int n, int start_off,
                                    int2* __restrict__ out) {

@@ -73,13 +73,16 @@ struct p2p_ctx {
     int device = 0;
     int num_sm = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    double mass = 1.0, eps = 0.0, rs = 0.0, scale = 1.0;
-    double part_scale = 0.0;   // scale the resident particles were packed with (0: none resident)
+    double mass = 1.0, eps = 0.0, rs = 0.0;
+    double origin[3] = {0, 0, 0}, extent = 0.0;   // fixed-point frame; extent 0: derive from the particles
+    bool box_set = false;
     int variant = P2P_KERNEL_AUTO;
+    int tune_tt = 0, tune_nsrc = 0, tune_minb = 0;
     long long npart = 0, nghost = 0, ntask = 0, npairs = -1;
     int nleaf = 0, nghostleaf = 0, max_target_leaf = 0;
     bool csr_valid = false;
-    DevBuf<float4> part, acc;
+    DevBuf<int4> part;
+    DevBuf<float4> acc;
     DevBuf<int2> leaf;
     DevBuf<int> tt, ts, col, itmp;
     DevBuf<long long> row_ptr;
@@ -92,6 +95,7 @@ struct p2p_ctx {
     size_t h_pinned_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float ms_compute = 0.f, ms_csr = 0.f;
+    int last_blocks_per_sm = 0;
     bool timed_compute = false, timed_csr = false;
 };
 
@@ -108,9 +112,25 @@ int use(p2p_ctx* c) {
         if (r__) return r__; \
     } while (0)
 
-double pick_scale(double rs) {
-    if (!(rs > 0.0)) return 1.0;
-    return exp2(round(log2(1.0 / (2.0 * rs))));
+// bounding cube of host positions, doubled, so that no separation reaches extent / 2
+int auto_box(p2p_ctx* c, const double* pos, long long stride, long long n) {
+    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    bool first = true;
+    for (long long i = 0; i < n; i++) {
+        const double* p = pos + i * stride;
+        if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))) continue;   // padding slots of the compat layouts
+        for (int k = 0; k < 3; k++) {
+            if (first || p[k] < lo[k]) lo[k] = p[k];
+            if (first || p[k] > hi[k]) hi[k] = p[k];
+        }
+        first = false;
+    }
+    double w = 0.0;
+    for (int k = 0; k < 3; k++) w = std::max(w, hi[k] - lo[k]);
+    if (!(w > 0.0)) w = 1.0;
+    c->extent = 4.0 * w;
+    for (int k = 0; k < 3; k++) c->origin[k] = 0.5 * (lo[k] + hi[k]) - 0.5 * c->extent;
+    return 0;
 }
 
 int pinned(p2p_ctx* c, size_t bytes, void** out) {
@@ -125,8 +145,8 @@ int pinned(p2p_ctx* c, size_t bytes, void** out) {
     return 0;
 }
 
-// host rows of 3 doubles (stride in doubles) -> device float4 at dst[0..n)
-int upload_xyz(p2p_ctx* c, const double* pos, long long stride, long long n, float4* dst) {
+// host rows of 3 doubles (stride in doubles) -> device fixed-point int4 at dst[0..n)
+int upload_xyz(p2p_ctx* c, const double* pos, long long stride, long long n, int4* dst) {
     if (n == 0) return 0;
     CU(c->stage.reserve((size_t)n * 24, c->stream));
     if (stride == 3) {
@@ -136,7 +156,8 @@ int upload_xyz(p2p_ctx* c, const double* pos, long long stride, long long n, flo
     }
     const int B = 256;
     p2p::pack_particles_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(
-        reinterpret_cast<const double*>(c->stage.p), n, c->scale, (float)c->mass, dst);
+        reinterpret_cast<const double*>(c->stage.p), n, c->origin[0], c->origin[1], c->origin[2], 4294967296.0 / c->extent,
+        (float)c->mass, dst);
     CU(cudaGetLastError());
     return 0;
 }
@@ -153,10 +174,12 @@ int upload_ints(p2p_ctx* c, const int* a, const int* b, long long n, int** da, i
     return 0;
 }
 
-template <int TT, bool TRUNC, bool PACKED>
+constexpr int kStage = 384;   // particles per staging buffer: 2 x 6 KB + targets per warp -> 16 warps / SM fit
+
+template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB>
 int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
-    auto kern = p2p::p2p_rows_kernel<TT, TRUNC, false, PACKED>;
-    const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT>);
+    auto kern = p2p::p2p_rows_kernel<TT, NSRC, kStage, TRUNC, PACKED, MINB>;
+    const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT, kStage>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
@@ -165,14 +188,26 @@ int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
     int grid = (int)std::min<long long>((long long)c->num_sm * per_sm, std::max<long long>(want, 1));
     kern<<<grid, 128, smem, c->stream>>>(P);
     CU(cudaGetLastError());
+    c->last_blocks_per_sm = per_sm;
     return 0;
 }
 
+template <int TT, int NSRC, bool TRUNC, bool PACKED>
+int launch_minb(p2p_ctx* c, const p2p::KernelParams& P, int minb) {
+    if constexpr (!TRUNC) {
+        return launch_rows<TT, 1, false, PACKED, 3>(c, P);   // plain kernel: one tuning only
+    } else {
+        if (minb == 2) return launch_rows<TT, NSRC, TRUNC, PACKED, 2>(c, P);
+        if (minb == 4) return launch_rows<TT, NSRC, TRUNC, PACKED, 4>(c, P);
+        return launch_rows<TT, NSRC, TRUNC, PACKED, 3>(c, P);
+    }
+}
+
 template <bool TRUNC, bool PACKED>
-int launch_tt(p2p_ctx* c, const p2p::KernelParams& P) {
-    if (c->max_target_leaf <= 8) return launch_rows<8, TRUNC, PACKED>(c, P);
-    if (c->max_target_leaf <= 16) return launch_rows<16, TRUNC, PACKED>(c, P);
-    return launch_rows<32, TRUNC, PACKED>(c, P);
+int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P, int tt, int nsrc, int minb) {
+    if (tt == 8) return nsrc == 2 ? launch_minb<8, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<8, 1, TRUNC, PACKED>(c, P, minb);
+    if (tt == 16) return nsrc == 2 ? launch_minb<16, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<16, 1, TRUNC, PACKED>(c, P, minb);
+    return nsrc == 2 ? launch_minb<32, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<32, 1, TRUNC, PACKED>(c, P, minb);
 }
 
 }  // namespace
@@ -238,7 +273,21 @@ int p2p_set_physics(p2p_ctx* c, double mass, double eps, double rs) {
     if (!c) return fail(P2P_ERR_ARG, "null context");
     if (!(eps >= 0.0) || !isfinite(mass)) return fail(P2P_ERR_ARG, "bad physics (mass %g eps %g)", mass, eps);
     c->mass = mass; c->eps = eps; c->rs = rs;
-    c->scale = pick_scale(rs);
+    return 0;
+}
+
+int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
+    if (!c || !origin || !(extent > 0.0)) return fail(P2P_ERR_ARG, "bad box");
+    for (int k = 0; k < 3; k++) c->origin[k] = origin[k];
+    c->extent = extent;
+    c->box_set = true;
+    return 0;
+}
+
+int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
+    if (!c || (tt && tt != 8 && tt != 16 && tt != 32) || nsrc < 0 || nsrc > 2 || minb < 0 || minb == 1 || minb > 4)
+        return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16/32, sources_per_lane 1/2, min_blocks 2..4)");
+    c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb;
     return 0;
 }
 
@@ -260,9 +309,9 @@ int p2p_upload_particles(p2p_ctx* c, const double* pos, int64_t stride, int64_t 
     c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false;
     CU(c->part.reserve((size_t)npart + 1, c->stream));
     CU(c->acc.reserve((size_t)npart + 1, c->stream));
+    if (!c->box_set) auto_box(c, pos, stride, npart);
     int r = upload_xyz(c, pos, stride, npart, c->part.p);
     if (r) return r;
-    c->part_scale = c->scale;
     CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), c->stream));
     return 0;
 }
@@ -295,7 +344,7 @@ static int append_ghost_leaves(p2p_ctx* c, const int* start, const int* count, i
         if (count[i] < 0 || start[i] < 0 || (long long)start[i] + count[i] > nbody)
             return fail(P2P_ERR_ARG, "ghost leaf %d {start %d, count %d} outside the batch of %lld bodies", i, start[i],
                         count[i], nbody);
-        if (count[i] > p2p::kStageParticles) return fail(P2P_ERR_ARG, "ghost leaf %d too large (%d)", i, count[i]);
+        if (count[i] > kStage) return fail(P2P_ERR_ARG, "ghost leaf %d too large (%d > %d)", i, count[i], kStage);
     }
     const int first = c->nleaf + c->nghostleaf;
     CU(c->leaf.reserve((size_t)first + nleaf + 1, c->stream, (size_t)first));
@@ -319,7 +368,7 @@ int p2p_append_ghosts(p2p_ctx* c, const double* pos, int64_t stride, int64_t nbo
     USE(c);
     if (nbody < 0 || nleaf < 0 || (nbody && !pos) || (nleaf && (!start || !count)) || stride < 3)
         return fail(P2P_ERR_ARG, "bad ghost batch");
-    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "upload particles after p2p_set_physics");
+    if (!(c->extent > 0.0)) return fail(P2P_ERR_STATE, "upload local particles (or set the box) before ghosts");
     const long long base = c->npart + c->nghost;
     CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
     int r = upload_xyz(c, pos, stride, nbody, c->part.p + base);
@@ -331,12 +380,13 @@ int p2p_append_ghosts_device(p2p_ctx* c, const void* d_xyzm, int64_t nbody, cons
                              int* first_leaf_id) {
     USE(c);
     if (nbody < 0 || nleaf < 0 || (nbody && !d_xyzm) || (nleaf && (!start || !count))) return fail(P2P_ERR_ARG, "bad ghost batch");
-    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "upload particles after p2p_set_physics");
+    if (!(c->extent > 0.0)) return fail(P2P_ERR_STATE, "upload local particles (or set the box) before ghosts");
     const long long base = c->npart + c->nghost;
     CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
     if (nbody) {
-        p2p::rescale_particles_kernel<<<(unsigned)((nbody + 255) / 256), 256, 0, c->stream>>>(
-            reinterpret_cast<const float4*>(d_xyzm), nbody, (float)c->scale, c->part.p + base);
+        p2p::pack_particles_f4_kernel<<<(unsigned)((nbody + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const float4*>(d_xyzm), nbody, c->origin[0], c->origin[1], c->origin[2], 4294967296.0 / c->extent,
+            c->part.p + base);
         CU(cudaGetLastError());
     }
     return append_ghost_leaves(c, start, count, nleaf, nbody, first_leaf_id);
@@ -444,31 +494,34 @@ int p2p_build_csr(p2p_ctx* c) {
 int p2p_compute(p2p_ctx* c) {
     USE(c);
     if (!c->csr_valid) return fail(P2P_ERR_STATE, "p2p_compute before p2p_build_csr");
-    if (c->part_scale != c->scale) return fail(P2P_ERR_STATE, "particles were uploaded before p2p_set_physics changed r_s");
-    if (c->max_target_leaf > 32) return fail(P2P_ERR_ARG, "target leaves above 32 particles are not supported by this build");
+    if (c->max_target_leaf > P2P_MAX_LEAF) return fail(P2P_ERR_ARG, "target leaves above %d particles are not supported", P2P_MAX_LEAF);
     p2p::KernelParams P;
     memset(&P, 0, sizeof P);
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.acc = c->acc.p;
     P.counter = c->d_counter; P.nrow = c->nleaf;
-    const double s = c->scale;
-    P.eps2 = (float)((c->eps * s) * (c->eps * s));
     const bool trunc = c->rs > 0.0;
+    // kernel length unit: 2 r_s (so that u = r) for the truncated kernel, the box extent otherwise
+    const double unit = trunc ? 2.0 * c->rs : (c->extent > 0.0 ? c->extent : 1.0);
+    P.k_fix = (float)(c->extent / 4294967296.0 / unit);
+    P.eps2 = (float)((c->eps / unit) * (c->eps / unit));
     if (trunc) {
-        const double kappa = 1.0 / (2.0 * c->rs * s);
-        P.nlog2e_k2 = (float)(-1.4426950408889634 * kappa * kappa);
-        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] * pow(kappa, j + 2));
-        P.far_coord = (float)(24.0 / kappa);
+        P.nlog2e = -1.4426950408889634f;
+        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)P2P_GCOEF_10[j + 2];
+        P.far_coord = 24.0f;
     } else {
         P.far_coord = 1.0e18f;
     }
-    P.out_scale = (float)(s * s * c->mass);
+    P.out_scale = (float)(c->mass / (unit * unit));
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
     CU(cudaEventRecord(c->ev0, c->stream));
     int r = 0;
     if (c->nleaf > 0 && c->ntask > 0) {
-        const bool packed = c->variant == P2P_KERNEL_PACKED;
-        if (trunc) r = packed ? launch_tt<true, true>(c, P) : launch_tt<true, false>(c, P);
-        else r = packed ? launch_tt<false, true>(c, P) : launch_tt<false, false>(c, P);
+        const bool packed = c->variant != P2P_KERNEL_SCALAR;
+        int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : (c->max_target_leaf <= 16 ? 16 : 32));
+        int nsrc = c->tune_nsrc ? c->tune_nsrc : 1;
+        int minb = c->tune_minb ? c->tune_minb : 3;
+        if (trunc) r = packed ? launch_cfg<true, true>(c, P, tt, nsrc, minb) : launch_cfg<true, false>(c, P, tt, nsrc, minb);
+        else r = packed ? launch_cfg<false, true>(c, P, tt, nsrc, minb) : launch_cfg<false, false>(c, P, tt, nsrc, minb);
     }
     if (r) return r;
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -557,6 +610,5 @@ int p2p_step_host(p2p_ctx* c, const double* pos, int64_t pos_stride, int64_t npa
 
 void* p2p_device_particles(p2p_ctx* c) { return c ? c->part.p : nullptr; }
 void* p2p_device_acc(p2p_ctx* c) { return c ? c->acc.p : nullptr; }
-double p2p_position_scale(p2p_ctx* c) { return c ? c->scale : 0.0; }
 
 }  // extern "C"

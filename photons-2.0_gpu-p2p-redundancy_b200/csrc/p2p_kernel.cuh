@@ -4,49 +4,57 @@
 // (target leaf, source leaf) task, sources in a per-thread stack array) and ComputeP2PDualNaive /
 // ComputeP2PSelfInteractions (2_Redundant/src/photoNs_CUDA.cu:225-309, 386-458).
 //
-// Work decomposition (one warp = one CSR row = one target leaf at a time, persistent warps pull
-// rows from an atomic counter):
+// Data: particles live in HBM as int4 {xi, yi, zi, mass bits}: 32-bit FIXED-POINT coordinates over
+// the (padded) box, so resolution is box/2^32 whatever the box size (FP32 absolute coordinates lose
+// ~6e-8*box, SURVEY hard part H2) and periodic images are free: the difference of two fixed-point
+// coordinates wraps to the minimal image, so image / halo sources need no displaced copies.
+//
+// Work decomposition (one warp = one CSR row = one target leaf at a time, persistent warps pull rows
+// from an atomic counter):
 //   * the row's source leaves are streamed through a private double-buffered shared-memory ring:
-//     each lane owns one source leaf of the chunk and issues ONE bulk async copy
-//     (cp.async.bulk, SASS UBLKCP) of that leaf's float4 {x,y,z,m} run; completion is tracked by
-//     an mbarrier transaction count, so the warp never blocks on a load it issued itself;
-//   * SOURCES are spread over the 32 lanes, TARGETS are walked by an unrolled loop with the target
-//     coordinates broadcast from shared memory and the per-target accumulators held in registers.
-//     Lane utilisation is therefore independent of the leaf occupancy (a lane=target mapping would
-//     idle 14-30 % of the lanes at the reference's leaf fill of 57-76 %); the
-//     32-lane reduction happens once per row, not once per tile;
-//   * partial 32-source slices are carried across chunk boundaries in registers, so only the last
-//     slice of a row is ragged.
+//     each lane owns one source leaf of the chunk and issues ONE bulk async copy (cp.async.bulk,
+//     SASS UBLKCP) of that leaf's particle run; completion is tracked by an mbarrier transaction
+//     count, so a warp never blocks on a load it issued itself;
+//   * SOURCES are spread over the lanes (NSRC per lane), TARGETS are walked by an unrolled loop with
+//     the target coordinates broadcast from shared memory and the per-target accumulators held in
+//     registers.  Lane utilisation is therefore independent of the leaf occupancy (a lane = target
+//     mapping idles 14-30 % of the lanes at the reference's leaf fill of 57-76 %),
+//     and the 32-lane reduction happens once per row, not once per tile;
+//   * when a source is loaded from the ring it is converted to FP32 RELATIVE to the row's first
+//     target (integer subtract, I2F, scale): all FP32 arithmetic is on short separations;
+//   * partial slices are carried across chunk boundaries in registers, so only the last slice of a
+//     row is ragged (padded with a dummy source whose contribution is exactly 0).
 // Pair arithmetic (2_Redundant/src/photoNs_CUDA.cu:432-450 with the eps branch of
-// 1_Indexing/src/photoNs_CUDA.cu:346-350 as an fmax on r^2):
-//     r2 = max(|dx|^2, eps^2); rinv = rsqrt(r2); f = rinv^3 * g(u),  u = r/(2 r_s)
+// 1_Indexing/src/photoNs_CUDA.cu:346-350 as an fmax on r^2), in units of 2 r_s so that u = r:
+//     r2 = max(|dx|^2, eps^2); rinv = rsqrt(r2); f = rinv^3 * g(u)
 //     g(u) = exp(-u^2) * Q(u),  Q = 1 + u^2 + q3 u^3 + ... + q10 u^10   (tools/fit_gfactor.py)
-// evaluated in units where positions are pre-scaled by a power of two s ~ 1/(2 r_s), so u = kappa*r'
-// with kappa in [0.71, 1.41] folded into the coefficients.  23 FP32-pipe instructions, 1 FMNMX and
-// 2 MUFU (RSQ, EX2) per pair; the packed variant issues the FP32 work as FFMA2/FMUL2/FADD2 on
-// target pairs.
+// = 23 FP32-pipe instructions, 1 FMNMX and 2 MUFU (RSQ, EX2) per pair.  The packed variant issues
+// the FP32 work as FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2, new on sm_100) on PAIRS OF TARGETS, which
+// halves the issue slots the FP32 pipe needs and leaves them to MUFU / FMNMX / LDS.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace p2p {
 
-constexpr int kStageParticles = 512;   // capacity of one staging buffer (float4 each -> 8 KB)
 constexpr int kStages = 2;
 constexpr int kPolyTerms = 9;          // R(v) = c[0] + c[1] v + ... + c[8] v^8
 
 struct KernelParams {
-    const float4* part;      // scaled positions + mass, local then ghost particles
+    const int4* part;        // fixed-point positions + mass bits, local then ghost particles
     const int2* leaf;        // {first particle, count}: local leaves then ghost leaves
     const long long* row_ptr;  // [nrow + 1]
     const int* col;          // source leaf ids, ascending within a row
     float4* acc;             // per local particle, accumulated into
     unsigned int* counter;   // dynamic row scheduler
     int nrow;
-    float eps2;              // (eps * s)^2
-    float nlog2e_k2;         // -log2(e) * kappa^2   (exp(-u^2) = ex2(nlog2e_k2 * r'^2)); 0 for plain
-    float c[kPolyTerms];     // kappa^(k+2) * q[k+2]
-    float out_scale;         // s^2 (and * mass when all masses are equal)
+    float k_fix;             // fixed-point step in kernel length units (box / 2^32 / unit)
+    float eps2;              // (eps / unit)^2
+    float nlog2e;            // -log2(e) for the truncated kernel (exp(-u^2) = ex2(nlog2e * r^2))
+    float c[kPolyTerms];     // q[k+2]
+    float out_scale;         // mass / unit^2
     float far_coord;         // coordinate offset that makes a dummy source contribute exactly 0
 };
 
@@ -91,93 +99,97 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- pair arithmetic ---------------------------------------------------------------------------
-template <bool TRUNC, bool PERMASS>
-__device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, float sy, float sz, float sm, float4 t,
-                                            float& ax, float& ay, float& az) {
-    // t holds the NEGATED target coordinates
-    float dx = sx + t.x, dy = sy + t.y, dz = sz + t.z;
+// t holds the NEGATED target coordinates.
+template <bool TRUNC>
+__device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, float sy, float sz, float tx, float ty,
+                                            float tz, float& ax, float& ay, float& az) {
+    const float dx = sx + tx, dy = sy + ty, dz = sz + tz;
     float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     r2 = fmaxf(r2, P.eps2);
-    float rinv = rsqrt_approx(r2);
-    float rinv2 = rinv * rinv;
+    const float rinv = rsqrt_approx(r2);
+    const float rinv2 = rinv * rinv;
     float f;
     if (TRUNC) {
-        float e = ex2_approx(r2 * P.nlog2e_k2);
-        float v = r2 * rinv;
+        const float e = ex2_approx(r2 * P.nlog2e);
+        const float v = r2 * rinv;
         float R = P.c[8];
 #pragma unroll
         for (int k = 7; k >= 0; k--) R = fmaf(R, v, P.c[k]);
-        float S = fmaf(v, R, rinv);          // rinv * Q(u)
+        const float S = fmaf(v, R, rinv);    // rinv * Q(u)
         f = (rinv2 * e) * S;
     } else {
         f = rinv2 * rinv;
     }
-    if (PERMASS) f *= sm;
     ax = fmaf(dx, f, ax);
     ay = fmaf(dy, f, ay);
     az = fmaf(dz, f, az);
 }
 
 // two targets at once with the sm_100a packed FP32 instructions (FFMA2 / FMUL2 / FADD2)
-template <bool TRUNC, bool PERMASS>
-__device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 sm,
-                                            float2 tx, float2 ty, float2 tz, float2& ax, float2& ay, float2& az) {
-    float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
+template <bool TRUNC>
+__device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty,
+                                            float2 tz, float2& ax, float2& ay, float2& az) {
+    const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
     float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
     r2.x = fmaxf(r2.x, P.eps2);
     r2.y = fmaxf(r2.y, P.eps2);
-    float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-    float2 rinv2 = __fmul2_rn(rinv, rinv);
+    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    const float2 rinv2 = __fmul2_rn(rinv, rinv);
     float2 f;
     if (TRUNC) {
-        float2 a = __fmul2_rn(r2, make_float2(P.nlog2e_k2, P.nlog2e_k2));
-        float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-        float2 v = __fmul2_rn(r2, rinv);
+        const float2 a = __fmul2_rn(r2, make_float2(P.nlog2e, P.nlog2e));
+        const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        const float2 v = __fmul2_rn(r2, rinv);
         float2 R = make_float2(P.c[8], P.c[8]);
 #pragma unroll
         for (int k = 7; k >= 0; k--) R = __ffma2_rn(R, v, make_float2(P.c[k], P.c[k]));
-        float2 S = __ffma2_rn(v, R, rinv);
+        const float2 S = __ffma2_rn(v, R, rinv);
         f = __fmul2_rn(__fmul2_rn(rinv2, e), S);
     } else {
         f = __fmul2_rn(rinv2, rinv);
     }
-    if (PERMASS) f = __fmul2_rn(f, sm);
     ax = __ffma2_rn(dx, f, ax);
     ay = __ffma2_rn(dy, f, ay);
     az = __ffma2_rn(dz, f, az);
 }
 
 // ---- per-warp shared state ---------------------------------------------------------------------
-template <int TT>
+struct alignas(16) TargetPair {     // negated, relative coordinates of targets (2p, 2p+1)
+    float4 xy;                      // {-x0, -x1, -y0, -y1}
+    float2 z;                       // {-z0, -z1}
+    float2 pad;
+};
+
+template <int TT, int STAGE>
 struct alignas(128) WarpSmem {
-    float4 stage[kStages][kStageParticles];
-    float4 tgt[TT];            // negated target coordinates (scalar variant)
-    float2 tgt2[3][TT / 2];    // packed variant: [x|y|z][pair] = {-t(2p), -t(2p+1)}
+    int4 stage[kStages][STAGE];
+    TargetPair tgt[TT / 2];
     float4 out[TT];
     uint64_t full[kStages];
 };
 
 // Issues the bulk copies of the next chunk of source leaves of the current row into `stage`.
 // Returns the number of particles that will land (warp-uniform) and advances e.
-__device__ __forceinline__ int issue_chunk(const KernelParams& P, float4* stage, uint64_t* bar, long long& e,
+template <int STAGE>
+__device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, uint64_t* bar, long long& e,
                                            long long e_end, int lane) {
     int cnt = 0, start = 0;
     if (e + lane < e_end) {
-        int s = __ldg(P.col + e + lane);
-        int2 ld = __ldg(P.leaf + s);
+        const int s = __ldg(P.col + e + lane);
+        const int2 ld = __ldg(P.leaf + s);
         start = ld.x;
         cnt = ld.y;
     }
     int incl = cnt;                                   // inclusive scan over the lanes
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
     }
-    long long remaining = e_end - e;
-    int nl = remaining < 32 ? (int)remaining : 32;
-    unsigned fit = __ballot_sync(0xffffffffu, lane < nl && incl <= kStageParticles);
-    int nfit = __popc(fit);                           // leaves are taken in order, so `fit` is a prefix mask
+    const long long remaining = e_end - e;
+    const int nl = remaining < 32 ? (int)remaining : 32;
+    const unsigned fit = __ballot_sync(0xffffffffu, lane < nl && incl <= STAGE);
+    const int nfit = __popc(fit);                     // leaves are taken in order, so `fit` is a prefix mask
     int total = __shfl_sync(0xffffffffu, incl, nfit > 0 ? nfit - 1 : 0);
     if (nfit == 0) total = 0;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 16u);
@@ -187,11 +199,15 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, float4* stage,
     return total;
 }
 
-template <int TT, bool TRUNC, bool PERMASS, bool PACKED>
-__global__ void __launch_bounds__(128) p2p_rows_kernel(const KernelParams P) {
+// TT     targets per pass (accumulators in registers); rows with more targets take several passes
+// NSRC   sources per lane per slice (1 or 2)
+// STAGE  particles per staging buffer
+template <int TT, int NSRC, int STAGE, bool TRUNC, bool PACKED, int MINB>
+__global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmem<TT>& S = reinterpret_cast<WarpSmem<TT>*>(smem_raw)[wid];
+    WarpSmem<TT, STAGE>& S = reinterpret_cast<WarpSmem<TT, STAGE>*>(smem_raw)[wid];
+    constexpr int SLICE = 32 * NSRC;
 
     if (lane == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&S.full[s], 1);
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(128) p2p_rows_kernel(const KernelParams P) {
     }
     fence_proxy_async();
     __syncwarp();
-    uint32_t phase[kStages] = {0, 0};
+    uint32_t phase0 = 0, phase1 = 0;
 
     for (;;) {
         int row = 0;
@@ -207,104 +223,136 @@ __global__ void __launch_bounds__(128) p2p_rows_kernel(const KernelParams P) {
         row = __shfl_sync(0xffffffffu, row, 0);
         if (row >= P.nrow) break;
         const int2 tl = __ldg(P.leaf + row);
-        const int nt = tl.y;
-        long long e = __ldg(P.row_ptr + row);
+        const int nt_all = tl.y;
+        const long long e_begin = __ldg(P.row_ptr + row);
         const long long e_end = __ldg(P.row_ptr + row + 1);
-        if (nt <= 0 || e >= e_end) continue;
+        if (nt_all <= 0 || e_begin >= e_end) continue;
+        // reference point of the row: its first target particle (fixed-point)
+        const int4 c4 = __ldg(P.part + tl.x);
 
-        // targets -> shared (negated); padding targets sit on the first target, results dropped
-        {
-            float4 t = __ldg(P.part + tl.x + (lane < nt ? lane : 0));
-            if (lane < TT) {
-                S.tgt[lane] = make_float4(-t.x, -t.y, -t.z, 0.f);
-                reinterpret_cast<float*>(&S.tgt2[0][0])[lane] = -t.x;
-                reinterpret_cast<float*>(&S.tgt2[1][0])[lane] = -t.y;
-                reinterpret_cast<float*>(&S.tgt2[2][0])[lane] = -t.z;
+        for (int t0 = 0; t0 < nt_all; t0 += TT) {
+            const int nt = min(TT, nt_all - t0);
+            // targets -> shared: negated, relative to c4; padding slots repeat the first target
+            {
+                const int4 t4 = __ldg(P.part + tl.x + t0 + (lane < nt ? lane : 0));
+                const float x = -(float)(t4.x - c4.x) * P.k_fix, y = -(float)(t4.y - c4.y) * P.k_fix,
+                            z = -(float)(t4.z - c4.z) * P.k_fix;
+                if (lane < TT) {
+                    float* base = reinterpret_cast<float*>(&S.tgt[lane >> 1]);
+                    base[0 + (lane & 1)] = x;
+                    base[2 + (lane & 1)] = y;
+                    base[4 + (lane & 1)] = z;
+                }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        float ax[TT], ay[TT], az[TT];
+            float ax[TT], ay[TT], az[TT];
 #pragma unroll
-        for (int j = 0; j < TT; j++) ax[j] = ay[j] = az[j] = 0.f;
+            for (int j = 0; j < TT; j++) ax[j] = ay[j] = az[j] = 0.f;
 
-        // a dummy source far enough that exp(-u^2) (or rinv^3 in the plain kernel) flushes to 0
-        const float4 t0 = S.tgt[0];
-        const float fx = P.far_coord - t0.x;
-        float sx = fx, sy = -t0.y, sz = -t0.z, sm = 0.f;
-        int have = 0;                                    // lanes [0, have) hold carried-over sources
-
-        int np[kStages];
-        int cur = 0;
-        fence_proxy_async();
-        np[0] = issue_chunk(P, S.stage[0], &S.full[0], e, e_end, lane);
-        bool more = e < e_end;
-
-        auto compute_slice = [&]() {
-            if (PACKED) {
-                const float2 sx2 = make_float2(sx, sx), sy2 = make_float2(sy, sy), sz2 = make_float2(sz, sz),
-                             sm2 = make_float2(sm, sm);
+            // per-lane sources of the current slice (relative FP32); dummy = far away along x
+            float sx[NSRC], sy[NSRC], sz[NSRC];
 #pragma unroll
-                for (int p = 0; p < TT / 2; p++) {
-                    if (2 * p < nt) {
+            for (int q = 0; q < NSRC; q++) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+            int have = 0;                                 // sources [0, have) of the slice are already in registers
+
+            auto load_source = [&](const int4* buf, int idx, int q) {
+                const int4 s4 = buf[idx];
+                sx[q] = (float)(s4.x - c4.x) * P.k_fix;
+                sy[q] = (float)(s4.y - c4.y) * P.k_fix;
+                sz[q] = (float)(s4.z - c4.z) * P.k_fix;
+            };
+
+            // One slice (SLICE sources, NSRC per lane) against the first 2*K targets of the pass.
+            // K is a compile-time constant so that the body is straight-line code: no per-target
+            // branches, constants stay in (uniform) registers and the scheduler can interleave the
+            // independent target-pair chains.
+            auto slice_body = [&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+#pragma unroll
+                for (int p = 0; p < K; p++) {
+                    const float4 txy = S.tgt[p].xy;
+                    const float2 tz = S.tgt[p].z;
+                    if (PACKED) {
                         float2 x2 = make_float2(ax[2 * p], ax[2 * p + 1]), y2 = make_float2(ay[2 * p], ay[2 * p + 1]),
                                z2 = make_float2(az[2 * p], az[2 * p + 1]);
-                        pair_packed<TRUNC, PERMASS>(P, sx2, sy2, sz2, sm2, S.tgt2[0][p], S.tgt2[1][p], S.tgt2[2][p], x2,
-                                                    y2, z2);
+#pragma unroll
+                        for (int q = 0; q < NSRC; q++)
+                            pair_packed<TRUNC>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
+                                               make_float2(txy.x, txy.y), make_float2(txy.z, txy.w), tz, x2, y2, z2);
                         ax[2 * p] = x2.x; ax[2 * p + 1] = x2.y;
                         ay[2 * p] = y2.x; ay[2 * p + 1] = y2.y;
                         az[2 * p] = z2.x; az[2 * p + 1] = z2.y;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NSRC; q++) {
+                            pair_scalar<TRUNC>(P, sx[q], sy[q], sz[q], txy.x, txy.z, tz.x, ax[2 * p], ay[2 * p], az[2 * p]);
+                            pair_scalar<TRUNC>(P, sx[q], sy[q], sz[q], txy.y, txy.w, tz.y, ax[2 * p + 1], ay[2 * p + 1], az[2 * p + 1]);
+                        }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < TT; j++) {
-                    if (j < nt) pair_scalar<TRUNC, PERMASS>(P, sx, sy, sz, sm, S.tgt[j], ax[j], ay[j], az[j]);
+            };
+            const int ntp = (nt + 1) >> 1;                     // target pairs of this pass (warp-uniform)
+            auto compute_slice = [&]() {
+                // one indirect branch per slice instead of a guard per target pair
+                switch (ntp) {
+#define P2P_CASE(k) case k: if constexpr (k <= TT / 2) slice_body(std::integral_constant<int, k>{}); break;
+                    P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
+                    P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
+#undef P2P_CASE
+                    default: break;
                 }
-            }
-        };
+            };
 
-        for (;;) {
-            const int nxt = cur ^ 1;
-            if (more) {
-                // the other stage was fully read (values are in registers) before this point
-                fence_proxy_async();
-                np[nxt] = issue_chunk(P, S.stage[nxt], &S.full[nxt], e, e_end, lane);
-            }
-            const bool had_more = more;
-            more = e < e_end;
-            mbar_wait(&S.full[cur], phase[cur]);
-            phase[cur] ^= 1u;
-            const float4* buf = S.stage[cur];
-            const int n = np[cur];
-            int pos = 0;
-            while (have + (n - pos) >= 32) {
-                if (lane >= have) {
-                    float4 s4 = buf[pos + lane - have];
-                    sx = s4.x; sy = s4.y; sz = s4.z; sm = s4.w;
+            long long e = e_begin;
+            int np0 = 0, np1 = 0, cur = 0;
+            fence_proxy_async();
+            np0 = issue_chunk<STAGE>(P, S.stage[0], &S.full[0], e, e_end, lane);
+            bool more = e < e_end;
+
+            for (;;) {                                            // chunks of the row
+                if (more) {
+                    // the other stage was fully consumed (its values are in registers) before this point
+                    fence_proxy_async();
+                    const int n = issue_chunk<STAGE>(P, S.stage[cur ^ 1], &S.full[cur ^ 1], e, e_end, lane);
+                    if (cur) np0 = n; else np1 = n;
                 }
-                pos += 32 - have;
-                have = 0;
-                compute_slice();
-            }
-            if (lane >= have && lane - have < n - pos) {
-                float4 s4 = buf[pos + lane - have];
-                sx = s4.x; sy = s4.y; sz = s4.z; sm = s4.w;
-            }
-            have += n - pos;
-            __syncwarp();
-            if (!had_more) break;
-            cur = nxt;
-        }
-        if (have > 0) {                                  // ragged tail of the row
-            if (lane >= have) { sx = fx; sy = -t0.y; sz = -t0.z; sm = 0.f; }
-            compute_slice();
-        }
-
-        // 32-lane reduction, once per row
+                const bool last_chunk = !more;
+                more = e < e_end;
+                if (cur) { mbar_wait(&S.full[1], phase1); phase1 ^= 1u; } else { mbar_wait(&S.full[0], phase0); phase0 ^= 1u; }
+                const int4* buf = S.stage[cur];
+                const int n = cur ? np1 : np0;
+                int pos = 0;
+                for (;;) {                                        // slices; ONE call site of the slice code
+                    const int avail = n - pos;
+                    const bool full = have + avail >= SLICE;
+                    const int take = full ? SLICE - have : avail;
 #pragma unroll
-        for (int j = 0; j < TT; j++) {
-            if (j < nt) {
+                    for (int q = 0; q < NSRC; q++) {
+                        const int k = q * 32 + lane - have;       // position of this lane's slot in the new run
+                        if (k >= 0 && k < take) load_source(buf, pos + k, q);
+                    }
+                    pos += take;
+                    have += take;
+                    bool run = full;
+                    if (!full && last_chunk && have > 0) {        // ragged tail of the row: pad with dummies
+#pragma unroll
+                        for (int q = 0; q < NSRC; q++) {
+                            if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+                        }
+                        run = true;
+                    }
+                    if (run) { compute_slice(); have = 0; }
+                    if (!full) break;
+                }
+                __syncwarp();
+                if (last_chunk) break;
+                cur ^= 1;
+            }
+
+            // 32-lane reduction, once per row pass
+#pragma unroll
+            for (int j = 0; j < TT; j++) {
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) {
                     ax[j] += __shfl_xor_sync(0xffffffffu, ax[j], d);
@@ -313,18 +361,18 @@ __global__ void __launch_bounds__(128) p2p_rows_kernel(const KernelParams P) {
                 }
                 if (lane == 0) S.out[j] = make_float4(ax[j], ay[j], az[j], 0.f);
             }
+            __syncwarp();
+            if (lane < nt) {
+                const float4 o = S.out[lane];
+                float4* dst = P.acc + tl.x + t0 + lane;
+                float4 a = *dst;
+                a.x = fmaf(o.x, P.out_scale, a.x);
+                a.y = fmaf(o.y, P.out_scale, a.y);
+                a.z = fmaf(o.z, P.out_scale, a.z);
+                *dst = a;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane < nt) {
-            float4 o = S.out[lane];
-            float4* dst = P.acc + tl.x + lane;
-            float4 a = *dst;
-            a.x = fmaf(o.x, P.out_scale, a.x);
-            a.y = fmaf(o.y, P.out_scale, a.y);
-            a.z = fmaf(o.z, P.out_scale, a.z);
-            *dst = a;
-        }
-        __syncwarp();
     }
 }
 

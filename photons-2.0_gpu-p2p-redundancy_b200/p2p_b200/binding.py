@@ -42,13 +42,14 @@ def load_library():
     L.p2p_last_error.restype = C.c_char_p
     L.p2p_device_particles.restype = C.c_void_p
     L.p2p_device_acc.restype = C.c_void_p
-    L.p2p_position_scale.restype = C.c_double
     L.p2p_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     for name in ("p2p_destroy", "p2p_clear_ghosts", "p2p_clear_tasks", "p2p_build_csr", "p2p_compute", "p2p_zero_acc",
                  "p2p_synchronize"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.p2p_set_physics.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
     L.p2p_set_kernel_variant.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_set_box.argtypes = [C.c_void_p, _dp, C.c_double]
+    L.p2p_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.p2p_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.p2p_upload_particles.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64]
     L.p2p_upload_leaves.argtypes = [C.c_void_p, _ip, _ip, C.c_int]
@@ -64,7 +65,6 @@ def load_library():
                                 C.c_int64, C.c_int]
     L.p2p_device_particles.argtypes = [C.c_void_p]
     L.p2p_device_acc.argtypes = [C.c_void_p]
-    L.p2p_position_scale.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -112,6 +112,14 @@ class P2PContext:
 
     def set_kernel_variant(self, v):
         self._chk(self._L.p2p_set_kernel_variant(self._h, int(v)))
+
+    def set_box(self, origin, extent):
+        o = _f64(origin)
+        assert o.shape == (3,)
+        self._chk(self._L.p2p_set_box(self._h, o.ctypes.data_as(_dp), float(extent)))
+
+    def set_tuning(self, targets_per_pass=0, sources_per_lane=0, min_blocks=0):
+        self._chk(self._L.p2p_set_tuning(self._h, int(targets_per_pass), int(sources_per_lane), int(min_blocks)))
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self._L.p2p_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
@@ -216,6 +224,3 @@ class P2PContext:
     def device_acc_ptr(self):
         return self._L.p2p_device_acc(self._h)
 
-    @property
-    def position_scale(self):
-        return self._L.p2p_position_scale(self._h)

@@ -69,7 +69,7 @@ def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, 
             out.gts = np.concatenate(gts).astype(np.int32)
     t3 = time.perf_counter()
     out.timings = dict(build_s=t1 - t0, walk_s=t2 - t1, images_s=t3 - t2)
-    out.params = dict(rs=rs, rcut=rcut, eps=eps)
+    out.params = dict(rs=rs, rcut=rcut, eps=eps, box=box)
     return out
 
 
@@ -84,6 +84,7 @@ class ShortRangeStep:
         T, c = lists.tree, self.ctx
         prm = lists.params
         c.set_physics(mass, prm["eps"], prm["rs"] if truncated else 0.0)
+        c.set_box([0.0, 0.0, 0.0], prm["box"])       # periodic frame: displaced ghosts wrap onto their originals
         c.upload_particles(T.pos)
         c.upload_leaves(T.leaf_npart, T.leaf_ipart)
         c.clear_tasks()

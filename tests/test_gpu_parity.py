@@ -1,0 +1,164 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the fp64 oracle.
+
+Tolerances: lists / CSR / pair counts bit-exact;
+  max_i |a_i - a_ref,i| <= 1e-5 * mean_j |a_ref,j|      and
+  max_i |a_i - a_ref,i| / sum_pairs |term|_i <= 1e-5
+with a_ref the fp64 oracle on the identical list."""
+import numpy as np
+import pytest
+from conftest import DEMO_BOX, DEMO_MASS, DEMO_NSIDE, THETA
+
+import flow
+import oracle
+import p2p_b200
+from p2p_b200 import host, step, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = p2p_b200.P2PContext(0)
+    yield c
+    c.close()
+
+
+def _errors(acc, ref, absref):
+    d = np.linalg.norm(acc - ref, axis=1)
+    return d.max() / np.linalg.norm(ref, axis=1).mean(), (d / np.maximum(np.linalg.norm(absref, axis=1), 1e-300)).max()
+
+
+def _run(ctx, T, tt, ts, mass, eps, rs, variant):
+    ctx.set_kernel_variant(variant)
+    ctx.set_physics(mass, eps, rs)
+    ctx.upload_particles(T.pos)
+    ctx.upload_leaves(T.leaf_npart[:T.nleaf], T.leaf_ipart[:T.nleaf])
+    ctx.clear_tasks()
+    ctx.append_tasks(tt, ts)
+    ctx.build_csr()
+    ctx.compute()
+    return ctx.download_acc()
+
+
+@pytest.mark.parametrize("maxleaf", [8, 16, 32])
+@pytest.mark.parametrize("truncated", [True, False])
+@pytest.mark.parametrize("variant", [p2p_b200.binding.KERNEL_SCALAR, p2p_b200.binding.KERNEL_PACKED])
+def test_demo_local_list(ctx, demo_pos, golden, maxleaf, truncated, variant):
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    rs = rs if truncated else 0.0
+    T = oracle.Tree(demo_pos, maxleaf, [0, 0, 0], [DEMO_BOX] * 3, 0)
+    tt, ts = T.walk_p2p(THETA, rcut)
+    acc = _run(ctx, T, tt, ts, DEMO_MASS, eps, rs, variant)
+    g = next(c for c in golden["cases"] if c["maxleaf"] == maxleaf and c["nproc"] == 1)["ranks"][0]
+    assert ctx.counts() == (g["local_tasks"], g["local_pairs"])                       # bit-exact counts
+    row, col = ctx.download_csr()
+    order = np.lexsort((ts, tt))
+    assert np.array_equal(col, ts[order])                                             # CSR == sorted list
+    assert np.array_equal(row, np.searchsorted(tt[order], np.arange(T.nleaf + 1)))
+    ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, DEMO_MASS, eps, rs)
+    absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, DEMO_MASS, eps, rs, absterms=True)
+    e1, e2 = _errors(acc, ref, absr)
+    assert e1 < TOL and e2 < TOL, (e1, e2)
+
+
+def test_demo_full_step_with_periodic_images(demo_pos):
+    """Product host code + ghosts + kernel == oracle's intended whole step (D6 fixed), original particle order."""
+    L = step.build_lists(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, periodic=True)
+    st = step.ShortRangeStep(0)
+    acc = st.run(L, DEMO_MASS, truncated=True)
+    ref, ntask, npairs = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, 1, True)
+    assert st.ctx.counts() == (ntask, npairs) == (381377 + 205240, 83354950 + 36821870)
+    absr, _, _ = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, 1, True, absterms=True)
+    e1, e2 = _errors(acc, ref, absr)
+    assert e1 < TOL and e2 < TOL, (e1, e2)
+
+
+def test_edge_cases(ctx):
+    """Empty leaves, single-particle leaves, coincident particles, pairs inside the softening length,
+    rows with one source, sources without targets' row (ragged everything)."""
+    rng = np.random.default_rng(2)
+    box = 64.0
+    pos = rng.uniform(0, box, (3000, 3))
+    pos[100:140] = pos[100]                     # 40 coincident particles
+    pos[200:260] = pos[200] + rng.normal(0, 1e-3, (60, 3))   # well inside eps
+    pos = pos.astype(np.float32).astype(np.float64)
+    eps, rs, mass = 0.05, 2.5, 3.0
+    for maxleaf in (1, 3, 8, 32):
+        T = oracle.Tree(pos, maxleaf, [0, 0, 0], [box] * 3, 0)
+        tt, ts = T.walk_p2p(THETA, 4.5 * rs)
+        keep = np.ones(len(tt), bool)
+        keep[rng.integers(0, len(tt), len(tt) // 3)] = False            # break the symmetry / make rows ragged
+        tt, ts = tt[keep], ts[keep]
+        for variant in (1, 2):
+            acc = _run(ctx, T, tt, ts, mass, eps, rs, variant)
+            ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs)
+            absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs, absterms=True)
+            assert ctx.counts() == (len(tt), npairs)
+            assert np.isfinite(acc).all()
+            _, e2 = _errors(acc, ref, absr)
+            assert e2 < TOL, (maxleaf, variant, e2)
+
+
+def test_empty_inputs(ctx):
+    ctx.set_physics(1.0, 0.1, 1.0)
+    ctx.upload_particles(np.zeros((0, 3)))
+    ctx.upload_leaves(np.zeros(0, np.int32), np.zeros(0, np.int32))
+    ctx.clear_tasks()
+    ctx.build_csr()
+    ctx.compute()
+    assert ctx.download_acc().shape == (0, 3) and ctx.counts() == (0, 0)
+    # particles but no tasks
+    ctx.upload_particles(np.ones((5, 3)))
+    ctx.upload_leaves(np.array([5], np.int32), np.array([0], np.int32))
+    ctx.clear_tasks()
+    ctx.build_csr()
+    ctx.compute()
+    assert np.array_equal(ctx.download_acc(), np.zeros((5, 3)))
+
+
+def test_argument_errors(ctx):
+    ctx.set_physics(1.0, 0.1, 1.0)
+    ctx.upload_particles(np.ones((10, 3)))
+    with pytest.raises(p2p_b200.P2PError) as e:
+        ctx.upload_leaves(np.array([11], np.int32), np.array([0], np.int32))     # leaf outside the particles
+    assert e.value.code == -2
+    ctx.upload_leaves(np.array([10], np.int32), np.array([0], np.int32))
+    ctx.clear_tasks()
+    with pytest.raises(p2p_b200.P2PError):
+        ctx.append_tasks(np.array([0], np.int32), np.array([3], np.int32))       # unknown source leaf
+    with pytest.raises(p2p_b200.P2PError) as e:
+        ctx.compute()                                                             # no CSR yet
+    assert e.value.code == -3
+
+
+def test_properties_at_scale():
+    """Size-independent properties at 128^3 (8.5e9 + 0.8e9 pairs): pair count equals the host-side
+    sum n_t*n_s, the closed symmetric local list obeys Newton's third law, results are
+    bit-reproducible run to run, scalar and packed kernels agree, and a sample of target leaves
+    matches the oracle."""
+    ns = 128
+    pos, box = synth.zeldovich_like(ns)
+    L = step.build_lists(pos, box, 32, ns, THETA, periodic=False)
+    T = L.tree
+    want_pairs = int((T.leaf_npart[L.tt].astype(np.int64) * T.leaf_npart[L.ts]).sum())
+    st = step.ShortRangeStep(0, variant=p2p_b200.binding.KERNEL_PACKED)
+    a1 = st.run(L, synth.DEMO_MASS, True)
+    assert st.ctx.counts() == (len(L.tt), want_pairs)
+    st.ctx.zero_acc(); st.compute()
+    a2 = st.download(L)
+    assert np.array_equal(a1, a2)                                                   # deterministic
+    st2 = step.ShortRangeStep(0, variant=p2p_b200.binding.KERNEL_SCALAR)
+    a3 = st2.run(L, synth.DEMO_MASS, True)
+    amean = np.linalg.norm(a1, axis=1).mean()
+    assert np.linalg.norm(a1 - a3, axis=1).max() / amean < TOL
+    assert np.abs(a1.sum(axis=0)).max() / np.abs(a1).sum(axis=0).max() < 1e-6       # sum m a = 0 (third law)
+    # oracle on a sample of rows
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(T.nleaf, 200, replace=False)).astype(np.int32)
+    m = np.isin(L.tt, rows)
+    ref, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, L.tt[m], L.ts[m],
+                        synth.DEMO_MASS, L.params["eps"], L.params["rs"])
+    sel = np.concatenate([np.arange(T.leaf_ipart[r], T.leaf_ipart[r] + T.leaf_npart[r]) for r in rows])
+    got = st.ctx.download_acc()[sel]
+    assert np.linalg.norm(got - ref[sel], axis=1).max() / np.linalg.norm(ref[sel], axis=1).mean() < TOL
