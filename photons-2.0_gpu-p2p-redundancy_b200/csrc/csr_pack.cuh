@@ -14,10 +14,17 @@
 
 namespace p2p {
 
-__global__ void csr_count_kernel(const int* __restrict__ tt, long long n, unsigned int* __restrict__ cnt) {
+// Counts tasks per target leaf.  Task ids are validated HERE (the host never walks the list): a task
+// outside [0,nrow) x [0,nsrc) raises *bad and is dropped by the scatter as well.
+__global__ void csr_count_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
+                                 unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) atomicAdd(cnt + tt[i], 1u);
+    for (; i < n; i += stride) {
+        const int t = tt[i], s = ts[i];
+        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) atomicAdd(cnt + t, 1u);
+        else atomicAdd(bad, 1u);
+    }
 }
 
 // three-phase exclusive scan of unsigned counts into 64-bit offsets
@@ -99,13 +106,15 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const unsigned int* __r
     if (i0 <= n - 1 && n - 1 < i0 + 8) row_ptr[n] = (long long)run;  // owner of the last item closes the array
 }
 
-__global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n,
+__global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
                                    unsigned long long* __restrict__ cursor, int* __restrict__ col) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        unsigned long long p = atomicAdd(cursor + tt[i], 1ull);
-        col[p] = ts[i];
+        const int t = tt[i], s = ts[i];
+        if ((unsigned)t >= (unsigned)nrow || (unsigned)s >= (unsigned)nsrc) continue;
+        unsigned long long p = atomicAdd(cursor + t, 1ull);
+        col[p] = s;
     }
 }
 

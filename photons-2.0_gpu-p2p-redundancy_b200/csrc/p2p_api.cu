@@ -93,6 +93,9 @@ struct p2p_ctx {
     unsigned long long* d_npairs = nullptr;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+    unsigned int* h_flags = nullptr;        // pinned copy of d_counter after build_csr
+    bool flags_pending = false;
+    DevBuf<double> acc64;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     float ms_compute = 0.f, ms_csr = 0.f;
     int last_blocks_per_sm = 0;
@@ -246,6 +249,7 @@ int p2p_create(p2p_ctx** out, int device) {
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_counter, 4 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_npairs, sizeof(unsigned long long)));
+    CU(cudaMallocHost(&c->h_flags, 4 * sizeof(unsigned int)));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreate(&c->ev2));
@@ -263,6 +267,8 @@ int p2p_destroy(p2p_ctx* c) {
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_npairs) cudaFree(c->d_npairs);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    c->acc64.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -404,21 +410,9 @@ int p2p_clear_tasks(p2p_ctx* c) {
     return 0;
 }
 
-static int check_tasks(p2p_ctx* c, const int* tt, const int* ts, long long n, int step, int off) {
-    const int nsrc = c->nleaf + c->nghostleaf;
-    for (long long i = 0; i < n; i++) {
-        int t = tt[i * step], s = ts[i * step] + off;
-        if (t < 0 || t >= c->nleaf || s < 0 || s >= nsrc)
-            return fail(P2P_ERR_ARG, "task %lld = (target %d, source %d) outside [0,%d) x [0,%d)", i, t, s, c->nleaf, nsrc);
-    }
-    return 0;
-}
-
 int p2p_append_tasks(p2p_ctx* c, const int* tt, const int* ts, int64_t n, int off) {
     USE(c);
     if (n < 0 || (n && (!tt || !ts))) return fail(P2P_ERR_ARG, "bad task arrays");
-    int r = check_tasks(c, tt, ts, n, 1, off);
-    if (r) return r;
     CU(c->tt.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
     CU(c->ts.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
     if (n) {
@@ -436,8 +430,6 @@ int p2p_append_tasks(p2p_ctx* c, const int* tt, const int* ts, int64_t n, int of
 int p2p_append_tasks_interleaved(p2p_ctx* c, const int* pairs, int64_t n, int off) {
     USE(c);
     if (n < 0 || (n && !pairs)) return fail(P2P_ERR_ARG, "bad task array");
-    int r = check_tasks(c, pairs, pairs + 1, n, 2, off);
-    if (r) return r;
     CU(c->tt.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
     CU(c->ts.reserve((size_t)(c->ntask + n) + 1, c->stream, (size_t)c->ntask));
     if (n) {
@@ -470,7 +462,8 @@ int p2p_build_csr(p2p_ctx* c) {
     } else {
         const int G = c->num_sm * 8;
         if (n) {
-            p2p::csr_count_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, n, c->cnt.p);
+            p2p::csr_count_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, nrow, c->nleaf + c->nghostleaf, c->cnt.p,
+                                                            c->d_counter + 2);
             CU(cudaGetLastError());
         }
         p2p::scan_tile_sums_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p);
@@ -478,16 +471,36 @@ int p2p_build_csr(p2p_ctx* c) {
         p2p::scan_apply_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p, c->row_ptr.p, c->cursor.p);
         CU(cudaGetLastError());
         if (n) {
-            p2p::csr_scatter_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, c->cursor.p, c->col.p);
+            p2p::csr_scatter_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, nrow, c->nleaf + c->nghostleaf, c->cursor.p,
+                                                              c->col.p);
             p2p::csr_sort_rows_kernel<<<G, 128, 0, c->stream>>>(c->row_ptr.p, nrow, c->col.p, c->d_counter + 1);
             p2p::pair_count_kernel<<<G, 256, 0, c->stream>>>(c->row_ptr.p, c->col.p, c->leaf.p, nrow, c->d_npairs);
             CU(cudaGetLastError());
         }
     }
+    if (nrow == 0 && n > 0) {
+        // no rows at all: every task is out of range
+        CU(cudaMemsetAsync(c->d_counter + 2, 0xff, sizeof(unsigned int), c->stream));
+    }
+    CU(cudaMemcpyAsync(c->h_flags, c->d_counter, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev3, c->stream));
     c->timed_csr = true;
     c->csr_valid = true;
+    c->flags_pending = true;
     c->npairs = -1;
+    return 0;
+}
+
+// The list is validated on the device while it is counted; the verdict is read at the next point
+// that synchronises anyway (download / counts / synchronize).
+static int check_flags(p2p_ctx* c) {
+    if (!c->flags_pending) return 0;
+    c->flags_pending = false;
+    if (c->h_flags[2] != 0) {
+        c->csr_valid = false;
+        return fail(P2P_ERR_ARG, "%u task(s) reference leaves outside [0,%d) x [0,%d)", c->h_flags[2], c->nleaf,
+                    c->nleaf + c->nghostleaf);
+    }
     return 0;
 }
 
@@ -517,9 +530,10 @@ int p2p_compute(p2p_ctx* c) {
     int r = 0;
     if (c->nleaf > 0 && c->ntask > 0) {
         const bool packed = c->variant != P2P_KERNEL_SCALAR;
-        int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : (c->max_target_leaf <= 16 ? 16 : 32));
-        int nsrc = c->tune_nsrc ? c->tune_nsrc : 1;
-        int minb = c->tune_minb ? c->tune_minb : 3;
+        // defaults from the 128^3 sweeps (profiles/): 16 targets per pass, 2 sources per lane, 4 blocks / SM
+        int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
+        int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
+        int minb = c->tune_minb ? c->tune_minb : 4;
         if (trunc) r = packed ? launch_cfg<true, true>(c, P, tt, nsrc, minb) : launch_cfg<true, false>(c, P, tt, nsrc, minb);
         else r = packed ? launch_cfg<false, true>(c, P, tt, nsrc, minb) : launch_cfg<false, false>(c, P, tt, nsrc, minb);
     }
@@ -538,19 +552,30 @@ int p2p_zero_acc(p2p_ctx* c) {
 int p2p_synchronize(p2p_ctx* c) {
     USE(c);
     CU(cudaStreamSynchronize(c->stream));
-    return 0;
+    return check_flags(c);
 }
 
 int p2p_download_acc(p2p_ctx* c, double* acc, int64_t stride, int accumulate) {
     USE(c);
     if ((c->npart && !acc) || stride < 3) return fail(P2P_ERR_ARG, "bad acc array");
     const long long n = c->npart;
-    if (n == 0) return 0;
+    if (n == 0) { CU(cudaStreamSynchronize(c->stream)); return check_flags(c); }
+    if (stride == 3 && !accumulate) {
+        // packed destination: convert on the device and copy straight into the caller's buffer
+        // (full PCIe rate when that buffer is pinned)
+        CU(c->acc64.reserve((size_t)n * 3, c->stream));
+        p2p::acc_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->acc.p, n, c->acc64.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(acc, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return check_flags(c);
+    }
     void* hp;
     int r = pinned(c, (size_t)n * sizeof(float4), &hp);
     if (r) return r;
     CU(cudaMemcpyAsync(hp, c->acc.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if ((r = check_flags(c))) return r;
     const float4* a = reinterpret_cast<const float4*>(hp);
     if (accumulate) {
         for (long long i = 0; i < n; i++) { double* d = acc + i * stride; d[0] += a[i].x; d[1] += a[i].y; d[2] += a[i].z; }
@@ -569,6 +594,8 @@ int p2p_counts(p2p_ctx* c, int64_t* ntask, int64_t* npairs) {
             unsigned long long v = 0;
             CU(cudaMemcpyAsync(&v, c->d_npairs, sizeof v, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
+            int r = check_flags(c);
+            if (r) return r;
             c->npairs = (long long)v;
         }
         *npairs = c->npairs;

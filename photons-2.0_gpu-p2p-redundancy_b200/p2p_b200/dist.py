@@ -1,0 +1,150 @@
+"""Multi-rank short-range step: spatial domain decomposition + halo exchange over torch.distributed.
+
+One process per GPU (torchrun); the backend is NCCL over NVLink on the GPU box and gloo in the CPU
+tests.  Mirrors the reference flow (1_Indexing/src/domains.c:386-396, 1_Indexing/src/fmm.c:1026-1145,
+1_Indexing/src/remotes.c:740-809) with ONE grouped exchange per step instead of 27 x P blocking
+ring rounds: every rank prunes its tree against every peer's domain box for all 27 periodic
+displacements, the pruned images (nodes + leaf bodies) travel in three all-to-all-v calls, and the
+receiver walks its tree against each image.  No data-path collective is needed afterwards: every
+target particle has exactly one owner."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import host
+from .step import HostLists
+
+ALL_SHIFTS = [(0, 0, 0)] + [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) if (i, j, k) != (0, 0, 0)]
+"""zero displacement first, then the 26 images in the order of 1_Indexing/src/fmm.c:1084-1106"""
+
+
+def _dev(group):
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def _a2a_counts(send_counts, group):
+    """send_counts: int64 array [P, k] -> recv [P, k] (row p = what rank p sends to me)."""
+    d = _dev(group)
+    s = torch.from_numpy(np.ascontiguousarray(send_counts, np.int64)).to(d)
+    r = torch.empty_like(s)
+    dist.all_to_all_single(r, s, group=group)
+    return r.cpu().numpy()
+
+
+def _a2a_v(chunks, recv_rows, width, dtype, group):
+    """chunks[p]: array [n_p, width] for rank p; recv_rows[p] rows expected from rank p.
+    Returns the list of received arrays."""
+    d = _dev(group)
+    tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
+    send = np.concatenate([np.ascontiguousarray(c, dtype).reshape(-1, width) for c in chunks]) if chunks else np.zeros((0, width), dtype)
+    s = torch.from_numpy(send).to(d).reshape(-1)
+    in_split = [int(np.asarray(c).reshape(-1, width).shape[0]) * width for c in chunks]
+    out_split = [int(n) * width for n in recv_rows]
+    r = torch.empty(int(sum(out_split)), dtype=tdt, device=d)
+    dist.all_to_all_single(r, s, out_split, in_split, group=group)
+    r = r.cpu().numpy()
+    out, o = [], 0
+    for n in out_split:
+        out.append(r[o:o + n].reshape(-1, width))
+        o += n
+    return out
+
+
+def decompose(pos, box, group=None):
+    """Initial routing as the reference does it (1_Indexing/src/domains.c:298-377): rank r starts from
+    the slab [N r/P, N (r+1)/P) of the input order, partitions it in place by the equal-volume rank
+    kd-tree and ships the blocks; blocks are concatenated in source-rank order.
+    Returns (local positions, original indices, toptree centre/width, direct_of_node, domain id)."""
+    P, r = dist.get_world_size(group), dist.get_rank(group)
+    n = pos.shape[0]
+    split, center, width, direct = host.domain_setup(P, box)
+    lo, hi = n * r // P, n * (r + 1) // P
+    p = np.array(pos[lo:hi], np.float64, order="C", copy=True)
+    idx = np.arange(lo, hi, dtype=np.int64)
+    if P == 1:
+        return p, idx, center, width, direct, 0
+    send = host.domain_route(P, split, p, idx)
+    off = np.concatenate([[0], np.cumsum(send)])
+    rc = _a2a_counts(send.reshape(P, 1), group)[:, 0]
+    pr = _a2a_v([p[off[d]:off[d + 1]] for d in range(P)], rc, 3, np.float64, group)
+    ir = _a2a_v([idx[off[d]:off[d + 1]].reshape(-1, 1) for d in range(P)], rc, 1, np.int64, group)
+    return np.concatenate(pr), np.concatenate(ir)[:, 0], center, width, direct, host.domain_of_rank(P, r)
+
+
+def build_lists(pos, box, maxleaf, nside, theta=0.4, nthreads=0, group=None, literal_d6=False):
+    """Per-rank HostLists (local list + ghost leaves/tasks from every peer and periodic image).
+    `pos` is the GLOBAL particle array (identical on all ranks; only this rank's slab is read).
+    literal_d6=True also replays the reference's zero-shift self exchange (SURVEY defect D6)."""
+    P, me = dist.get_world_size(group), dist.get_rank(group)
+    rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
+    lp, lidx, tcenter, twidth, direct, dom = decompose(pos, box, group)
+    c, w = tcenter[dom], twidth[dom]
+    T = host.LocalTree(lp, maxleaf, c - 0.5 * w, c + 0.5 * w, int(direct[dom]), nthreads)
+    out = HostLists()
+    out.tree = T
+    out.orig_index = lidx[T.perm]
+    out.tt, out.ts = T.walk_task_p2p(theta, rcut, nthreads)
+    out.params = dict(rs=rs, rcut=rcut, eps=eps, box=box)
+    # every domain's box is its local root box (connect_local_toptree, 1_Indexing/src/toptree.c:18-45)
+    mine = np.concatenate([T.node_center[0], T.node_width[0]]) if T.nnode else np.concatenate([c, w])
+    d = _dev(group)
+    boxes = [torch.empty(6, dtype=torch.float64, device=d) for _ in range(P)]
+    dist.all_gather(boxes, torch.from_numpy(mine).to(d), group=group)
+    boxes = [b.cpu().numpy() for b in boxes]
+    # prune my tree for every (peer, displacement); the peer with ring index n receives what
+    # fmm_remote(n, shift) would have sent it (1_Indexing/src/remotes.c:746-774)
+    S = len(ALL_SHIFTS)
+    counts = np.zeros((P, S * 2), np.int64)
+    ni, nd, nb = [[] for _ in range(P)], [[] for _ in range(P)], [[] for _ in range(P)]
+    for p in range(P):
+        for si, sh in enumerate(ALL_SHIFTS):
+            if si == 0 and p == me and not literal_d6:
+                continue
+            img = T.prepare_sendtree(boxes[p][:3], boxes[p][3:], np.array(sh, np.float64) * box, theta, rcut)
+            counts[p, 2 * si], counts[p, 2 * si + 1] = len(img.npart), len(img.body)
+            ni[p].append(np.concatenate([img.npart.reshape(-1, 1), img.son], axis=1))
+            nd[p].append(np.concatenate([img.center, img.width], axis=1))
+            nb[p].append(img.body)
+    cat = lambda lst, wdt, dt: [np.concatenate(x) if x else np.zeros((0, wdt), dt) for x in lst]
+    rcounts = _a2a_counts(counts, group)
+    rn = rcounts[:, 0::2].sum(axis=1)
+    rb = rcounts[:, 1::2].sum(axis=1)
+    gi = _a2a_v(cat(ni, 3, np.int32), rn, 3, np.int32, group)
+    gd = _a2a_v(cat(nd, 6, np.float64), rn, 6, np.float64, group)
+    gb = _a2a_v(cat(nb, 3, np.float64), rb, 3, np.float64, group)
+    # walk my tree against every received image, in the reference's call order (shift-major, ring index)
+    gp, gs, gc, gtt, gts = [], [], [], [], []
+    nbody = nleaf = 0
+    out.remote_calls = []
+    for si in range(S):
+        for n in range(P):
+            src = (me - n + P) % P
+            if si == 0 and src == me and not literal_d6:
+                continue
+            o_n = int(rcounts[src, 0:2 * si:2].sum())
+            o_b = int(rcounts[src, 1:2 * si:2].sum())
+            k_n, k_b = int(rcounts[src, 2 * si]), int(rcounts[src, 2 * si + 1])
+            I = gi[src][o_n:o_n + k_n]
+            D = gd[src][o_n:o_n + k_n]
+            img = host.Image(I[:, 0], I[:, 1:3], D[:, :3], D[:, 3:], gb[src][o_b:o_b + k_b])
+            tt, ts = T.walk_task_p2p_ext(img, theta, rcut, nthreads)
+            out.remote_calls.append((si, src, len(tt)))
+            if len(tt) == 0:
+                continue
+            used, inv = np.unique(ts, return_inverse=True)
+            cnt, st = img.npart[used], img.son[used, 0]
+            sel = np.concatenate([np.arange(s, s + k) for s, k in zip(st, cnt)]) if len(used) else np.zeros(0, np.int64)
+            gp.append(img.body[sel])
+            gs.append(nbody + np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32))
+            gc.append(cnt.astype(np.int32))
+            gtt.append(tt)
+            gts.append((nleaf + inv).astype(np.int32))
+            nbody += int(cnt.sum())
+            nleaf += len(used)
+    if gp:
+        out.ghost_pos = np.concatenate(gp)
+        out.ghost_start = np.concatenate(gs).astype(np.int32)
+        out.ghost_count = np.concatenate(gc).astype(np.int32)
+        out.gtt = np.concatenate(gtt).astype(np.int32)
+        out.gts = np.concatenate(gts).astype(np.int32)
+    return out

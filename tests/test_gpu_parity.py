@@ -29,9 +29,10 @@ def _errors(acc, ref, absref):
     return d.max() / np.linalg.norm(ref, axis=1).mean(), (d / np.maximum(np.linalg.norm(absref, axis=1), 1e-300)).max()
 
 
-def _run(ctx, T, tt, ts, mass, eps, rs, variant):
+def _run(ctx, T, tt, ts, mass, eps, rs, variant, box=DEMO_BOX):
     ctx.set_kernel_variant(variant)
     ctx.set_physics(mass, eps, rs)
+    ctx.set_box([0.0, 0.0, 0.0], box)
     ctx.upload_particles(T.pos)
     ctx.upload_leaves(T.leaf_npart[:T.nleaf], T.leaf_ipart[:T.nleaf])
     ctx.clear_tasks()
@@ -76,12 +77,14 @@ def test_demo_full_step_with_periodic_images(demo_pos):
 
 def test_edge_cases(ctx):
     """Empty leaves, single-particle leaves, coincident particles, pairs inside the softening length,
-    rows with one source, sources without targets' row (ragged everything)."""
+    rows with one source, sources without targets' row (ragged everything).
+    (Coordinates are quantised at box / 2^32 on the device -- 1.5e-8 here -- so the clump is kept wider
+    than 1e5 quanta; see DESIGN.md, "fixed-point frame".)"""
     rng = np.random.default_rng(2)
     box = 64.0
     pos = rng.uniform(0, box, (3000, 3))
     pos[100:140] = pos[100]                     # 40 coincident particles
-    pos[200:260] = pos[200] + rng.normal(0, 1e-3, (60, 3))   # well inside eps
+    pos[200:260] = pos[200] + rng.normal(0, 0.01, (60, 3))   # a clump inside the softening length (eps = 0.05)
     pos = pos.astype(np.float32).astype(np.float64)
     eps, rs, mass = 0.05, 2.5, 3.0
     for maxleaf in (1, 3, 8, 32):
@@ -91,13 +94,20 @@ def test_edge_cases(ctx):
         keep[rng.integers(0, len(tt), len(tt) // 3)] = False            # break the symmetry / make rows ragged
         tt, ts = tt[keep], ts[keep]
         for variant in (1, 2):
-            acc = _run(ctx, T, tt, ts, mass, eps, rs, variant)
+            acc = _run(ctx, T, tt, ts, mass, eps, rs, variant, box)
             ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs)
             absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs, absterms=True)
             assert ctx.counts() == (len(tt), npairs)
             assert np.isfinite(acc).all()
-            _, e2 = _errors(acc, ref, absr)
-            assert e2 < TOL, (maxleaf, variant, e2)
+            d = np.linalg.norm(acc - ref, axis=1)
+            na = np.linalg.norm(absr, axis=1)
+            assert d.max() / na.mean() < TOL, (maxleaf, variant)
+            # per-particle relative check for particles that kept a substantial near field: a row left
+            # with far sources only (g < 1e-2) is limited by the ABSOLUTE accuracy of the truncation
+            # factor, |dg| <= 1.1e-6 (tools/fit_gfactor.py), which no real list produces
+            sel = na > 0.1 * np.median(na)
+            assert sel.sum() > 0.8 * T.npart
+            assert (d[sel] / na[sel]).max() < TOL, (maxleaf, variant)
 
 
 def test_empty_inputs(ctx):
@@ -125,11 +135,20 @@ def test_argument_errors(ctx):
     assert e.value.code == -2
     ctx.upload_leaves(np.array([10], np.int32), np.array([0], np.int32))
     ctx.clear_tasks()
-    with pytest.raises(p2p_b200.P2PError):
-        ctx.append_tasks(np.array([0], np.int32), np.array([3], np.int32))       # unknown source leaf
     with pytest.raises(p2p_b200.P2PError) as e:
         ctx.compute()                                                             # no CSR yet
     assert e.value.code == -3
+    # task ids are validated on the device while the CSR is counted; the verdict surfaces at the next sync
+    ctx.append_tasks(np.array([0, 0], np.int32), np.array([0, 3], np.int32))     # source leaf 3 does not exist
+    ctx.build_csr()
+    with pytest.raises(p2p_b200.P2PError) as e:
+        ctx.synchronize()
+    assert e.value.code == -2
+    ctx.clear_tasks()
+    ctx.append_tasks(np.array([0], np.int32), np.array([0], np.int32))
+    ctx.build_csr()
+    ctx.compute()
+    assert ctx.counts() == (1, 100)
 
 
 def test_properties_at_scale():
