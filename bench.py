@@ -126,11 +126,12 @@ def run_reference_arm(args):
         return
     from p2p_b200 import step
     pos, box, mass = make_workload(args.nside, args.clustered)
-    L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True)
+    L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=os.cpu_count() or 1)
     rates, tot_pairs, tot_dt = [], 0, 0.0
-    per_step_pairs = args.cpu_pairs
+    # one step = a bounded sample (default 5e9 pairs ~ 9 s on 16 cores) so that W + K steps end within minutes
+    per_step_pairs = min(args.cpu_pairs, 5e9)
     for i in range(args.warmup + args.steps):
-        rate, npairs, nrow, dt, threads = cpu_oracle_rate(L, mass, per_step_pairs, 0)
+        rate, npairs, nrow, dt, threads = cpu_oracle_rate(L, mass, per_step_pairs, os.cpu_count() or 1)
         if i >= args.warmup:
             rates.append(rate); tot_pairs += npairs; tot_dt += dt
     value = tot_pairs / tot_dt
@@ -192,10 +193,12 @@ def main():
     pos, box, mass = make_workload(args.nside, args.clustered)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
+    # torchrun exports OMP_NUM_THREADS=1; the host producers take an explicit thread count instead
+    nthreads = max(1, (os.cpu_count() or 1) // world)
     if distributed:
-        L = pdist.build_lists(pos, box, args.maxleaf, args.nside, THETA)
+        L = pdist.build_lists(pos, box, args.maxleaf, args.nside, THETA, nthreads=nthreads)
     else:
-        L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True)
+        L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=nthreads)
     t_lists = time.perf_counter() - t0
     del pos
     T = L.tree
@@ -320,7 +323,7 @@ def main():
             "clocks": sampler.result(),
         }
         if not args.no_cpu_baseline and not distributed:
-            rate, npr, nrow, dt, threads = cpu_oracle_rate(L, mass, args.cpu_pairs, 0)
+            rate, npr, nrow, dt, threads = cpu_oracle_rate(L, mass, args.cpu_pairs, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": rate, "unit": "pair/s", "cores": threads, "kind": "port",
                                    "sample": f"first {nrow} of {T.nleaf} target leaves (complete CSR rows) = {npr} pairs in {dt:.1f} s, "
                                              "fp64 oracle (erfc/exp), OpenMP dynamic over target leaves"}
