@@ -72,8 +72,8 @@ int p2p_set_kernel_variant(p2p_ctx* ctx, int variant);
  * the lists imply must stay below extent / 2 per axis).  Must precede p2p_upload_particles.
  * If never called, the box is derived from the uploaded particles (bounding cube, doubled). */
 int p2p_set_box(p2p_ctx* ctx, const double origin[3], double extent);
-/* kernel tuning knobs for the ncu sweeps: targets per pass (8/16/32), sources per lane (1/2),
- * min resident blocks per SM (2..4); 0 keeps the default of that knob */
+/* kernel tuning knobs for the ncu sweeps: targets per pass (8/16), sources per lane (1/2/4), min
+ * resident blocks per SM (3/4; +16 selects the even/odd split polynomial); 0 keeps the default */
 int p2p_set_tuning(p2p_ctx* ctx, int targets_per_pass, int sources_per_lane, int min_blocks);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
 int p2p_set_stream(p2p_ctx* ctx, void* cuda_stream);

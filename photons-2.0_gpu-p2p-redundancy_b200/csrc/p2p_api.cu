@@ -77,7 +77,7 @@ struct p2p_ctx {
     double origin[3] = {0, 0, 0}, extent = 0.0;   // fixed-point frame; extent 0: derive from the particles
     bool box_set = false;
     int variant = P2P_KERNEL_AUTO;
-    int tune_tt = 0, tune_nsrc = 0, tune_minb = 0;
+    int tune_tt = 0, tune_nsrc = 0, tune_minb = 0, tune_poly = 0;
     long long npart = 0, nghost = 0, ntask = 0, npairs = -1;
     int nleaf = 0, nghostleaf = 0, max_target_leaf = 0;
     bool csr_valid = false;
@@ -179,9 +179,9 @@ int upload_ints(p2p_ctx* c, const int* a, const int* b, long long n, int** da, i
 
 constexpr int kStage = 384;   // particles per staging buffer: 2 x 6 KB + targets per warp -> 16 warps / SM fit
 
-template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB>
+template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB, int POLY>
 int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
-    auto kern = p2p::p2p_rows_kernel<TT, NSRC, kStage, TRUNC, PACKED, MINB>;
+    auto kern = p2p::p2p_rows_kernel<TT, NSRC, kStage, TRUNC, PACKED, MINB, POLY>;
     const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT, kStage>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
@@ -195,22 +195,22 @@ int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
     return 0;
 }
 
-template <int TT, int NSRC, bool TRUNC, bool PACKED>
-int launch_minb(p2p_ctx* c, const p2p::KernelParams& P, int minb) {
-    if constexpr (!TRUNC) {
-        return launch_rows<TT, 1, false, PACKED, 3>(c, P);   // plain kernel: one tuning only
+// Instantiated tunings.  Production default: TT 16 (8 for leaves <= 8), 2 sources per lane, 4 blocks / SM.
+// The sweep set (tools/sweep.py) adds 1 / 4 sources per lane, 3 blocks / SM and the split polynomial
+// for the truncated packed kernel only, to keep the build time bounded.
+template <int TT, bool TRUNC, bool PACKED>
+int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb, int poly) {
+    if constexpr (TRUNC && PACKED) {
+        if (poly == 1) {
+            if (nsrc == 4) return minb == 3 ? launch_rows<TT, 4, true, true, 3, 1>(c, P) : launch_rows<TT, 4, true, true, 4, 1>(c, P);
+            return minb == 3 ? launch_rows<TT, 2, true, true, 3, 1>(c, P) : launch_rows<TT, 2, true, true, 4, 1>(c, P);
+        }
+        if (nsrc == 1) return minb == 3 ? launch_rows<TT, 1, true, true, 3, 0>(c, P) : launch_rows<TT, 1, true, true, 4, 0>(c, P);
+        if (nsrc == 4) return minb == 3 ? launch_rows<TT, 4, true, true, 3, 0>(c, P) : launch_rows<TT, 4, true, true, 4, 0>(c, P);
+        return minb == 3 ? launch_rows<TT, 2, true, true, 3, 0>(c, P) : launch_rows<TT, 2, true, true, 4, 0>(c, P);
     } else {
-        if (minb == 2) return launch_rows<TT, NSRC, TRUNC, PACKED, 2>(c, P);
-        if (minb == 4) return launch_rows<TT, NSRC, TRUNC, PACKED, 4>(c, P);
-        return launch_rows<TT, NSRC, TRUNC, PACKED, 3>(c, P);
+        return launch_rows<TT, 2, TRUNC, PACKED, 4, 0>(c, P);
     }
-}
-
-template <bool TRUNC, bool PACKED>
-int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P, int tt, int nsrc, int minb) {
-    if (tt == 8) return nsrc == 2 ? launch_minb<8, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<8, 1, TRUNC, PACKED>(c, P, minb);
-    if (tt == 16) return nsrc == 2 ? launch_minb<16, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<16, 1, TRUNC, PACKED>(c, P, minb);
-    return nsrc == 2 ? launch_minb<32, 2, TRUNC, PACKED>(c, P, minb) : launch_minb<32, 1, TRUNC, PACKED>(c, P, minb);
 }
 
 }  // namespace
@@ -291,9 +291,12 @@ int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
 }
 
 int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
-    if (!c || (tt && tt != 8 && tt != 16 && tt != 32) || nsrc < 0 || nsrc > 2 || minb < 0 || minb == 1 || minb > 4)
-        return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16/32, sources_per_lane 1/2, min_blocks 2..4)");
-    c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb;
+    // min_blocks: 3 or 4; adding 16 selects the even/odd split polynomial (sweeps only)
+    const int poly = minb >= 16 ? 1 : 0;
+    if (poly) minb -= 16;
+    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4))
+        return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16, sources_per_lane 1/2/4, min_blocks 3/4)");
+    c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb; c->tune_poly = poly;
     return 0;
 }
 
@@ -513,14 +516,16 @@ int p2p_compute(p2p_ctx* c) {
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.acc = c->acc.p;
     P.counter = c->d_counter; P.nrow = c->nleaf;
     const bool trunc = c->rs > 0.0;
-    // kernel length unit: 2 r_s (so that u = r) for the truncated kernel, the box extent otherwise
-    const double unit = trunc ? 2.0 * c->rs : (c->extent > 0.0 ? c->extent : 1.0);
+    // kernel length unit: 2 r_s / sqrt(log2 e) for the truncated kernel (then exp(-u^2) = 2^(-r'^2) and the
+    // polynomial argument is r' = u sqrt(log2 e)), the box extent otherwise
+    const double sl2e = sqrt(1.4426950408889634);
+    const double unit = trunc ? 2.0 * c->rs / sl2e : (c->extent > 0.0 ? c->extent : 1.0);
     P.k_fix = (float)(c->extent / 4294967296.0 / unit);
     P.eps2 = (float)((c->eps / unit) * (c->eps / unit));
     if (trunc) {
-        P.nlog2e = -1.4426950408889634f;
-        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)P2P_GCOEF_10[j + 2];
-        P.far_coord = 24.0f;
+        // rinv' Q(u) = rinv' + v (c0 + c1 v + ...), v = r' : c_j = q_{j+2} / sl2e^(j+2)
+        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] / pow(sl2e, j + 2));
+        P.far_coord = 24.0f * (float)sl2e;
     } else {
         P.far_coord = 1.0e18f;
     }
@@ -534,8 +539,14 @@ int p2p_compute(p2p_ctx* c) {
         int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
         int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
         int minb = c->tune_minb ? c->tune_minb : 4;
-        if (trunc) r = packed ? launch_cfg<true, true>(c, P, tt, nsrc, minb) : launch_cfg<true, false>(c, P, tt, nsrc, minb);
-        else r = packed ? launch_cfg<false, true>(c, P, tt, nsrc, minb) : launch_cfg<false, false>(c, P, tt, nsrc, minb);
+        const int poly = c->tune_minb ? c->tune_poly : 1;      // default: even/odd split polynomial
+        if (tt == 8) {
+            if (trunc) r = packed ? launch_cfg<8, true, true>(c, P, nsrc, minb, poly) : launch_cfg<8, true, false>(c, P, nsrc, minb, poly);
+            else r = packed ? launch_cfg<8, false, true>(c, P, nsrc, minb, poly) : launch_cfg<8, false, false>(c, P, nsrc, minb, poly);
+        } else {
+            if (trunc) r = packed ? launch_cfg<16, true, true>(c, P, nsrc, minb, poly) : launch_cfg<16, true, false>(c, P, nsrc, minb, poly);
+            else r = packed ? launch_cfg<16, false, true>(c, P, nsrc, minb, poly) : launch_cfg<16, false, false>(c, P, nsrc, minb, poly);
+        }
     }
     if (r) return r;
     CU(cudaEventRecord(c->ev1, c->stream));

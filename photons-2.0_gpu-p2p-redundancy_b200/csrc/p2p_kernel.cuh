@@ -25,7 +25,8 @@
 //   * partial slices are carried across chunk boundaries in registers, so only the last slice of a
 //     row is ragged (padded with a dummy source whose contribution is exactly 0).
 // Pair arithmetic (2_Redundant/src/photoNs_CUDA.cu:432-450 with the eps branch of
-// 1_Indexing/src/photoNs_CUDA.cu:346-350 as an fmax on r^2), in units of 2 r_s so that u = r:
+// 1_Indexing/src/photoNs_CUDA.cu:346-350 as an fmax on r^2), in units of 2 r_s / sqrt(log2 e) so that
+// exp(-u^2) = 2^(-r^2):
 //     r2 = max(|dx|^2, eps^2); rinv = rsqrt(r2); f = rinv^3 * g(u)
 //     g(u) = exp(-u^2) * Q(u),  Q = 1 + u^2 + q3 u^3 + ... + q10 u^10   (tools/fit_gfactor.py)
 // = 23 FP32-pipe instructions, 1 FMNMX and 2 MUFU (RSQ, EX2) per pair.  The packed variant issues
@@ -52,22 +53,15 @@ struct KernelParams {
     int nrow;
     float k_fix;             // fixed-point step in kernel length units (box / 2^32 / unit)
     float eps2;              // (eps / unit)^2
-    float nlog2e;            // -log2(e) for the truncated kernel (exp(-u^2) = ex2(nlog2e * r^2))
-    float c[kPolyTerms];     // q[k+2]
+    float c[kPolyTerms];     // q[k+2] / log2(e)^((k+2)/2): coefficients in the kernel's length unit
     float out_scale;         // mass / unit^2
     float far_coord;         // coordinate offset that makes a dummy source contribute exactly 0
 };
 
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
+// MUFU.RSQ / MUFU.EX2.  The file is compiled with --use_fast_math, under which rsqrtf / exp2f ARE the bare
+// rsqrt.approx.ftz / ex2.approx.ftz instructions; unlike inline asm they let ptxas fold an operand negation.
+__device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,7 +104,7 @@ __device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, flo
     const float rinv2 = rinv * rinv;
     float f;
     if (TRUNC) {
-        const float e = ex2_approx(r2 * P.nlog2e);
+        const float e = ex2_approx(-r2);
         const float v = r2 * rinv;
         float R = P.c[8];
 #pragma unroll
@@ -126,7 +120,9 @@ __device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, flo
 }
 
 // two targets at once with the sm_100a packed FP32 instructions (FFMA2 / FMUL2 / FADD2)
-template <bool TRUNC>
+// POLY = 0: Horner (8 dependent FFMA2); POLY = 1: even/odd split (one more FMUL2, dependency depth 6,
+// two independent chains)
+template <bool TRUNC, int POLY = 0>
 __device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty,
                                             float2 tz, float2& ax, float2& ay, float2& az) {
     const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
@@ -137,12 +133,29 @@ __device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, fl
     const float2 rinv2 = __fmul2_rn(rinv, rinv);
     float2 f;
     if (TRUNC) {
-        const float2 a = __fmul2_rn(r2, make_float2(P.nlog2e, P.nlog2e));
+        // the length unit is 2 r_s / sqrt(log2 e), so exp(-u^2) = 2^(-r2).  MUFU takes no negate modifier on
+        // sm_100 (ptxas materialises it as two scalar FADDs), so the sign costs one packed multiply
+        const float2 a = __fmul2_rn(r2, make_float2(-1.f, -1.f));
         const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
         const float2 v = __fmul2_rn(r2, rinv);
-        float2 R = make_float2(P.c[8], P.c[8]);
+        float2 R;
+        if (POLY == 0) {
+            R = make_float2(P.c[8], P.c[8]);
 #pragma unroll
-        for (int k = 7; k >= 0; k--) R = __ffma2_rn(R, v, make_float2(P.c[k], P.c[k]));
+            for (int k = 7; k >= 0; k--) R = __ffma2_rn(R, v, make_float2(P.c[k], P.c[k]));
+        } else {
+            // v^2 = r2 * rinv^2 * r2 = r2 (in exact arithmetic v = r); use r2 directly: no extra multiply
+            const float2 w = r2;
+            float2 E = make_float2(P.c[8], P.c[8]), O = make_float2(P.c[7], P.c[7]);
+            E = __ffma2_rn(E, w, make_float2(P.c[6], P.c[6]));
+            O = __ffma2_rn(O, w, make_float2(P.c[5], P.c[5]));
+            E = __ffma2_rn(E, w, make_float2(P.c[4], P.c[4]));
+            O = __ffma2_rn(O, w, make_float2(P.c[3], P.c[3]));
+            E = __ffma2_rn(E, w, make_float2(P.c[2], P.c[2]));
+            O = __ffma2_rn(O, w, make_float2(P.c[1], P.c[1]));
+            E = __ffma2_rn(E, w, make_float2(P.c[0], P.c[0]));
+            R = __ffma2_rn(v, O, E);
+        }
         const float2 S = __ffma2_rn(v, R, rinv);
         f = __fmul2_rn(__fmul2_rn(rinv2, e), S);
     } else {
@@ -202,7 +215,7 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, u
 // TT     targets per pass (accumulators in registers); rows with more targets take several passes
 // NSRC   sources per lane per slice (1 or 2)
 // STAGE  particles per staging buffer
-template <int TT, int NSRC, int STAGE, bool TRUNC, bool PACKED, int MINB>
+template <int TT, int NSRC, int STAGE, bool TRUNC, bool PACKED, int MINB, int POLY = 0>
 __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
                                z2 = make_float2(az[2 * p], az[2 * p + 1]);
 #pragma unroll
                         for (int q = 0; q < NSRC; q++)
-                            pair_packed<TRUNC>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
+                            pair_packed<TRUNC, POLY>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
                                                make_float2(txy.x, txy.y), make_float2(txy.z, txy.w), tz, x2, y2, z2);
                         ax[2 * p] = x2.x; ax[2 * p + 1] = x2.y;
                         ay[2 * p] = y2.x; ay[2 * p + 1] = y2.y;

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import host
-from .step import HostLists
+from .step import HostLists, check_wrap_condition
 
 ALL_SHIFTS = [(0, 0, 0)] + [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) if (i, j, k) != (0, 0, 0)]
 """zero displacement first, then the 26 images in the order of 1_Indexing/src/fmm.c:1084-1106"""
@@ -80,6 +80,7 @@ def build_lists(pos, box, maxleaf, nside, theta=0.4, nthreads=0, group=None, lit
     lp, lidx, tcenter, twidth, direct, dom = decompose(pos, box, group)
     c, w = tcenter[dom], twidth[dom]
     T = host.LocalTree(lp, maxleaf, c - 0.5 * w, c + 0.5 * w, int(direct[dom]), nthreads)
+    check_wrap_condition(T, box, rcut, "dist.build_lists")
     out = HostLists()
     out.tree = T
     out.orig_index = lidx[T.perm]

@@ -15,6 +15,18 @@ SHIFTS = [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1) 
 """The 26 periodic displacements in the order 1_Indexing/src/fmm.c:1084-1106 issues them."""
 
 
+def check_wrap_condition(tree, box, rcut, what="list"):
+    """The device stores fixed-point coordinates whose differences wrap to the minimal image
+    (csrc/p2p_kernel.cuh).  That equals the displaced-copy semantics of the reference
+    (1_Indexing/src/remotes.c:360-366) iff every separation a listed leaf pair implies stays below
+    box/2 per axis.  A listed pair has a box gap below r_cut, so r_cut + 2 * (largest leaf width) is a
+    bound on any such separation."""
+    wmax = float(tree.leaf_width.max()) if tree.nleaf else 0.0
+    if rcut + 2.0 * wmax >= 0.5 * box:
+        raise ValueError(f"{what}: r_cut ({rcut:g}) + 2 x largest leaf width ({wmax:g}) reaches box/2 ({0.5 * box:g}); "
+                         "the periodic box is too small for minimal-image coordinates (needs roughly NSIDE >= 32)")
+
+
 class HostLists:
     """Everything the device needs for one rank, produced on the host."""
 
@@ -38,6 +50,8 @@ def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, 
     T = host.LocalTree(pos, maxleaf, bdl, bdr, direct_start, nthreads)
     t1 = time.perf_counter()
     out.tree = T
+    if periodic:
+        check_wrap_condition(T, box, rcut, "build_lists")
     out.tt, out.ts = T.walk_task_p2p(theta, rcut, nthreads)
     t2 = time.perf_counter()
     if periodic:
