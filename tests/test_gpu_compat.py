@@ -130,3 +130,34 @@ def test_redundant_abi(demo_pos):
     rr = (_dp * 1)(res2.ctypes.data_as(_dp))
     L.readResultsGPU(rr, 0, 1, maxp, nt2, nt2 * maxp * 3, 0)
     assert np.allclose(res2.reshape(nt2, maxp, 3), result[:nt2], rtol=0, atol=1e-12 * np.abs(result).max())
+
+
+@pytest.mark.parametrize("truncated", [False, True])
+def test_reference_host_code_linked_against_our_library(demo_pos, tmp_path, truncated):
+    """THE drop-in test: oracle/_ref/ref_dropin is the reference's unmodified fmm.c / remotes.c / toptree.c /
+    domains.c / operator.c linked against lib/libphotoNs_CUDA_indexing.so (oracle/Makefile).  Its own
+    fmm_prepare + fmm_task build the tree, walk it, pack the Indexing buffers, drive our C-ABI and reduce
+    the result slots into part[].acc (1_Indexing/src/fmm.c:842-911)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref", "ref_dropin")
+    if not os.path.isfile(exe):
+        pytest.skip("oracle/_ref/ref_dropin not built (needs /root/reference at build time)")
+    pf, of = tmp_path / "pos.f64", tmp_path / "acc.f64"
+    np.ascontiguousarray(demo_pos).tofile(pf)
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    env = dict(os.environ)
+    env.pop("P2P_B200_RS", None)
+    if truncated:
+        env["P2P_B200_RS"] = repr(rs)
+    subprocess.run([exe, str(pf), str(len(demo_pos)), repr(DEMO_BOX), "16", str(DEMO_NSIDE), repr(THETA), repr(DEMO_MASS), str(of)],
+                   check=True, env=env, timeout=600, stdout=subprocess.DEVNULL)
+    acc = np.fromfile(of).reshape(-1, 3)
+    T = oracle.Tree(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, 0)
+    tt, ts = T.walk_p2p(THETA, rcut)
+    ref_t, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, DEMO_MASS, eps,
+                          rs if truncated else 0.0)
+    ref = np.empty_like(ref_t)
+    ref[T.perm] = ref_t
+    nr = np.linalg.norm(ref, axis=1)
+    err = (np.linalg.norm(acc - ref, axis=1) / np.maximum(nr, nr.mean())).max()
+    assert err < 1e-5, err
