@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--clustered", action="store_true")
     ap.add_argument("--cpu-pairs", type=float, default=1.5e10, help="pairs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true", help="skip the walk/compute pipeline measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -200,7 +201,6 @@ def main():
     else:
         L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=nthreads)
     t_lists = time.perf_counter() - t0
-    del pos
     T = L.tree
 
     st = step.ShortRangeStep(local_rank)
@@ -280,6 +280,24 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---------------------------------------------------------------- full step with the walk/compute pipeline
+    full_step = None
+    if not distributed and not args.no_full_step:
+        ctx2 = step.ShortRangeStep(local_rank).ctx
+        ctx2.set_stream(stream.cuda_stream)
+        barrier()
+        t0 = time.perf_counter()
+        _, tp, n_t, n_p = step.run_full_step_pipelined(ctx2, pos, box, args.maxleaf, args.nside, mass, THETA, nchunks=32,
+                                                       periodic=True, nthreads=nthreads)
+        barrier()
+        t_pipe = time.perf_counter() - t0
+        assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
+        full_step = {"what": "tree build + dual-tree walk + 26 image walks + H2D + CSR + P2P + D2H, one rank",
+                     "pipelined_s": t_pipe, "pipelined_breakdown": tp,
+                     "sequential_s": t_lists + e2e_s / args.steps, "host_threads": nthreads, "chunks": 32}
+        ctx2.close()
+    del pos
+
     # ---------------------------------------------------------------- reduce over ranks
     if distributed:
         t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
@@ -322,6 +340,8 @@ def main():
                                  "peak_gbs": peaks["hbm_gbs"], "note": "compulsory particle/CSR/acc traffic of one launch; the kernel is FP32-pipe bound"}},
             "clocks": sampler.result(),
         }
+        if full_step:
+            out["config"]["full_step"] = full_step
         if not args.no_cpu_baseline and not distributed:
             rate, npr, nrow, dt, threads = cpu_oracle_rate(L, mass, args.cpu_pairs, os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": rate, "unit": "pair/s", "cores": threads, "kind": "port",

@@ -113,6 +113,9 @@ int p2p_synchronize(p2p_ctx* ctx);
 int p2p_download_acc(p2p_ctx* ctx, double* acc, int64_t stride_doubles, int accumulate);
 
 int p2p_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
+/* totals over every p2p_compute since the accelerations were last zeroed (p2p_zero_acc / p2p_upload_particles):
+ * what the current accelerations contain; summed on the device, so chunked pipelines never synchronise */
+int p2p_accumulated_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
 /* copies of the device CSR for parity tests: row_ptr[nleaf+1] (int64), col[ntask] (int32) */
 int p2p_download_csr(p2p_ctx* ctx, int64_t* row_ptr, int* col);
 /* milliseconds spent by the last p2p_compute / p2p_build_csr launch sequence (CUDA events) */

@@ -53,6 +53,19 @@ int p2p_tree_get(const p2p_tree* t, p2p_tree_view* view);
  * indices (target, source) in the reference's traversal order; release with p2p_host_free. */
 int p2p_walk_task_p2p(const p2p_tree* t, double theta, double rcut, int nthreads, int** tt, int** ts, int64_t* ntask);
 
+/* Walk/compute pipeline (replaces the ping-pong task buffers of fmm_task / turn2compute_p2p,
+ * 1_Indexing/src/fmm.c:365-400,947-1024): the dual-tree recursion is expanded to a frontier whose items are
+ * grouped by TARGET chunk (a contiguous range of target leaves = a subtree of the local tree); the chunks
+ * are then walked one at a time, so that the device can pack and compute chunk c while the host walks
+ * chunk c+1.  The union of the chunks is exactly the task multiset of p2p_walk_task_p2p, and every task
+ * of chunk c has its target leaf in [row_begin, row_end) of that chunk. */
+typedef struct p2p_walk_plan p2p_walk_plan;
+int p2p_walk_plan_create(const p2p_tree* t, double theta, double rcut, int nchunks_wanted, p2p_walk_plan** plan);
+int p2p_walk_plan_nchunks(const p2p_walk_plan* plan);
+int p2p_walk_plan_rows(const p2p_walk_plan* plan, int chunk, int* row_begin, int* row_end);
+int p2p_walk_plan_run(const p2p_walk_plan* plan, int chunk, int nthreads, int** tt, int** ts, int64_t* ntask);
+void p2p_walk_plan_free(p2p_walk_plan* plan);
+
 /* Pruned image of the local tree for one target domain box and displacement (the halo a peer
  * needs).  The image is the reference's RemoteNode/RemoteBody content (1_Indexing/inc/photoNs.h:202-214). */
 typedef struct {

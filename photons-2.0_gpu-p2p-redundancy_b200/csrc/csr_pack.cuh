@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
     if (lane == 0 && s) atomicAdd(npairs, s);
 }
 
+__global__ void add_counter_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst += *src;
+}
+
 // 32-bit fixed-point coordinate over the (padded) box: q = round((x - origin) * 2^32 / extent) mod 2^32.
 // Differences of two such coordinates wrap to the minimal image, so displaced (periodic image /
 // halo) copies of a particle map to the same value as the original.

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
@@ -253,13 +254,44 @@ struct ExtWalk {
     }
 };
 
-// Frontier-parallel driver shared by both walks.
+struct Item { Pair p; bool emit; };
+
+// Runs a list of frontier items on all host threads and concatenates the per-item outputs in list order.
+template <class W>
+int run_items(const W& w, const std::vector<Item>& cur, int nthreads, bool ext, int** tt, int** ts, int64_t* ntask) {
+    const int64_t nitem = (int64_t)cur.size();
+    std::vector<std::vector<int>> outs((size_t)nitem);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int64_t i = 0; i < nitem; i++) {
+        if (cur[i].emit) continue;
+        w.run(cur[i].p, outs[i]);
+    }
+    std::vector<int64_t> off((size_t)nitem + 1, 0);
+    for (int64_t i = 0; i < nitem; i++) off[i + 1] = off[i] + (cur[i].emit ? 1 : (int64_t)outs[i].size() / 2);
+    const int64_t total = off[nitem];
+    int* t = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
+    int* s = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
+    if (!t || !s) { free(t); free(s); return -1; }
+    const int first_leaf = w.T->first_leaf;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t i = 0; i < nitem; i++) {
+        int64_t o = off[i];
+        if (cur[i].emit) {
+            t[o] = cur[i].p.im - first_leaf;
+            s[o] = ext ? cur[i].p.jm : cur[i].p.jm - first_leaf;
+            continue;
+        }
+        const std::vector<int>& v = outs[i];
+        for (size_t k = 0; k + 1 < v.size(); k += 2) { t[o] = v[k]; s[o] = v[k + 1]; o++; }
+    }
+    *tt = t; *ts = s; *ntask = total;
+    return 0;
+}
+
+// Expands the open items of `cur` (in traversal order) until there are at least `want` items.
 template <class W, int MAXK>
-int drive_walk(const W& w, Pair root, int nthreads, int** tt, int** ts, int64_t* ntask) {
-    struct Item { Pair p; bool emit; };
-    std::vector<Item> cur, nxt;
-    cur.push_back(Item{root, false});
-    const size_t want = (size_t)nthreads * 256;
+void expand_items(const W& w, std::vector<Item>& cur, size_t want) {
+    std::vector<Item> nxt;
     for (int round = 0; round < 64; round++) {
         size_t open = 0;
         for (const Item& it : cur) open += it.emit ? 0 : 1;
@@ -276,34 +308,15 @@ int drive_walk(const W& w, Pair root, int nthreads, int** tt, int** ts, int64_t*
         }
         cur.swap(nxt);
     }
-    const int64_t nitem = (int64_t)cur.size();
-    std::vector<std::vector<int>> outs((size_t)nitem);
-#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
-    for (int64_t i = 0; i < nitem; i++) {
-        if (cur[i].emit) continue;
-        w.run(cur[i].p, outs[i]);
-    }
-    std::vector<int64_t> off((size_t)nitem + 1, 0);
-    for (int64_t i = 0; i < nitem; i++) off[i + 1] = off[i] + (cur[i].emit ? 1 : (int64_t)outs[i].size() / 2);
-    const int64_t total = off[nitem];
-    int* t = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
-    int* s = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
-    if (!t || !s) { free(t); free(s); return -1; }
-    const int first_leaf = w.T->first_leaf;
-    const bool ext = MAXK == 2;
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
-    for (int64_t i = 0; i < nitem; i++) {
-        int64_t o = off[i];
-        if (cur[i].emit) {
-            t[o] = cur[i].p.im - first_leaf;
-            s[o] = ext ? cur[i].p.jm : cur[i].p.jm - first_leaf;
-            continue;
-        }
-        const std::vector<int>& v = outs[i];
-        for (size_t k = 0; k + 1 < v.size(); k += 2) { t[o] = v[k]; s[o] = v[k + 1]; o++; }
-    }
-    *tt = t; *ts = s; *ntask = total;
-    return 0;
+}
+
+// Frontier-parallel driver shared by both walks.
+template <class W, int MAXK>
+int drive_walk(const W& w, Pair root, int nthreads, int** tt, int** ts, int64_t* ntask) {
+    std::vector<Item> cur;
+    cur.push_back(Item{root, false});
+    expand_items<W, MAXK>(w, cur, (size_t)nthreads * 256);
+    return run_items(w, cur, nthreads, MAXK == 2, tt, ts, ntask);
 }
 
 int mostleft_of(int P) {  // 1_Indexing/src/initial.c:206-215
@@ -421,6 +434,115 @@ int p2p_walk_task_p2p(const p2p_tree* t, double theta, double rcut, int nthreads
     LocalWalk w{t, theta, rcut};
     return drive_walk<LocalWalk, 4>(w, Pair{t->first_node, t->first_node}, resolve_threads(nthreads), tt, ts, ntask);
 }
+
+}  // extern "C"
+
+struct p2p_walk_plan {
+    const p2p_tree* T;
+    double theta, rcut;
+    std::vector<int> row_begin;                     // [nchunk + 1] target-leaf boundaries
+    std::vector<std::vector<Item>> items;           // per chunk, traversal order
+};
+
+extern "C" {
+
+int p2p_walk_plan_create(const p2p_tree* t, double theta, double rcut, int nchunks_wanted, p2p_walk_plan** out) {
+    if (!t || !out || nchunks_wanted < 1) return -2;
+    p2p_walk_plan* P = new p2p_walk_plan();
+    P->T = t; P->theta = theta; P->rcut = rcut;
+    *out = P;
+    if (t->nnode == 0) { P->row_begin = {0, t->nleaf}; P->items.resize(1); return 0; }
+    // leaf range of every node (leaves are numbered left to right, nodes in pre-order)
+    std::vector<int> lo((size_t)t->nnode, 0), hi((size_t)t->nnode, 0), depth((size_t)t->nnode, 0);
+    for (int n = t->nnode - 1; n >= 0; n--) {       // children have larger pre-order ids than their parent
+        int l = t->nleaf, h = 0;
+        for (int k = 0; k < 2; k++) {
+            const int son = t->node_son[2 * (size_t)n + k];
+            if (son < 0) continue;
+            if (son < t->first_node) { l = std::min(l, son - t->first_leaf); h = std::max(h, son - t->first_leaf + 1); }
+            else { l = std::min(l, lo[(size_t)(son - t->first_node)]); h = std::max(h, hi[(size_t)(son - t->first_node)]); }
+        }
+        lo[(size_t)n] = l; hi[(size_t)n] = h;
+    }
+    for (int n = 0; n < t->nnode; n++)
+        for (int k = 0; k < 2; k++) {
+            const int son = t->node_son[2 * (size_t)n + k];
+            if (son >= t->first_node) depth[(size_t)(son - t->first_node)] = depth[(size_t)n] + 1;
+        }
+    // chunk boundaries: subtrees at the depth that yields about nchunks_wanted pieces of similar leaf count
+    int d = 0;
+    while ((1 << d) < nchunks_wanted) d++;
+    std::vector<int> bounds;
+    bounds.push_back(0);
+    std::vector<int> st;                            // global ids (leaf or node), visited left to right
+    st.push_back(t->first_node);
+    while (!st.empty()) {
+        const int id = st.back();
+        st.pop_back();
+        if (id < t->first_node) { bounds.push_back(id - t->first_leaf + 1); continue; }   // a leaf above the cut depth
+        const int n = id - t->first_node;
+        if (depth[(size_t)n] >= d) { bounds.push_back(hi[(size_t)n]); continue; }
+        for (int k = 1; k >= 0; k--) {
+            const int son = t->node_son[2 * (size_t)n + k];
+            if (son >= 0) st.push_back(son);
+        }
+    }
+    std::sort(bounds.begin(), bounds.end());
+    bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+    if (bounds.back() != t->nleaf) bounds.push_back(t->nleaf);
+    P->row_begin = bounds;
+    const int nchunk = (int)bounds.size() - 1;
+    P->items.resize((size_t)nchunk);
+    auto chunk_of_leaf = [&](int leaf) { return (int)(std::upper_bound(bounds.begin(), bounds.end(), leaf) - bounds.begin()) - 1; };
+    // expand from (root, root) until every item's target subtree lies inside one chunk
+    LocalWalk w{t, theta, rcut};
+    std::vector<Item> cur, nxt;
+    cur.push_back(Item{Pair{t->first_node, t->first_node}, false});
+    for (int round = 0; round < 256; round++) {
+        bool again = false;
+        nxt.clear();
+        for (const Item& it : cur) {
+            if (it.p.im == -1 || it.p.jm == -1) continue;
+            int l, h;
+            if (it.p.im < t->first_node) { l = it.p.im - t->first_leaf; h = l + 1; }
+            else { l = lo[(size_t)(it.p.im - t->first_node)]; h = hi[(size_t)(it.p.im - t->first_node)]; }
+            if (it.emit || chunk_of_leaf(l) == chunk_of_leaf(h - 1)) { nxt.push_back(it); continue; }
+            bool emit;
+            Pair kids[4];
+            const int nk = w.step(it.p, &emit, kids);
+            if (emit) nxt.push_back(Item{it.p, true});
+            for (int k = 0; k < nk; k++) nxt.push_back(Item{kids[k], false});
+            again = true;
+        }
+        cur.swap(nxt);
+        if (!again) break;
+    }
+    for (const Item& it : cur) {
+        const int l = it.p.im < t->first_node ? it.p.im - t->first_leaf : lo[(size_t)(it.p.im - t->first_node)];
+        P->items[(size_t)chunk_of_leaf(l)].push_back(it);
+    }
+    return 0;
+}
+
+int p2p_walk_plan_nchunks(const p2p_walk_plan* P) { return P ? (int)P->items.size() : -2; }
+
+int p2p_walk_plan_rows(const p2p_walk_plan* P, int c, int* b, int* e) {
+    if (!P || c < 0 || c >= (int)P->items.size()) return -2;
+    if (b) *b = P->row_begin[(size_t)c];
+    if (e) *e = P->row_begin[(size_t)c + 1];
+    return 0;
+}
+
+int p2p_walk_plan_run(const p2p_walk_plan* P, int c, int nthreads, int** tt, int** ts, int64_t* ntask) {
+    if (!P || !tt || !ts || !ntask || c < 0 || c >= (int)P->items.size()) return -2;
+    nthreads = resolve_threads(nthreads);
+    LocalWalk w{P->T, P->theta, P->rcut};
+    std::vector<Item> cur = P->items[(size_t)c];
+    expand_items<LocalWalk, 4>(w, cur, (size_t)nthreads * 64);      // enough items for the threads
+    return run_items(w, cur, nthreads, false, tt, ts, ntask);
+}
+
+void p2p_walk_plan_free(p2p_walk_plan* P) { delete P; }
 
 int p2p_walk_task_p2p_ext(const p2p_tree* t, const p2p_image* img, double theta, double rcut, int nthreads, int** tt,
                           int** ts, int64_t* ntask) {

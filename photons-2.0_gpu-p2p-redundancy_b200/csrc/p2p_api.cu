@@ -90,7 +90,8 @@ struct p2p_ctx {
     DevBuf<unsigned long long> cursor, tile;
     DevBuf<unsigned char> stage;
     unsigned int* d_counter = nullptr;      // [0] row scheduler, [1] unsorted rows
-    unsigned long long* d_npairs = nullptr;
+    unsigned long long* d_npairs = nullptr;      // [0] pairs of the current CSR, [1] pairs accumulated into acc
+    long long acc_tasks = 0;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
     unsigned int* h_flags = nullptr;        // pinned copy of d_counter after build_csr
@@ -248,7 +249,8 @@ int p2p_create(p2p_ctx** out, int device) {
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_counter, 4 * sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_npairs, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_npairs, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_npairs, 0, 2 * sizeof(unsigned long long)));
     CU(cudaMallocHost(&c->h_flags, 4 * sizeof(unsigned int)));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -322,6 +324,8 @@ int p2p_upload_particles(p2p_ctx* c, const double* pos, int64_t stride, int64_t 
     int r = upload_xyz(c, pos, stride, npart, c->part.p);
     if (r) return r;
     CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), c->stream));
+    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), c->stream));
+    c->acc_tasks = 0;
     return 0;
 }
 
@@ -551,12 +555,29 @@ int p2p_compute(p2p_ctx* c) {
     if (r) return r;
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timed_compute = true;
+    p2p::add_counter_kernel<<<1, 32, 0, c->stream>>>(c->d_npairs, c->d_npairs + 1);   // no host sync
+    CU(cudaGetLastError());
+    c->acc_tasks += c->ntask;
+    return 0;
+}
+
+int p2p_accumulated_counts(p2p_ctx* c, int64_t* ntask, int64_t* npairs) {
+    USE(c);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->d_npairs + 1, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int r = check_flags(c);
+    if (r) return r;
+    if (ntask) *ntask = c->acc_tasks;
+    if (npairs) *npairs = (long long)v;
     return 0;
 }
 
 int p2p_zero_acc(p2p_ctx* c) {
     USE(c);
     if (c->npart) CU(cudaMemsetAsync(c->acc.p, 0, (size_t)c->npart * sizeof(float4), c->stream));
+    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), c->stream));
+    c->acc_tasks = 0;
     return 0;
 }
 

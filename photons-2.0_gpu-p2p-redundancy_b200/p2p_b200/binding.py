@@ -59,6 +59,7 @@ def load_library():
     L.p2p_append_tasks_interleaved.argtypes = [C.c_void_p, _ip, C.c_int64, C.c_int]
     L.p2p_download_acc.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int]
     L.p2p_counts.argtypes = [C.c_void_p, _lp, _lp]
+    L.p2p_accumulated_counts.argtypes = [C.c_void_p, _lp, _lp]
     L.p2p_download_csr.argtypes = [C.c_void_p, _lp, _ip]
     L.p2p_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.p2p_step_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _ip, _ip, C.c_int64, _dp,
@@ -189,6 +190,11 @@ class P2PContext:
     def counts(self):
         nt, npairs = C.c_int64(), C.c_int64()
         self._chk(self._L.p2p_counts(self._h, C.byref(nt), C.byref(npairs)))
+        return nt.value, npairs.value
+
+    def accumulated_counts(self):
+        nt, npairs = C.c_int64(), C.c_int64()
+        self._chk(self._L.p2p_accumulated_counts(self._h, C.byref(nt), C.byref(npairs)))
         return nt.value, npairs.value
 
     def download_csr(self):

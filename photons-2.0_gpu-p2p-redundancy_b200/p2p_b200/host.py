@@ -40,6 +40,11 @@ def load_host_library():
         L.p2p_tree_get.argtypes = [C.c_void_p, C.POINTER(_TreeView)]
         L.p2p_walk_task_p2p.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.POINTER(_ip), C.POINTER(_ip),
                                         C.POINTER(C.c_int64)]
+        L.p2p_walk_plan_create.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+        L.p2p_walk_plan_nchunks.argtypes = [C.c_void_p]
+        L.p2p_walk_plan_rows.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+        L.p2p_walk_plan_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_ip), C.POINTER(_ip), C.POINTER(C.c_int64)]
+        L.p2p_walk_plan_free.argtypes = [C.c_void_p]
         L.p2p_prepare_sendtree.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double,
                                            C.POINTER(_Image)]
         L.p2p_image_free.argtypes = [C.POINTER(_Image)]
@@ -146,6 +151,10 @@ class LocalTree:
             raise P2PError(rc, "p2p_walk_task_p2p failed")
         return _take(tt, n.value, np.int32), _take(ts, n.value, np.int32)
 
+    def walk_plan(self, theta, rcut, nchunks):
+        """Chunked walk for the walk/compute pipeline (see p2p_host.h)."""
+        return WalkPlan(self, theta, rcut, nchunks)
+
     def prepare_sendtree(self, tcenter, twidth, displace, theta, rcut):
         L = load_host_library()
         img = _Image()
@@ -178,6 +187,41 @@ class LocalTree:
         if rc != 0:
             raise P2PError(rc, "p2p_walk_task_p2p_ext failed")
         return _take(tt, n.value, np.int32), _take(ts, n.value, np.int32)
+
+
+class WalkPlan:
+    """Frontier of the dual-tree recursion grouped by target chunk; run(c) walks one chunk."""
+
+    def __init__(self, tree, theta, rcut, nchunks):
+        L = load_host_library()
+        self._tree = tree                      # keeps the tree alive
+        h = C.c_void_p()
+        rc = L.p2p_walk_plan_create(tree._h, float(theta), float(rcut), int(nchunks), C.byref(h))
+        if rc != 0:
+            raise P2PError(rc, "p2p_walk_plan_create failed")
+        self._h = h
+        self.nchunks = L.p2p_walk_plan_nchunks(h)
+
+    def rows(self, c):
+        b, e = C.c_int(), C.c_int()
+        load_host_library().p2p_walk_plan_rows(self._h, int(c), C.byref(b), C.byref(e))
+        return b.value, e.value
+
+    def run(self, c, nthreads=0):
+        L = load_host_library()
+        tt, ts, n = _ip(), _ip(), C.c_int64()
+        rc = L.p2p_walk_plan_run(self._h, int(c), int(nthreads), C.byref(tt), C.byref(ts), C.byref(n))
+        if rc != 0:
+            raise P2PError(rc, "p2p_walk_plan_run failed")
+        return _take(tt, n.value, np.int32), _take(ts, n.value, np.int32)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                load_host_library().p2p_walk_plan_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def domain_setup(nproc, box):

@@ -122,3 +122,65 @@ class ShortRangeStep:
         self.upload(lists, mass, truncated)
         self.compute()
         return self.download(lists)
+
+
+def run_full_step_pipelined(ctx, pos, box, maxleaf, nside, mass, theta=0.4, nchunks=16, periodic=True, truncated=True,
+                            nthreads=0):
+    """The whole short-range step -- tree build, walk, P2P -- with the walk/compute pipeline: the device
+    packs and computes target chunk c while the host walks chunk c+1 (the reference's ping-pong task
+    buffers, 1_Indexing/src/fmm.c:365-400,947-1024, which this fork serialised).  Periodic-image ghost
+    tasks form one last chunk.  Returns (acc in ORIGINAL particle order, timings dict, ntask, npairs)."""
+    t = {}
+    t0 = time.perf_counter()
+    rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
+    T = host.LocalTree(pos, maxleaf, [0.0] * 3, [box] * 3, 0, nthreads)
+    if periodic:
+        check_wrap_condition(T, box, rcut, "run_full_step_pipelined")
+    t["build_s"] = time.perf_counter() - t0
+    ctx.set_physics(mass, eps, rs if truncated else 0.0)
+    ctx.set_box([0.0, 0.0, 0.0], box)
+    ctx.upload_particles(T.pos)                       # asynchronous: overlaps the planning below
+    ctx.upload_leaves(T.leaf_npart, T.leaf_ipart)
+    t1 = time.perf_counter()
+    plan = T.walk_plan(theta, rcut, nchunks)
+    walk_s = 0.0
+    nxt = plan.run(0, nthreads) if plan.nchunks else None
+    walk_s += time.perf_counter() - t1
+    for c in range(plan.nchunks):
+        tt, ts = nxt
+        ctx.clear_tasks()
+        ctx.append_tasks(tt, ts)
+        ctx.build_csr()
+        ctx.compute()                                 # returns at once; the device works on chunk c ...
+        t2 = time.perf_counter()
+        nxt = plan.run(c + 1, nthreads) if c + 1 < plan.nchunks else None   # ... while the host walks chunk c+1
+        walk_s += time.perf_counter() - t2
+    t["walk_s"] = walk_s
+    if periodic:
+        t3 = time.perf_counter()
+        first = None
+        gtt, gts, nleaf = [], [], 0
+        for sh in SHIFTS:
+            img = T.prepare_sendtree(T.node_center[0], T.node_width[0], np.array(sh, np.float64) * box, theta, rcut)
+            tt, ts = T.walk_task_p2p_ext(img, theta, rcut, nthreads)
+            if len(tt) == 0:
+                continue
+            used, inv = np.unique(ts, return_inverse=True)
+            cnt, st = img.npart[used], img.son[used, 0]
+            sel = np.concatenate([np.arange(s, s + k) for s, k in zip(st, cnt)])
+            f = ctx.append_ghosts(img.body[sel], np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32), cnt)
+            first = f if first is None else first
+            gtt.append(tt)
+            gts.append((f - first + inv).astype(np.int32))
+        t["images_s"] = time.perf_counter() - t3
+        if gtt:
+            ctx.clear_tasks()
+            ctx.append_tasks(np.concatenate(gtt), np.concatenate(gts), source_offset=first)
+            ctx.build_csr()
+            ctx.compute()
+    ntask, npairs = ctx.accumulated_counts()
+    acc_t = ctx.download_acc()
+    acc = np.empty_like(acc_t)
+    acc[T.perm] = acc_t
+    t["total_s"] = time.perf_counter() - t0
+    return acc, t, ntask, npairs

@@ -187,3 +187,14 @@ def test_properties_at_scale():
     got = st.ctx.download_acc()[sel]
     nr = np.linalg.norm(ref[sel], axis=1)
     assert (np.linalg.norm(got - ref[sel], axis=1) / np.maximum(nr, nr.mean())).max() < TOL
+
+
+def test_walk_compute_pipeline(demo_pos):
+    """Chunked walk + per-chunk CSR/compute (walk/compute pipeline) == the one-shot step == oracle."""
+    ctx = p2p_b200.P2PContext(0)
+    acc, t, ntask, npairs = step.run_full_step_pipelined(ctx, demo_pos, DEMO_BOX, 16, DEMO_NSIDE, DEMO_MASS, THETA, nchunks=8)
+    ref, rtask, rpairs = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, 1, True)
+    assert (ntask, npairs) == (rtask, rpairs)
+    nr = np.linalg.norm(ref, axis=1)
+    assert (np.linalg.norm(acc - ref, axis=1) / np.maximum(nr, nr.mean())).max() < TOL
+    ctx.close()
