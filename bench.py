@@ -32,6 +32,7 @@ for p in (os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200"),):
 
 FLOP_PER_PAIR = 38.0      # algorithmic FP32 flop of one truncated pair (FMA = 2)
 THETA = 0.4
+print_json = None
 
 
 def measured_peaks():
@@ -145,7 +146,7 @@ def run_reference_arm(args):
                                    f"{tot_pairs // args.steps} pairs per step, fp64 erfc/exp, OpenMP dynamic over target leaves"},
         "e2e": {"value": value, "unit": "pair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    print_json(out)
 
 
 def workload_config(args, box):
@@ -156,6 +157,13 @@ def workload_config(args, box):
 
 
 def main():
+    # Only the JSON line may reach stdout: NCCL (version banner) and the reference-style prints of the
+    # libraries go to fd 1 as well, so fd 1 is pointed at stderr and the JSON is written to the saved fd.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -285,16 +293,19 @@ def main():
     if not distributed and not args.no_full_step:
         ctx2 = step.ShortRangeStep(local_rank).ctx
         ctx2.set_stream(stream.cuda_stream)
-        barrier()
-        t0 = time.perf_counter()
-        _, tp, n_t, n_p = step.run_full_step_pipelined(ctx2, pos, box, args.maxleaf, args.nside, mass, THETA, nchunks=32,
-                                                       periodic=True, nthreads=nthreads)
-        barrier()
-        t_pipe = time.perf_counter() - t0
-        assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
-        full_step = {"what": "tree build + dual-tree walk + 26 image walks + H2D + CSR + P2P + D2H, one rank",
-                     "pipelined_s": t_pipe, "pipelined_breakdown": tp,
-                     "sequential_s": t_lists + e2e_s / args.steps, "host_threads": nthreads, "chunks": 32}
+        acc2 = torch.empty((T.npart, 3), dtype=torch.float64).pin_memory().numpy()
+        res = {}
+        for mode in (False, True, False, True):        # sequential / pipelined, twice: the second pair is reported
+            barrier()
+            t0 = time.perf_counter()
+            _, _, tp, n_t, n_p = step.run_full_step(ctx2, pos, box, args.maxleaf, args.nside, mass, THETA, nchunks=32,
+                                                    periodic=True, nthreads=nthreads, pipelined=mode, acc_out=acc2)
+            barrier()
+            res[mode] = (time.perf_counter() - t0, tp)
+            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
+        full_step = {"what": "tree build + H2D + dual-tree walk (32 target chunks) + CSR + P2P + 26 image walks + D2H, one rank",
+                     "pipelined_s": res[True][0], "pipelined_breakdown": res[True][1],
+                     "sequential_s": res[False][0], "sequential_breakdown": res[False][1], "host_threads": nthreads}
         ctx2.close()
     del pos
 
@@ -347,7 +358,7 @@ def main():
             out["cpu_baseline"] = {"value": rate, "unit": "pair/s", "cores": threads, "kind": "port",
                                    "sample": f"first {nrow} of {T.nleaf} target leaves (complete CSR rows) = {npr} pairs in {dt:.1f} s, "
                                              "fp64 oracle (erfc/exp), OpenMP dynamic over target leaves"}
-        print(json.dumps(out))
+        print_json(out)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()

@@ -64,6 +64,9 @@ int p2p_walk_plan_create(const p2p_tree* t, double theta, double rcut, int nchun
 int p2p_walk_plan_nchunks(const p2p_walk_plan* plan);
 int p2p_walk_plan_rows(const p2p_walk_plan* plan, int chunk, int* row_begin, int* row_end);
 int p2p_walk_plan_run(const p2p_walk_plan* plan, int chunk, int nthreads, int** tt, int** ts, int64_t* ntask);
+/* same, written straight into caller-owned buffers (e.g. pinned host memory that a DMA engine reads while
+ * the next chunk is being walked); returns -3 with *ntask = needed size if cap is too small */
+int p2p_walk_plan_run_into(const p2p_walk_plan* plan, int chunk, int nthreads, int* tt, int* ts, int64_t cap, int64_t* ntask);
 void p2p_walk_plan_free(p2p_walk_plan* plan);
 
 /* Pruned image of the local tree for one target domain box and displacement (the halo a peer

@@ -258,7 +258,8 @@ struct Item { Pair p; bool emit; };
 
 // Runs a list of frontier items on all host threads and concatenates the per-item outputs in list order.
 template <class W>
-int run_items(const W& w, const std::vector<Item>& cur, int nthreads, bool ext, int** tt, int** ts, int64_t* ntask) {
+int run_items(const W& w, const std::vector<Item>& cur, int nthreads, bool ext, int** tt, int** ts, int64_t* ntask,
+              int* tt_into = nullptr, int* ts_into = nullptr, int64_t cap = 0) {
     const int64_t nitem = (int64_t)cur.size();
     std::vector<std::vector<int>> outs((size_t)nitem);
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
@@ -269,9 +270,16 @@ int run_items(const W& w, const std::vector<Item>& cur, int nthreads, bool ext, 
     std::vector<int64_t> off((size_t)nitem + 1, 0);
     for (int64_t i = 0; i < nitem; i++) off[i + 1] = off[i] + (cur[i].emit ? 1 : (int64_t)outs[i].size() / 2);
     const int64_t total = off[nitem];
-    int* t = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
-    int* s = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
-    if (!t || !s) { free(t); free(s); return -1; }
+    int *t, *s;
+    if (tt_into) {
+        *ntask = total;
+        if (total > cap) return -3;
+        t = tt_into; s = ts_into;
+    } else {
+        t = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
+        s = (int*)malloc(sizeof(int) * (size_t)(total ? total : 1));
+        if (!t || !s) { free(t); free(s); return -1; }
+    }
     const int first_leaf = w.T->first_leaf;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
     for (int64_t i = 0; i < nitem; i++) {
@@ -284,7 +292,8 @@ int run_items(const W& w, const std::vector<Item>& cur, int nthreads, bool ext, 
         const std::vector<int>& v = outs[i];
         for (size_t k = 0; k + 1 < v.size(); k += 2) { t[o] = v[k]; s[o] = v[k + 1]; o++; }
     }
-    *tt = t; *ts = s; *ntask = total;
+    if (!tt_into) { *tt = t; *ts = s; }
+    *ntask = total;
     return 0;
 }
 
@@ -540,6 +549,15 @@ int p2p_walk_plan_run(const p2p_walk_plan* P, int c, int nthreads, int** tt, int
     std::vector<Item> cur = P->items[(size_t)c];
     expand_items<LocalWalk, 4>(w, cur, (size_t)nthreads * 64);      // enough items for the threads
     return run_items(w, cur, nthreads, false, tt, ts, ntask);
+}
+
+int p2p_walk_plan_run_into(const p2p_walk_plan* P, int c, int nthreads, int* tt, int* ts, int64_t cap, int64_t* ntask) {
+    if (!P || !tt || !ts || !ntask || c < 0 || c >= (int)P->items.size()) return -2;
+    nthreads = resolve_threads(nthreads);
+    LocalWalk w{P->T, P->theta, P->rcut};
+    std::vector<Item> cur = P->items[(size_t)c];
+    expand_items<LocalWalk, 4>(w, cur, (size_t)nthreads * 64);
+    return run_items(w, cur, nthreads, false, nullptr, nullptr, ntask, tt, ts, cap);
 }
 
 void p2p_walk_plan_free(p2p_walk_plan* P) { delete P; }

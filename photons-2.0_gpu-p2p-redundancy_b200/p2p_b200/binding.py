@@ -92,6 +92,7 @@ class P2PContext:
         self._h = h
         self.npart = 0
         self.nleaf = 0
+        self.stream_ptr = 0                          # externally owned stream, 0 = the context's own
 
     def _chk(self, rc):
         if rc != 0:
@@ -124,6 +125,7 @@ class P2PContext:
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self._L.p2p_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        self.stream_ptr = int(cuda_stream_ptr or 0)
 
     def upload_particles(self, pos):
         pos = _f64(pos)

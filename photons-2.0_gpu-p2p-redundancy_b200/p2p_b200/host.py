@@ -44,6 +44,7 @@ def load_host_library():
         L.p2p_walk_plan_nchunks.argtypes = [C.c_void_p]
         L.p2p_walk_plan_rows.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
         L.p2p_walk_plan_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_ip), C.POINTER(_ip), C.POINTER(C.c_int64)]
+        L.p2p_walk_plan_run_into.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, C.c_int64, C.POINTER(C.c_int64)]
         L.p2p_walk_plan_free.argtypes = [C.c_void_p]
         L.p2p_prepare_sendtree.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double,
                                            C.POINTER(_Image)]
@@ -214,6 +215,19 @@ class WalkPlan:
         if rc != 0:
             raise P2PError(rc, "p2p_walk_plan_run failed")
         return _take(tt, n.value, np.int32), _take(ts, n.value, np.int32)
+
+    def run_into(self, c, tt_buf, ts_buf, nthreads=0):
+        """Walk chunk c straight into caller-owned int32 buffers (pinned memory); returns the task count,
+        or -needed if the buffers are too small."""
+        L = load_host_library()
+        n = C.c_int64()
+        rc = L.p2p_walk_plan_run_into(self._h, int(c), int(nthreads), tt_buf.ctypes.data_as(_ip), ts_buf.ctypes.data_as(_ip),
+                                      min(len(tt_buf), len(ts_buf)), C.byref(n))
+        if rc == -3:
+            return -n.value
+        if rc != 0:
+            raise P2PError(rc, "p2p_walk_plan_run_into failed")
+        return n.value
 
     def __del__(self):
         try:

@@ -124,63 +124,103 @@ class ShortRangeStep:
         return self.download(lists)
 
 
-def run_full_step_pipelined(ctx, pos, box, maxleaf, nside, mass, theta=0.4, nchunks=16, periodic=True, truncated=True,
-                            nthreads=0):
-    """The whole short-range step -- tree build, walk, P2P -- with the walk/compute pipeline: the device
-    packs and computes target chunk c while the host walks chunk c+1 (the reference's ping-pong task
-    buffers, 1_Indexing/src/fmm.c:365-400,947-1024, which this fork serialised).  Periodic-image ghost
-    tasks form one last chunk.  Returns (acc in ORIGINAL particle order, timings dict, ntask, npairs)."""
+def run_full_step(ctx, pos, box, maxleaf, nside, mass, theta=0.4, nchunks=16, periodic=True, truncated=True, nthreads=0,
+                  pipelined=True, acc_out=None):
+    """The whole short-range step -- tree build, walk, P2P.
+
+    pipelined=True: walk/compute pipeline -- the device packs and computes target chunk c while the host
+    walks chunk c+1 into a pinned double buffer (the reference's ping-pong task buffers,
+    1_Indexing/src/fmm.c:365-400,947-1024, which this fork serialised).  pipelined=False: the same work
+    strictly in sequence (walk everything, then upload and compute everything), for comparison.
+    Periodic-image ghost tasks form one last chunk.
+    Returns (acc in TREE order, tree, timings dict, ntask, npairs); acc[i] belongs to input particle tree.perm[i]."""
+    import torch
     t = {}
     t0 = time.perf_counter()
     rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
     T = host.LocalTree(pos, maxleaf, [0.0] * 3, [box] * 3, 0, nthreads)
     if periodic:
-        check_wrap_condition(T, box, rcut, "run_full_step_pipelined")
+        check_wrap_condition(T, box, rcut, "run_full_step")
     t["build_s"] = time.perf_counter() - t0
     ctx.set_physics(mass, eps, rs if truncated else 0.0)
     ctx.set_box([0.0, 0.0, 0.0], box)
-    ctx.upload_particles(T.pos)                       # asynchronous: overlaps the planning below
+    ctx.upload_particles(T.pos)
     ctx.upload_leaves(T.leaf_npart, T.leaf_ipart)
     t1 = time.perf_counter()
+    t["upload_s"] = t1 - t0 - t["build_s"]
     plan = T.walk_plan(theta, rcut, nchunks)
-    walk_s = 0.0
-    nxt = plan.run(0, nthreads) if plan.nchunks else None
-    walk_s += time.perf_counter() - t1
-    for c in range(plan.nchunks):
-        tt, ts = nxt
+    cap = max(1024, int(1.3 * 120 * T.nleaf / max(plan.nchunks, 1)))
+    nslot = 2 if pipelined else plan.nchunks
+    bufs, views = [], []
+    for _ in range(nslot):
+        pair = [torch.empty(cap, dtype=torch.int32).pin_memory() for _ in range(2)]
+        bufs.append(pair)
+        views.append([b.numpy() for b in pair])
+    done = [torch.cuda.Event() for _ in range(nslot)]
+    used = [False] * nslot
+    t["plan_s"] = time.perf_counter() - t1
+
+    def walk_into(c, slot):
+        if used[slot]:
+            done[slot].synchronize()                  # the H2D that read this buffer has finished
+        n = plan.run_into(c, views[slot][0], views[slot][1], nthreads)
+        if n < 0:                                     # buffer too small for this chunk: replace it
+            pair = [torch.empty(int(-n * 1.2), dtype=torch.int32).pin_memory() for _ in range(2)]
+            bufs[slot] = pair
+            views[slot] = [b.numpy() for b in pair]
+            n = plan.run_into(c, views[slot][0], views[slot][1], nthreads)
+        return n
+
+    def submit(slot, n):
         ctx.clear_tasks()
-        ctx.append_tasks(tt, ts)
+        ctx.append_tasks(views[slot][0][:n], views[slot][1][:n])      # async H2D from pinned memory
+        if ctx.stream_ptr:
+            done[slot].record(torch.cuda.ExternalStream(ctx.stream_ptr))
+        else:
+            ctx.synchronize()
+        used[slot] = True
         ctx.build_csr()
-        ctx.compute()                                 # returns at once; the device works on chunk c ...
-        t2 = time.perf_counter()
-        nxt = plan.run(c + 1, nthreads) if c + 1 < plan.nchunks else None   # ... while the host walks chunk c+1
-        walk_s += time.perf_counter() - t2
-    t["walk_s"] = walk_s
+        ctx.compute()                                 # returns at once
+
+    t2 = time.perf_counter()
+    if pipelined:
+        n_next = walk_into(0, 0) if plan.nchunks else 0
+        for c in range(plan.nchunks):
+            submit(c & 1, n_next)                     # the device works on chunk c ...
+            if c + 1 < plan.nchunks:
+                n_next = walk_into(c + 1, (c + 1) & 1)   # ... while the host walks chunk c+1
+    else:
+        counts = [walk_into(c, c) for c in range(plan.nchunks)]
+        ctx.synchronize()
+        for c in range(plan.nchunks):
+            submit(c, counts[c])
+        ctx.synchronize()
+    t["walk_and_submit_s"] = time.perf_counter() - t2
     if periodic:
         t3 = time.perf_counter()
         first = None
-        gtt, gts, nleaf = [], [], 0
+        gtt, gts = [], []
         for sh in SHIFTS:
             img = T.prepare_sendtree(T.node_center[0], T.node_width[0], np.array(sh, np.float64) * box, theta, rcut)
             tt, ts = T.walk_task_p2p_ext(img, theta, rcut, nthreads)
             if len(tt) == 0:
                 continue
-            used, inv = np.unique(ts, return_inverse=True)
-            cnt, st = img.npart[used], img.son[used, 0]
+            used_l, inv = np.unique(ts, return_inverse=True)
+            cnt, st = img.npart[used_l], img.son[used_l, 0]
             sel = np.concatenate([np.arange(s, s + k) for s, k in zip(st, cnt)])
             f = ctx.append_ghosts(img.body[sel], np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32), cnt)
             first = f if first is None else first
             gtt.append(tt)
             gts.append((f - first + inv).astype(np.int32))
-        t["images_s"] = time.perf_counter() - t3
         if gtt:
             ctx.clear_tasks()
             ctx.append_tasks(np.concatenate(gtt), np.concatenate(gts), source_offset=first)
             ctx.build_csr()
             ctx.compute()
+        t["images_s"] = time.perf_counter() - t3
+    t4 = time.perf_counter()
     ntask, npairs = ctx.accumulated_counts()
-    acc_t = ctx.download_acc()
-    acc = np.empty_like(acc_t)
-    acc[T.perm] = acc_t
+    acc = ctx.download_acc(acc_out)
+    t["download_s"] = time.perf_counter() - t4
     t["total_s"] = time.perf_counter() - t0
-    return acc, t, ntask, npairs
+    return acc, T, t, ntask, npairs

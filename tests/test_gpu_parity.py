@@ -189,10 +189,14 @@ def test_properties_at_scale():
     assert (np.linalg.norm(got - ref[sel], axis=1) / np.maximum(nr, nr.mean())).max() < TOL
 
 
-def test_walk_compute_pipeline(demo_pos):
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_walk_compute_pipeline(demo_pos, pipelined):
     """Chunked walk + per-chunk CSR/compute (walk/compute pipeline) == the one-shot step == oracle."""
     ctx = p2p_b200.P2PContext(0)
-    acc, t, ntask, npairs = step.run_full_step_pipelined(ctx, demo_pos, DEMO_BOX, 16, DEMO_NSIDE, DEMO_MASS, THETA, nchunks=8)
+    acc_t, T, t, ntask, npairs = step.run_full_step(ctx, demo_pos, DEMO_BOX, 16, DEMO_NSIDE, DEMO_MASS, THETA, nchunks=8,
+                                                    pipelined=pipelined)
+    acc = np.empty_like(acc_t)
+    acc[T.perm] = acc_t
     ref, rtask, rpairs = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, 1, True)
     assert (ntask, npairs) == (rtask, rpairs)
     nr = np.linalg.norm(ref, axis=1)
