@@ -180,10 +180,10 @@ int upload_ints(p2p_ctx* c, const int* a, const int* b, long long n, int** da, i
 
 constexpr int kStage = 384;   // particles per staging buffer: 2 x 6 KB + targets per warp -> 16 warps / SM fit
 
-template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB, int POLY>
+template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB, int POLY, int STAGE = kStage>
 int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
-    auto kern = p2p::p2p_rows_kernel<TT, NSRC, kStage, TRUNC, PACKED, MINB, POLY>;
-    const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT, kStage>);
+    auto kern = p2p::p2p_rows_kernel<TT, NSRC, STAGE, TRUNC, PACKED, MINB, POLY>;
+    const int smem = 4 * (int)sizeof(p2p::WarpSmem<TT, STAGE>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
@@ -294,9 +294,9 @@ int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
 
 int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
     // min_blocks: 3 or 4; adding 16 selects the even/odd split polynomial (sweeps only)
-    const int poly = minb >= 16 ? 1 : 0;
-    if (poly) minb -= 16;
-    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4))
+    const int poly = minb / 16;                 // +16: even/odd split polynomial, +32: breadth-first 4-chain schedule
+    minb %= 16;
+    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4) || poly > 1)
         return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16, sources_per_lane 1/2/4, min_blocks 3/4)");
     c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb; c->tune_poly = poly;
     return 0;
@@ -526,6 +526,7 @@ int p2p_compute(p2p_ctx* c) {
     const double unit = trunc ? 2.0 * c->rs / sl2e : (c->extent > 0.0 ? c->extent : 1.0);
     P.k_fix = (float)(c->extent / 4294967296.0 / unit);
     P.eps2 = (float)((c->eps / unit) * (c->eps / unit));
+    P.neps2 = -P.eps2;
     if (trunc) {
         // rinv' Q(u) = rinv' + v (c0 + c1 v + ...), v = r' : c_j = q_{j+2} / sl2e^(j+2)
         for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] / pow(sl2e, j + 2));

@@ -29,7 +29,7 @@
 // exp(-u^2) = 2^(-r^2):
 //     r2 = max(|dx|^2, eps^2); rinv = rsqrt(r2); f = rinv^3 * g(u)
 //     g(u) = exp(-u^2) * Q(u),  Q = 1 + u^2 + q3 u^3 + ... + q10 u^10   (tools/fit_gfactor.py)
-// = 23 FP32-pipe instructions, 1 FMNMX and 2 MUFU (RSQ, EX2) per pair.  The packed variant issues
+// = 21 FP32-pipe instructions, 2 FMNMX and 2 MUFU (RSQ, EX2) per pair (see pair_packed).  The packed variant issues
 // the FP32 work as FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2, new on sm_100) on PAIRS OF TARGETS, which
 // halves the issue slots the FP32 pipe needs and leaves them to MUFU / FMNMX / LDS.
 #pragma once
@@ -53,6 +53,7 @@ struct KernelParams {
     int nrow;
     float k_fix;             // fixed-point step in kernel length units (box / 2^32 / unit)
     float eps2;              // (eps / unit)^2
+    float neps2;             // -eps2
     float c[kPolyTerms];     // q[k+2] / log2(e)^((k+2)/2): coefficients in the kernel's length unit
     float out_scale;         // mass / unit^2
     float far_coord;         // coordinate offset that makes a dummy source contribute exactly 0
@@ -62,6 +63,13 @@ struct KernelParams {
 // rsqrt.approx.ftz / ex2.approx.ftz instructions; unlike inline asm they let ptxas fold an operand negation.
 __device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
 __device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+// min(-q, neps): kept as inline PTX so that the front end cannot rewrite it into -(max(q, eps)), whose
+// negation would land on the FP32 pipe; ptxas folds the neg into the FMNMX source modifier (ALU pipe).
+__device__ __forceinline__ float neg_min(float q, float neps) {
+    float y;
+    asm("{\n.reg .f32 t;\nneg.ftz.f32 t, %1;\nmin.ftz.f32 %0, t, %2;\n}" : "=f"(y) : "f"(q), "f"(neps));
+    return y;
+}
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,68 +106,75 @@ template <bool TRUNC>
 __device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, float sy, float sz, float tx, float ty,
                                             float tz, float& ax, float& ay, float& az) {
     const float dx = sx + tx, dy = sy + ty, dz = sz + tz;
-    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    r2 = fmaxf(r2, P.eps2);
+    const float q2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float r2 = fmaxf(q2, P.eps2);
     const float rinv = rsqrt_approx(r2);
-    const float rinv2 = rinv * rinv;
     float f;
     if (TRUNC) {
-        const float e = ex2_approx(-r2);
+        // same formulation as pair_packed<POLY = 1>: f = (e rinv) (rinv^2 + E(w) + v O(w))
+        const float e = ex2_approx(neg_min(q2, P.neps2));
         const float v = r2 * rinv;
-        float R = P.c[8];
-#pragma unroll
-        for (int k = 7; k >= 0; k--) R = fmaf(R, v, P.c[k]);
-        const float S = fmaf(v, R, rinv);    // rinv * Q(u)
-        f = (rinv2 * e) * S;
+        float E = P.c[8], O = P.c[7];
+        E = fmaf(E, r2, P.c[6]); O = fmaf(O, r2, P.c[5]);
+        E = fmaf(E, r2, P.c[4]); O = fmaf(O, r2, P.c[3]);
+        E = fmaf(E, r2, P.c[2]); O = fmaf(O, r2, P.c[1]);
+        E = fmaf(E, r2, fmaf(rinv, rinv, P.c[0]));
+        f = (e * rinv) * fmaf(v, O, E);
     } else {
-        f = rinv2 * rinv;
+        f = (rinv * rinv) * rinv;
     }
     ax = fmaf(dx, f, ax);
     ay = fmaf(dy, f, ay);
     az = fmaf(dz, f, az);
 }
 
-// two targets at once with the sm_100a packed FP32 instructions (FFMA2 / FMUL2 / FADD2)
-// POLY = 0: Horner (8 dependent FFMA2); POLY = 1: even/odd split (one more FMUL2, dependency depth 6,
-// two independent chains)
-template <bool TRUNC, int POLY = 0>
+// two targets at once with the sm_100a packed FP32 instructions (FFMA2 / FMUL2 / FADD2).
+//
+// With Q(u) = 1 + v^2 R(v) (v = r in kernel units, R = c0 + c1 v + ... + c8 v^8) and v * rinv = 1:
+//     f = rinv^3 e Q = (e rinv) (rinv^2 + R(v)),      R(v) = E(w) + v O(w),  w = r^2
+// POLY = 1 (default): E and O are two independent Horner chains in w = r2 (no extra multiply: v^2 = r2 up
+//   to the rsqrt rounding), rinv^2 enters as the constant term of E through one FFMA2 (rinv*rinv + c0), and
+//   the sign MUFU.EX2 needs is produced on the ALU pipe by an FMNMX with negated operands (MUFU has no
+//   negate modifier on sm_100; a multiply by -1 would cost an FP32-pipe slot).
+//   FP32-pipe instructions per packed pair-op: 3 (dx) + 3 (r2) + 1 (v) + 3 (E) + 3 (O) + 1 (c0 + rinv^2)
+//   + 1 (E last) + 1 (T) + 2 (e rinv, f) + 3 (acc) = 21; ALU pipe: 4 FMNMX; XU pipe: 4 MUFU.
+// POLY = 0: the straightforward form (23 FP32-pipe instructions, Horner in v), kept for the sweeps.
+template <bool TRUNC, int POLY = 1>
 __device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty,
                                             float2 tz, float2& ax, float2& ay, float2& az) {
     const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
-    float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-    r2.x = fmaxf(r2.x, P.eps2);
-    r2.y = fmaxf(r2.y, P.eps2);
+    const float2 q2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    float2 r2;
+    r2.x = fmaxf(q2.x, P.eps2);
+    r2.y = fmaxf(q2.y, P.eps2);
     const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-    const float2 rinv2 = __fmul2_rn(rinv, rinv);
     float2 f;
-    if (TRUNC) {
-        // the length unit is 2 r_s / sqrt(log2 e), so exp(-u^2) = 2^(-r2).  MUFU takes no negate modifier on
-        // sm_100 (ptxas materialises it as two scalar FADDs), so the sign costs one packed multiply
+    if (TRUNC && POLY == 1) {
+        // exp(-u^2) = 2^(-r2) in the kernel's length unit; -max(r2, eps2) = min(-r2, -eps2) is one FMNMX
+        const float2 e = make_float2(ex2_approx(neg_min(q2.x, P.neps2)), ex2_approx(neg_min(q2.y, P.neps2)));
+        const float2 v = __fmul2_rn(r2, rinv);
+        float2 E = make_float2(P.c[8], P.c[8]), O = make_float2(P.c[7], P.c[7]);
+        E = __ffma2_rn(E, r2, make_float2(P.c[6], P.c[6]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[5], P.c[5]));
+        E = __ffma2_rn(E, r2, make_float2(P.c[4], P.c[4]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[3], P.c[3]));
+        E = __ffma2_rn(E, r2, make_float2(P.c[2], P.c[2]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[1], P.c[1]));
+        const float2 c0r = __ffma2_rn(rinv, rinv, make_float2(P.c[0], P.c[0]));   // c0 + rinv^2
+        E = __ffma2_rn(E, r2, c0r);
+        const float2 T = __ffma2_rn(v, O, E);                                     // rinv^2 + R(v)
+        f = __fmul2_rn(__fmul2_rn(e, rinv), T);
+    } else if (TRUNC) {
         const float2 a = __fmul2_rn(r2, make_float2(-1.f, -1.f));
         const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
         const float2 v = __fmul2_rn(r2, rinv);
-        float2 R;
-        if (POLY == 0) {
-            R = make_float2(P.c[8], P.c[8]);
+        float2 R = make_float2(P.c[8], P.c[8]);
 #pragma unroll
-            for (int k = 7; k >= 0; k--) R = __ffma2_rn(R, v, make_float2(P.c[k], P.c[k]));
-        } else {
-            // v^2 = r2 * rinv^2 * r2 = r2 (in exact arithmetic v = r); use r2 directly: no extra multiply
-            const float2 w = r2;
-            float2 E = make_float2(P.c[8], P.c[8]), O = make_float2(P.c[7], P.c[7]);
-            E = __ffma2_rn(E, w, make_float2(P.c[6], P.c[6]));
-            O = __ffma2_rn(O, w, make_float2(P.c[5], P.c[5]));
-            E = __ffma2_rn(E, w, make_float2(P.c[4], P.c[4]));
-            O = __ffma2_rn(O, w, make_float2(P.c[3], P.c[3]));
-            E = __ffma2_rn(E, w, make_float2(P.c[2], P.c[2]));
-            O = __ffma2_rn(O, w, make_float2(P.c[1], P.c[1]));
-            E = __ffma2_rn(E, w, make_float2(P.c[0], P.c[0]));
-            R = __ffma2_rn(v, O, E);
-        }
+        for (int k = 7; k >= 0; k--) R = __ffma2_rn(R, v, make_float2(P.c[k], P.c[k]));
         const float2 S = __ffma2_rn(v, R, rinv);
-        f = __fmul2_rn(__fmul2_rn(rinv2, e), S);
+        f = __fmul2_rn(__fmul2_rn(__fmul2_rn(rinv, rinv), e), S);
     } else {
-        f = __fmul2_rn(rinv2, rinv);
+        f = __fmul2_rn(__fmul2_rn(rinv, rinv), rinv);
     }
     ax = __ffma2_rn(dx, f, ax);
     ay = __ffma2_rn(dy, f, ay);
@@ -215,7 +230,7 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, u
 // TT     targets per pass (accumulators in registers); rows with more targets take several passes
 // NSRC   sources per lane per slice (1 or 2)
 // STAGE  particles per staging buffer
-template <int TT, int NSRC, int STAGE, bool TRUNC, bool PACKED, int MINB, int POLY = 0>
+template <int TT, int NSRC, int STAGE, bool TRUNC, bool PACKED, int MINB, int POLY = 1>
 __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -337,26 +352,39 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
                 const int n = cur ? np1 : np0;
                 int pos = 0;
                 for (;;) {                                        // slices; ONE call site of the slice code
-                    const int avail = n - pos;
-                    const bool full = have + avail >= SLICE;
-                    const int take = full ? SLICE - have : avail;
+                    bool run, more_slices;
+                    if (have == 0 && n - pos >= SLICE) {
+                        // fast path: a full slice straight from the stage, no carry bookkeeping
 #pragma unroll
-                    for (int q = 0; q < NSRC; q++) {
-                        const int k = q * 32 + lane - have;       // position of this lane's slot in the new run
-                        if (k >= 0 && k < take) load_source(buf, pos + k, q);
-                    }
-                    pos += take;
-                    have += take;
-                    bool run = full;
-                    if (!full && last_chunk && have > 0) {        // ragged tail of the row: pad with dummies
+                        for (int q = 0; q < NSRC; q++) load_source(buf, pos + q * 32 + lane, q);
+                        pos += SLICE;
+                        run = true;
+                        more_slices = pos < n;
+                    } else {
+                        // chunk boundary: top up the carried slice / keep the leftover for the next chunk
+                        const int avail = n - pos;
+                        const bool full = have + avail >= SLICE;
+                        const int take = full ? SLICE - have : avail;
 #pragma unroll
                         for (int q = 0; q < NSRC; q++) {
-                            if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+                            const int k = q * 32 + lane - have;   // position of this lane's slot in the new run
+                            if (k >= 0 && k < take) load_source(buf, pos + k, q);
                         }
-                        run = true;
+                        pos += take;
+                        have += take;
+                        run = full;
+                        if (!full && last_chunk && have > 0) {    // ragged tail of the row: pad with dummies
+#pragma unroll
+                            for (int q = 0; q < NSRC; q++) {
+                                if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+                            }
+                            run = true;
+                        }
+                        if (run) have = 0;
+                        more_slices = full;
                     }
-                    if (run) { compute_slice(); have = 0; }
-                    if (!full) break;
+                    if (run) compute_slice();
+                    if (!more_slices) break;
                 }
                 __syncwarp();
                 if (last_chunk) break;

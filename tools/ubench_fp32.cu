@@ -39,6 +39,35 @@ __global__ void __launch_bounds__(256) kern(float* out, float seed, long long* c
                 a2[i].x = rsqrtf(a2[i].x); a2[i].y = rsqrtf(a2[i].y);
                 a2[i] = __ffma2_rn(a2[i], b2, c2); a2[i] = __ffma2_rn(a2[i], b2, c2); a2[i] = __ffma2_rn(a2[i], b2, c2);
             }
+            if (MODE == 12) a2[i] = __ffma2_rn(a2[i], a2[(i + 1) % NCHAIN], a2[(i + 3) % NCHAIN]);   // FFMA2, 3 distinct register pairs
+            if (MODE == 13) a[i] = fmaf(a[i], a[(i + 1) % NCHAIN], a[(i + 3) % NCHAIN]);            // FFMA, 3 distinct registers
+            if (MODE == 14) {   // pair-kernel-like packed mix: 11 FFMA2-class (distinct operands) + 1 FMNMX pair + 2 MUFU pairs per 2x... 
+                float2 t = __ffma2_rn(a2[i], a2[(i + 1) % NCHAIN], a2[(i + 3) % NCHAIN]);
+                t = __ffma2_rn(t, a2[(i + 2) % NCHAIN], b2); t = __ffma2_rn(t, a2[(i + 5) % NCHAIN], c2);
+                t.x = fmaxf(t.x, c); t.y = fmaxf(t.y, c);
+                float2 r = make_float2(rsqrtf(t.x), rsqrtf(t.y));
+                float2 e = make_float2(exp2f(-t.x), exp2f(-t.y));
+                float2 w = __fmul2_rn(t, r);
+                float2 E = __ffma2_rn(w, t, b2), O = __ffma2_rn(w, t, c2);
+                E = __ffma2_rn(E, t, c2); O = __ffma2_rn(O, t, b2); E = __ffma2_rn(E, t, b2); O = __ffma2_rn(O, t, c2);
+                E = __ffma2_rn(w, O, E); E = __ffma2_rn(w, E, r);
+                r = __fmul2_rn(r, r); e = __fmul2_rn(r, e); e = __fmul2_rn(e, E);
+                a2[i] = __ffma2_rn(a2[(i + 1) % NCHAIN], e, a2[i]);
+            }
+            if (MODE >= 20 && MODE <= 24) {   // 10 reuse-friendly FFMA2 + (MODE-20) MUFU on a separate chain: pipe interference
+#pragma unroll
+                for (int k = 0; k < 10; k++) a2[i] = __ffma2_rn(a2[i], b2, c2);
+                if (MODE >= 21) a[i] = rsqrtf(a[i]);
+                if (MODE >= 22) a[i] = exp2f(a[i]);
+                if (MODE >= 23) a[i] = rsqrtf(a[i]);
+                if (MODE >= 24) a[i] = exp2f(a[i]);
+            }
+            if (MODE >= 25 && MODE <= 27) {   // 10 FFMA2 + (MODE-25)*2 FMNMX
+#pragma unroll
+                for (int k = 0; k < 10; k++) a2[i] = __ffma2_rn(a2[i], b2, c2);
+                if (MODE >= 26) { a[i] = fmaxf(a[i], a[(i + 1) % NCHAIN]); a[i] = fminf(a[i], a[(i + 2) % NCHAIN]); }
+                if (MODE >= 27) { a[i] = fmaxf(a[i], a[(i + 3) % NCHAIN]); a[i] = fminf(a[i], a[(i + 5) % NCHAIN]); }
+            }
             if (MODE == 10) a[i] = a[i] * b;                              // FMUL
             if (MODE == 11) a[i] = a[i] + b;                              // FADD
         }
@@ -88,5 +117,16 @@ int main() {
     run<7>("FFMA+FMUL+FADD", 3, nsm, d_out, d_cyc);
     run<8>("mix scalar 6F+MNMX+RSQ", 8, nsm, d_out, d_cyc);
     run<9>("mix packed 6F2+2MNMX+2RSQ", 16, nsm, d_out, d_cyc);
+    run<20>("10 FFMA2", 20, nsm, d_out, d_cyc);
+    run<21>("10 FFMA2 + 1 MUFU", 20, nsm, d_out, d_cyc);
+    run<22>("10 FFMA2 + 2 MUFU", 20, nsm, d_out, d_cyc);
+    run<23>("10 FFMA2 + 3 MUFU", 20, nsm, d_out, d_cyc);
+    run<24>("10 FFMA2 + 4 MUFU", 20, nsm, d_out, d_cyc);
+    run<25>("10 FFMA2 + 0 FMNMX", 20, nsm, d_out, d_cyc);
+    run<26>("10 FFMA2 + 2 FMNMX", 20, nsm, d_out, d_cyc);
+    run<27>("10 FFMA2 + 4 FMNMX", 20, nsm, d_out, d_cyc);
+    run<12>("FFMA2 3 distinct reg pairs", 2, nsm, d_out, d_cyc);
+    run<13>("FFMA 3 distinct regs", 1, nsm, d_out, d_cyc);
+    run<14>("pair-like packed (17 F2 + 2 MNMX + 4 MUFU)", 34, nsm, d_out, d_cyc);
     return 0;
 }
