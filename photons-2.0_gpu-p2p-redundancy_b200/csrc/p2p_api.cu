@@ -202,6 +202,7 @@ int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
 template <int TT, bool TRUNC, bool PACKED>
 int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb, int poly) {
     if constexpr (TRUNC && PACKED) {
+        if (poly == 3) return minb == 3 ? launch_rows<TT, 2, true, true, 3, 3>(c, P) : launch_rows<TT, 2, true, true, 4, 3>(c, P);
         if (poly == 1) {
             if (nsrc == 4) return minb == 3 ? launch_rows<TT, 4, true, true, 3, 1>(c, P) : launch_rows<TT, 4, true, true, 4, 1>(c, P);
             return minb == 3 ? launch_rows<TT, 2, true, true, 3, 1>(c, P) : launch_rows<TT, 2, true, true, 4, 1>(c, P);
@@ -294,9 +295,9 @@ int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
 
 int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
     // min_blocks: 3 or 4; adding 16 selects the even/odd split polynomial (sweeps only)
-    const int poly = minb / 16;                 // +16: even/odd split polynomial, +32: breadth-first 4-chain schedule
+    const int poly = minb / 16;                 // +16: split polynomial (21-op form); +48: same with the EX2 sign made on the ALU pipe
     minb %= 16;
-    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4) || poly > 1)
+    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4) || poly > 3 || poly == 2)
         return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16, sources_per_lane 1/2/4, min_blocks 3/4)");
     c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb; c->tune_poly = poly;
     return 0;
@@ -544,7 +545,7 @@ int p2p_compute(p2p_ctx* c) {
         int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
         int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
         int minb = c->tune_minb ? c->tune_minb : 4;
-        const int poly = c->tune_minb ? c->tune_poly : 1;      // default: even/odd split polynomial
+        const int poly = c->tune_minb ? c->tune_poly : 3;      // default: 21-op split polynomial, EX2 sign on the ALU pipe
         if (tt == 8) {
             if (trunc) r = packed ? launch_cfg<8, true, true>(c, P, nsrc, minb, poly) : launch_cfg<8, true, false>(c, P, nsrc, minb, poly);
             else r = packed ? launch_cfg<8, false, true>(c, P, nsrc, minb, poly) : launch_cfg<8, false, false>(c, P, nsrc, minb, poly);

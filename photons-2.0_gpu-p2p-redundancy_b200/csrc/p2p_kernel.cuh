@@ -139,7 +139,7 @@ __device__ __forceinline__ void pair_scalar(const KernelParams& P, float sx, flo
 //   FP32-pipe instructions per packed pair-op: 3 (dx) + 3 (r2) + 1 (v) + 3 (E) + 3 (O) + 1 (c0 + rinv^2)
 //   + 1 (E last) + 1 (T) + 2 (e rinv, f) + 3 (acc) = 21; ALU pipe: 4 FMNMX; XU pipe: 4 MUFU.
 // POLY = 0: the straightforward form (23 FP32-pipe instructions, Horner in v), kept for the sweeps.
-template <bool TRUNC, int POLY = 1>
+template <bool TRUNC, int POLY = 1, int NEGALU = 0>
 __device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty,
                                             float2 tz, float2& ax, float2& ay, float2& az) {
     const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
@@ -151,7 +151,13 @@ __device__ __forceinline__ void pair_packed(const KernelParams& P, float2 sx, fl
     float2 f;
     if (TRUNC && POLY == 1) {
         // exp(-u^2) = 2^(-r2) in the kernel's length unit; -max(r2, eps2) = min(-r2, -eps2) is one FMNMX
-        const float2 e = make_float2(ex2_approx(neg_min(q2.x, P.neps2)), ex2_approx(neg_min(q2.y, P.neps2)));
+        float2 e;
+        if (NEGALU) {
+            e = make_float2(ex2_approx(neg_min(q2.x, P.neps2)), ex2_approx(neg_min(q2.y, P.neps2)));
+        } else {
+            const float2 a = __fmul2_rn(r2, make_float2(-1.f, -1.f));
+            e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        }
         const float2 v = __fmul2_rn(r2, rinv);
         float2 E = make_float2(P.c[8], P.c[8]), O = make_float2(P.c[7], P.c[7]);
         E = __ffma2_rn(E, r2, make_float2(P.c[6], P.c[6]));
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
                                z2 = make_float2(az[2 * p], az[2 * p + 1]);
 #pragma unroll
                         for (int q = 0; q < NSRC; q++)
-                            pair_packed<TRUNC, POLY>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
+                            pair_packed<TRUNC, (POLY & 1), (POLY >> 1)>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
                                                make_float2(txy.x, txy.y), make_float2(txy.z, txy.w), tz, x2, y2, z2);
                         ax[2 * p] = x2.x; ax[2 * p + 1] = x2.y;
                         ay[2 * p] = y2.x; ay[2 * p + 1] = y2.y;

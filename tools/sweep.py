@@ -16,7 +16,7 @@ for maxleaf in (32, 16):
     print(f"maxleaf {maxleaf}: leaves {L.tree.nleaf} tasks {nt} pairs {npairs}", flush=True)
     base = None
     for variant, tt, nsrc, minb in [(1, 16, 2, 4), (2, 16, 1, 3), (2, 16, 1, 4), (2, 16, 2, 3), (2, 16, 2, 4), (2, 16, 4, 3), (2, 16, 4, 4),
-                                    (2, 16, 2, 19), (2, 16, 2, 20), (2, 16, 4, 19), (2, 16, 4, 20), (2, 8, 2, 4), (2, 8, 4, 4), (2, 8, 4, 20)]:
+                                    (2, 16, 2, 19), (2, 16, 2, 20), (2, 16, 4, 19), (2, 16, 4, 20), (2, 8, 2, 4), (2, 8, 4, 4), (2, 8, 4, 20), (2, 16, 2, 51), (2, 16, 2, 52)]:
         st.ctx.set_kernel_variant(variant); st.ctx.set_tuning(tt, nsrc, minb)
         for _ in range(2):
             st.ctx.zero_acc(); st.ctx.compute()
