@@ -228,7 +228,21 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, u
     if (nfit == 0) total = 0;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 16u);
     __syncwarp();
-    if (lane < nfit && cnt > 0) bulk_g2s(stage + (incl - cnt), P.part + start, (uint32_t)cnt * 16u, bar);
+    // Source leaves that follow each other in the particle array (consecutive leaf ids of one tree do)
+    // are merged into ONE bulk copy: the destination is contiguous anyway, and every copy costs ~10
+    // serialised instructions (UBLKCP takes uniform operands, so the lanes issue one after the other).
+    const int prev_end = __shfl_up_sync(0xffffffffu, start + cnt, 1);
+    const bool in_chunk = lane < nfit;
+    const bool head = in_chunk && (lane == 0 || start != prev_end);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    // last lane of my run: the lane before the next head (or the last lane of the chunk)
+    const unsigned later = lane >= 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+    const int last = later ? (__ffs(later) - 2) : (nfit - 1);
+    const int run_end = __shfl_sync(0xffffffffu, incl, (last < 0 ? 0 : last) & 31);
+    if (head) {
+        const int run = run_end - (incl - cnt);
+        if (run > 0) bulk_g2s(stage + (incl - cnt), P.part + start, (uint32_t)run * 16u, bar);
+    }
     e += nfit;
     return total;
 }
