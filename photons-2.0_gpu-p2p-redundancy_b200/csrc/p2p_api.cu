@@ -545,7 +545,7 @@ int p2p_compute(p2p_ctx* c) {
         int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
         int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
         int minb = c->tune_minb ? c->tune_minb : 4;
-        const int poly = c->tune_minb ? c->tune_poly : 3;      // default: 21-op split polynomial, EX2 sign on the ALU pipe
+        const int poly = c->tune_minb ? c->tune_poly : 1;      // default: split polynomial, EX2 sign by a packed multiply (sweep v12)
         if (tt == 8) {
             if (trunc) r = packed ? launch_cfg<8, true, true>(c, P, nsrc, minb, poly) : launch_cfg<8, true, false>(c, P, nsrc, minb, poly);
             else r = packed ? launch_cfg<8, false, true>(c, P, nsrc, minb, poly) : launch_cfg<8, false, false>(c, P, nsrc, minb, poly);

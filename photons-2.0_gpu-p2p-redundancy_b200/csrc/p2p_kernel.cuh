@@ -340,75 +340,75 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
                     }
                 }
             };
-            const int ntp = (nt + 1) >> 1;                     // target pairs of this pass (warp-uniform)
-            auto compute_slice = [&]() {
-                // one indirect branch per slice instead of a guard per target pair
-                switch (ntp) {
-#define P2P_CASE(k) case k: if constexpr (k <= TT / 2) slice_body(std::integral_constant<int, k>{}); break;
-                    P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
-                    P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
-#undef P2P_CASE
-                    default: break;
+            // The whole pass (chunk loop + slice loop) is instantiated per number of target pairs K and
+            // dispatched ONCE per pass, so the slice loop calls straight-line code without any dispatch.
+            auto run_pass = [&](auto kc) {
+                auto compute_slice = [&]() { slice_body(kc); };
+                long long e = e_begin;
+                int np0 = 0, np1 = 0, cur = 0;
+                fence_proxy_async();
+                np0 = issue_chunk<STAGE>(P, S.stage[0], &S.full[0], e, e_end, lane);
+                bool more = e < e_end;
+
+                for (;;) {                                            // chunks of the row
+                    if (more) {
+                        // the other stage was fully consumed (its values are in registers) before this point
+                        fence_proxy_async();
+                        const int n = issue_chunk<STAGE>(P, S.stage[cur ^ 1], &S.full[cur ^ 1], e, e_end, lane);
+                        if (cur) np0 = n; else np1 = n;
+                    }
+                    const bool last_chunk = !more;
+                    more = e < e_end;
+                    if (cur) { mbar_wait(&S.full[1], phase1); phase1 ^= 1u; } else { mbar_wait(&S.full[0], phase0); phase0 ^= 1u; }
+                    const int4* buf = S.stage[cur];
+                    const int n = cur ? np1 : np0;
+                    int pos = 0;
+                    for (;;) {                                        // slices; ONE call site of the slice code
+                        bool run, more_slices;
+                        if (have == 0 && n - pos >= SLICE) {
+                            // fast path: a full slice straight from the stage, no carry bookkeeping
+    #pragma unroll
+                            for (int q = 0; q < NSRC; q++) load_source(buf, pos + q * 32 + lane, q);
+                            pos += SLICE;
+                            run = true;
+                            more_slices = pos < n;
+                        } else {
+                            // chunk boundary: top up the carried slice / keep the leftover for the next chunk
+                            const int avail = n - pos;
+                            const bool full = have + avail >= SLICE;
+                            const int take = full ? SLICE - have : avail;
+    #pragma unroll
+                            for (int q = 0; q < NSRC; q++) {
+                                const int k = q * 32 + lane - have;   // position of this lane's slot in the new run
+                                if (k >= 0 && k < take) load_source(buf, pos + k, q);
+                            }
+                            pos += take;
+                            have += take;
+                            run = full;
+                            if (!full && last_chunk && have > 0) {    // ragged tail of the row: pad with dummies
+    #pragma unroll
+                                for (int q = 0; q < NSRC; q++) {
+                                    if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+                                }
+                                run = true;
+                            }
+                            if (run) have = 0;
+                            more_slices = full;
+                        }
+                        if (run) compute_slice();
+                        if (!more_slices) break;
+                    }
+                    __syncwarp();
+                    if (last_chunk) break;
+                    cur ^= 1;
                 }
             };
-
-            long long e = e_begin;
-            int np0 = 0, np1 = 0, cur = 0;
-            fence_proxy_async();
-            np0 = issue_chunk<STAGE>(P, S.stage[0], &S.full[0], e, e_end, lane);
-            bool more = e < e_end;
-
-            for (;;) {                                            // chunks of the row
-                if (more) {
-                    // the other stage was fully consumed (its values are in registers) before this point
-                    fence_proxy_async();
-                    const int n = issue_chunk<STAGE>(P, S.stage[cur ^ 1], &S.full[cur ^ 1], e, e_end, lane);
-                    if (cur) np0 = n; else np1 = n;
-                }
-                const bool last_chunk = !more;
-                more = e < e_end;
-                if (cur) { mbar_wait(&S.full[1], phase1); phase1 ^= 1u; } else { mbar_wait(&S.full[0], phase0); phase0 ^= 1u; }
-                const int4* buf = S.stage[cur];
-                const int n = cur ? np1 : np0;
-                int pos = 0;
-                for (;;) {                                        // slices; ONE call site of the slice code
-                    bool run, more_slices;
-                    if (have == 0 && n - pos >= SLICE) {
-                        // fast path: a full slice straight from the stage, no carry bookkeeping
-#pragma unroll
-                        for (int q = 0; q < NSRC; q++) load_source(buf, pos + q * 32 + lane, q);
-                        pos += SLICE;
-                        run = true;
-                        more_slices = pos < n;
-                    } else {
-                        // chunk boundary: top up the carried slice / keep the leftover for the next chunk
-                        const int avail = n - pos;
-                        const bool full = have + avail >= SLICE;
-                        const int take = full ? SLICE - have : avail;
-#pragma unroll
-                        for (int q = 0; q < NSRC; q++) {
-                            const int k = q * 32 + lane - have;   // position of this lane's slot in the new run
-                            if (k >= 0 && k < take) load_source(buf, pos + k, q);
-                        }
-                        pos += take;
-                        have += take;
-                        run = full;
-                        if (!full && last_chunk && have > 0) {    // ragged tail of the row: pad with dummies
-#pragma unroll
-                            for (int q = 0; q < NSRC; q++) {
-                                if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
-                            }
-                            run = true;
-                        }
-                        if (run) have = 0;
-                        more_slices = full;
-                    }
-                    if (run) compute_slice();
-                    if (!more_slices) break;
-                }
-                __syncwarp();
-                if (last_chunk) break;
-                cur ^= 1;
+            switch ((nt + 1) >> 1) {                              // target pairs of this pass (warp-uniform)
+#define P2P_CASE(k) case k: if constexpr (k <= TT / 2) run_pass(std::integral_constant<int, k>{}); break;
+                P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
+                P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
+#undef P2P_CASE
+                default: break;
             }
 
             // 32-lane reduction, once per row pass
