@@ -127,6 +127,16 @@ int p2p_step_host(p2p_ctx* ctx, const double* pos, int64_t pos_stride, int64_t n
                   const int* leaf_ipart, int nleaf, const int* tt, const int* ts, int64_t ntask, double* acc,
                   int64_t acc_stride, int accumulate);
 
+/* Pipelined variant: the tasks come in `nchunk` groups (group g = tasks [chunk_off[g], chunk_off[g+1]), e.g. the
+ * target chunks of p2p_walk_plan or the 16384-task flushes of the Redundant walk, 2_Redundant/src/fmm.c:416-418).
+ * While the force kernel of group g runs, the tasks of group g+1 are copied and packed on a second stream
+ * (double-buffered list storage).  Source ids >= nleaf address the ghost leaves of this call.  A target leaf
+ * may appear in several groups: the accelerations accumulate.  Host buffers should be pinned. */
+int p2p_step_host_chunked(p2p_ctx* ctx, const double* pos, int64_t pos_stride, int64_t npart, const int* leaf_npart,
+                          const int* leaf_ipart, int nleaf, const double* ghost_pos, int64_t ghost_stride, int64_t nghost,
+                          const int* ghost_start, const int* ghost_count, int nghostleaf, const int* tt, const int* ts,
+                          const int64_t* chunk_off, int nchunk, double* acc, int64_t acc_stride, int accumulate);
+
 /* raw device pointers for plumbing layers that keep data on the GPU (torch / NCCL) */
 void* p2p_device_particles(p2p_ctx* ctx);   /* int4[npart + nghost], fixed-point */
 void* p2p_device_acc(p2p_ctx* ctx);         /* float4[npart], accelerations in .xyz */

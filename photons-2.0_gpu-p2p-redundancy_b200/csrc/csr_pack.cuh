@@ -17,14 +17,27 @@ namespace p2p {
 // Counts tasks per target leaf.  Task ids are validated HERE (the host never walks the list): a task
 // outside [0,nrow) x [0,nsrc) raises *bad and is dropped by the scatter as well.
 __global__ void csr_count_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
-                                 unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad) {
+                                 unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad,
+                                 unsigned int* __restrict__ row_min, unsigned int* __restrict__ row_max) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int lo = 0xffffffffu, hi = 0u;
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
-        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) atomicAdd(cnt + t, 1u);
-        else atomicAdd(bad, 1u);
+        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) {
+            atomicAdd(cnt + t, 1u);
+            lo = min(lo, (unsigned)t);
+            hi = max(hi, (unsigned)t);
+        } else {
+            atomicAdd(bad, 1u);
+        }
     }
+    // range of target rows this list touches: the force kernel only schedules rows in [row_min, row_max]
+    for (int d = 16; d >= 1; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0 && lo != 0xffffffffu) { atomicMin(row_min, lo); atomicMax(row_max, hi); }
 }
 
 // three-phase exclusive scan of unsigned counts into 64-bit offsets

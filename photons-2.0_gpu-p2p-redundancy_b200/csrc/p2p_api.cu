@@ -94,6 +94,16 @@ struct p2p_ctx {
     long long acc_tasks = 0;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+    // second set of list buffers + copy stream for the chunk-pipelined step (p2p_step_host_chunked)
+    DevBuf<int> tt2, ts2, col2;
+    DevBuf<long long> row_ptr2;
+    DevBuf<unsigned int> cnt2;
+    DevBuf<unsigned long long> cursor2, tile2;
+    unsigned int* d_counter2 = nullptr;
+    unsigned int* d_bad = nullptr;          // tasks with ids out of range, summed over every packed list
+    unsigned long long* d_npairs2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_ready = nullptr;
     unsigned int* h_flags = nullptr;        // pinned copy of d_counter after build_csr
     bool flags_pending = false;
     DevBuf<double> acc64;
@@ -252,7 +262,17 @@ int p2p_create(p2p_ctx** out, int device) {
     CU(cudaMalloc(&c->d_counter, 4 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_npairs, 2 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_npairs, 0, 2 * sizeof(unsigned long long)));
-    CU(cudaMallocHost(&c->h_flags, 4 * sizeof(unsigned int)));
+    CU(cudaMallocHost(&c->h_flags, 8 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_counter2, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_bad, sizeof(unsigned int)));
+    CU(cudaMemset(c->d_bad, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_npairs2, sizeof(unsigned long long)));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreate(&c->ev2));
@@ -272,6 +292,13 @@ int p2p_destroy(p2p_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     c->acc64.release();
+    c->tt2.release(); c->ts2.release(); c->col2.release(); c->row_ptr2.release(); c->cnt2.release(); c->cursor2.release(); c->tile2.release();
+    if (c->d_counter2) cudaFree(c->d_counter2);
+    if (c->d_bad) cudaFree(c->d_bad);
+    if (c->d_npairs2) cudaFree(c->d_npairs2);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < 2; k++) { if (c->ev_packed[k]) cudaEventDestroy(c->ev_packed[k]); if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]); }
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -451,46 +478,74 @@ int p2p_append_tasks_interleaved(p2p_ctx* c, const int* pairs, int64_t n, int of
     return 0;
 }
 
+namespace {
+struct ListSet {                       // one set of task / CSR buffers (the context owns two)
+    DevBuf<int>*tt, *ts, *col;
+    DevBuf<long long>* row_ptr;
+    DevBuf<unsigned int>* cnt;
+    DevBuf<unsigned long long>*cursor, *tile;
+    unsigned int* d_counter;           // [0] row scheduler, [1] unsorted rows, [2] first row with tasks, [3] last row
+    unsigned long long* d_npairs;
+};
+ListSet list_set(p2p_ctx* c, int k) {
+    if (k == 0) return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, c->d_counter, c->d_npairs};
+    return ListSet{&c->tt2, &c->ts2, &c->col2, &c->row_ptr2, &c->cnt2, &c->cursor2, &c->tile2, c->d_counter2, c->d_npairs2};
+}
+
+int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
+    const int nrow = c->nleaf;
+    CU(L.row_ptr->reserve((size_t)nrow + 2, st));
+    CU(L.cnt->reserve((size_t)nrow + 1, st));
+    CU(L.cursor->reserve((size_t)nrow + 1, st));
+    CU(L.col->reserve((size_t)n + 1, st));
+    CU(L.tile->reserve((size_t)((nrow + p2p::kScanTile - 1) / p2p::kScanTile) + 1, st));
+    return 0;
+}
+
+// count -> scan -> scatter -> sort -> pair count of the n tasks in L.tt / L.ts, all on stream st
+int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
+    const int nrow = c->nleaf;
+    int r = reserve_csr(c, L, n, st);
+    if (r) return r;
+    const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
+    CU(cudaMemsetAsync(L.cnt->p, 0, ((size_t)nrow + 1) * 4, st));
+    CU(cudaMemsetAsync(L.d_counter, 0, 4 * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(L.d_counter + 2, 0xff, sizeof(unsigned int), st));      // [2] first row with tasks, [3] last
+    CU(cudaMemsetAsync(L.d_npairs, 0, sizeof(unsigned long long), st));
+    if (nrow == 0) {
+        CU(cudaMemsetAsync(L.row_ptr->p, 0, sizeof(long long), st));
+        if (n > 0) CU(cudaMemsetAsync(c->d_bad, 0xff, sizeof(unsigned int), st));          // every task is out of range
+        return 0;
+    }
+    const int G = c->num_sm * 8;
+    const int nsrc = c->nleaf + c->nghostleaf;
+    if (n) {
+        p2p::csr_count_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cnt->p, c->d_bad, L.d_counter + 2,
+                                                 L.d_counter + 3);
+        CU(cudaGetLastError());
+    }
+    p2p::scan_tile_sums_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p);
+    p2p::scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(L.tile->p, ntile);
+    p2p::scan_apply_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p, L.row_ptr->p, L.cursor->p);
+    CU(cudaGetLastError());
+    if (n) {
+        p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p);
+        p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p, nrow, L.col->p, L.d_counter + 1);
+        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+}  // namespace
+
 int p2p_build_csr(p2p_ctx* c) {
     USE(c);
-    const int nrow = c->nleaf;
-    const long long n = c->ntask;
     CU(cudaEventRecord(c->ev2, c->stream));
-    CU(c->row_ptr.reserve((size_t)nrow + 2, c->stream));
-    CU(c->cnt.reserve((size_t)nrow + 1, c->stream));
-    CU(c->cursor.reserve((size_t)nrow + 1, c->stream));
-    CU(c->col.reserve((size_t)n + 1, c->stream));
-    const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
-    CU(c->tile.reserve((size_t)ntile + 1, c->stream));
-    CU(cudaMemsetAsync(c->cnt.p, 0, ((size_t)nrow + 1) * 4, c->stream));
-    CU(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned int), c->stream));
-    CU(cudaMemsetAsync(c->d_npairs, 0, sizeof(unsigned long long), c->stream));
-    if (nrow == 0) {
-        CU(cudaMemsetAsync(c->row_ptr.p, 0, sizeof(long long), c->stream));
-    } else {
-        const int G = c->num_sm * 8;
-        if (n) {
-            p2p::csr_count_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, nrow, c->nleaf + c->nghostleaf, c->cnt.p,
-                                                            c->d_counter + 2);
-            CU(cudaGetLastError());
-        }
-        p2p::scan_tile_sums_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p);
-        p2p::scan_tile_offsets_kernel<<<1, 1024, 0, c->stream>>>(c->tile.p, ntile);
-        p2p::scan_apply_kernel<<<ntile, 256, 0, c->stream>>>(c->cnt.p, nrow, c->tile.p, c->row_ptr.p, c->cursor.p);
-        CU(cudaGetLastError());
-        if (n) {
-            p2p::csr_scatter_kernel<<<G, 256, 0, c->stream>>>(c->tt.p, c->ts.p, n, nrow, c->nleaf + c->nghostleaf, c->cursor.p,
-                                                              c->col.p);
-            p2p::csr_sort_rows_kernel<<<G, 128, 0, c->stream>>>(c->row_ptr.p, nrow, c->col.p, c->d_counter + 1);
-            p2p::pair_count_kernel<<<G, 256, 0, c->stream>>>(c->row_ptr.p, c->col.p, c->leaf.p, nrow, c->d_npairs);
-            CU(cudaGetLastError());
-        }
-    }
-    if (nrow == 0 && n > 0) {
-        // no rows at all: every task is out of range
-        CU(cudaMemsetAsync(c->d_counter + 2, 0xff, sizeof(unsigned int), c->stream));
-    }
-    CU(cudaMemcpyAsync(c->h_flags, c->d_counter, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    const ListSet L = list_set(c, 0);
+    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(unsigned int), c->stream));
+    int r = pack_csr(c, L, c->ntask, c->stream);
+    if (r) return r;
+    CU(cudaMemcpyAsync(c->h_flags + 2, c->d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev3, c->stream));
     c->timed_csr = true;
     c->csr_valid = true;
@@ -512,14 +567,14 @@ static int check_flags(p2p_ctx* c) {
     return 0;
 }
 
-int p2p_compute(p2p_ctx* c) {
-    USE(c);
-    if (!c->csr_valid) return fail(P2P_ERR_STATE, "p2p_compute before p2p_build_csr");
+namespace {
+// launches the force kernel over the CSR of L on stream st and adds its pair count to the running total
+int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st) {
     if (c->max_target_leaf > P2P_MAX_LEAF) return fail(P2P_ERR_ARG, "target leaves above %d particles are not supported", P2P_MAX_LEAF);
     p2p::KernelParams P;
     memset(&P, 0, sizeof P);
-    P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = c->row_ptr.p; P.col = c->col.p; P.acc = c->acc.p;
-    P.counter = c->d_counter; P.nrow = c->nleaf;
+    P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = L.row_ptr->p; P.col = L.col->p; P.acc = c->acc.p;
+    P.counter = L.d_counter; P.row_range = L.d_counter + 2; P.nrow = c->nleaf;
     const bool trunc = c->rs > 0.0;
     // kernel length unit: 2 r_s / sqrt(log2 e) for the truncated kernel (then exp(-u^2) = 2^(-r'^2) and the
     // polynomial argument is r' = u sqrt(log2 e)), the box extent otherwise
@@ -536,16 +591,17 @@ int p2p_compute(p2p_ctx* c) {
         P.far_coord = 1.0e18f;
     }
     P.out_scale = (float)(c->mass / (unit * unit));
-    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
-    CU(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaMemsetAsync(L.d_counter, 0, sizeof(unsigned int), st));
     int r = 0;
-    if (c->nleaf > 0 && c->ntask > 0) {
+    if (c->nleaf > 0 && ntask > 0) {
         const bool packed = c->variant != P2P_KERNEL_SCALAR;
         // defaults from the 128^3 sweeps (profiles/): 16 targets per pass, 2 sources per lane, 4 blocks / SM
         int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
         int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
         int minb = c->tune_minb ? c->tune_minb : 4;
         const int poly = c->tune_minb ? c->tune_poly : 1;      // default: split polynomial, EX2 sign by a packed multiply (sweep v12)
+        cudaStream_t keep = c->stream;
+        c->stream = st;                                         // launch_rows launches on c->stream
         if (tt == 8) {
             if (trunc) r = packed ? launch_cfg<8, true, true>(c, P, nsrc, minb, poly) : launch_cfg<8, true, false>(c, P, nsrc, minb, poly);
             else r = packed ? launch_cfg<8, false, true>(c, P, nsrc, minb, poly) : launch_cfg<8, false, false>(c, P, nsrc, minb, poly);
@@ -553,13 +609,24 @@ int p2p_compute(p2p_ctx* c) {
             if (trunc) r = packed ? launch_cfg<16, true, true>(c, P, nsrc, minb, poly) : launch_cfg<16, true, false>(c, P, nsrc, minb, poly);
             else r = packed ? launch_cfg<16, false, true>(c, P, nsrc, minb, poly) : launch_cfg<16, false, false>(c, P, nsrc, minb, poly);
         }
+        c->stream = keep;
     }
+    if (r) return r;
+    p2p::add_counter_kernel<<<1, 32, 0, st>>>(L.d_npairs, c->d_npairs + 1);   // no host sync
+    CU(cudaGetLastError());
+    c->acc_tasks += ntask;
+    return 0;
+}
+}  // namespace
+
+int p2p_compute(p2p_ctx* c) {
+    USE(c);
+    if (!c->csr_valid) return fail(P2P_ERR_STATE, "p2p_compute before p2p_build_csr");
+    CU(cudaEventRecord(c->ev0, c->stream));
+    int r = launch_force(c, list_set(c, 0), c->ntask, c->stream);
     if (r) return r;
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timed_compute = true;
-    p2p::add_counter_kernel<<<1, 32, 0, c->stream>>>(c->d_npairs, c->d_npairs + 1);   // no host sync
-    CU(cudaGetLastError());
-    c->acc_tasks += c->ntask;
     return 0;
 }
 
@@ -666,6 +733,60 @@ int p2p_step_host(p2p_ctx* c, const double* pos, int64_t pos_stride, int64_t npa
     if ((r = p2p_append_tasks(c, tt, ts, ntask, 0))) return r;
     if ((r = p2p_build_csr(c))) return r;
     if ((r = p2p_compute(c))) return r;
+    return p2p_download_acc(c, acc, acc_stride, accumulate);
+}
+
+int p2p_step_host_chunked(p2p_ctx* c, const double* pos, int64_t pos_stride, int64_t npart, const int* leaf_npart,
+                          const int* leaf_ipart, int nleaf, const double* ghost_pos, int64_t ghost_stride, int64_t nghost,
+                          const int* ghost_start, const int* ghost_count, int nghostleaf, const int* tt, const int* ts,
+                          const int64_t* chunk_off, int nchunk, double* acc, int64_t acc_stride, int accumulate) {
+    USE(c);
+    if (nchunk < 0 || (nchunk && (!chunk_off || !tt || !ts))) return fail(P2P_ERR_ARG, "bad chunk arrays");
+    int r;
+    if ((r = p2p_upload_particles(c, pos, pos_stride, npart))) return r;
+    if ((r = p2p_upload_leaves(c, leaf_npart, leaf_ipart, nleaf))) return r;
+    if (nghostleaf > 0 || nghost > 0) {
+        int first = 0;
+        if ((r = p2p_append_ghosts(c, ghost_pos, ghost_stride, nghost, ghost_start, ghost_count, nghostleaf, &first))) return r;
+    }
+    cudaStream_t S0 = c->stream, S1 = c->copy_stream;
+    long long maxn = 0;
+    for (int g = 0; g < nchunk; g++) {
+        if (chunk_off[g + 1] < chunk_off[g]) return fail(P2P_ERR_ARG, "chunk offsets must be non-decreasing");
+        maxn = std::max<long long>(maxn, chunk_off[g + 1] - chunk_off[g]);
+    }
+    // both buffer sets are sized up front: nothing may be reallocated while the pipeline is in flight
+    for (int k = 0; k < 2; k++) {
+        const ListSet L = list_set(c, k);
+        CU(L.tt->reserve((size_t)maxn + 1, S0));
+        CU(L.ts->reserve((size_t)maxn + 1, S0));
+        if ((r = reserve_csr(c, L, maxn, S0))) return r;
+    }
+    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(unsigned int), S0));
+    CU(cudaEventRecord(c->ev_ready, S0));                    // particles, leaves and ghosts are queued on S0
+    CU(cudaStreamWaitEvent(S1, c->ev_ready, 0));
+    CU(cudaEventRecord(c->ev0, S0));
+    for (int g = 0; g < nchunk; g++) {
+        const int b = g & 1;
+        const ListSet L = list_set(c, b);
+        const long long n = chunk_off[g + 1] - chunk_off[g];
+        if (g >= 2) CU(cudaStreamWaitEvent(S1, c->ev_done[b], 0));      // the kernel of chunk g-2 has released set b
+        if (n) {
+            CU(cudaMemcpyAsync(L.tt->p, tt + chunk_off[g], (size_t)n * 4, cudaMemcpyHostToDevice, S1));
+            CU(cudaMemcpyAsync(L.ts->p, ts + chunk_off[g], (size_t)n * 4, cudaMemcpyHostToDevice, S1));
+        }
+        if ((r = pack_csr(c, L, n, S1))) return r;
+        CU(cudaEventRecord(c->ev_packed[b], S1));
+        CU(cudaStreamWaitEvent(S0, c->ev_packed[b], 0));                 // copy + packing of chunk g overlapped kernel g-1
+        if ((r = launch_force(c, L, n, S0))) return r;
+        CU(cudaEventRecord(c->ev_done[b], S0));
+    }
+    CU(cudaEventRecord(c->ev1, S0));
+    c->timed_compute = true;
+    c->csr_valid = false;                                   // the resident CSR is only the last chunk's
+    c->ntask = 0;
+    CU(cudaMemcpyAsync(c->h_flags + 2, c->d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, S0));
+    c->flags_pending = true;
     return p2p_download_acc(c, acc, acc_stride, accumulate);
 }
 

@@ -64,6 +64,8 @@ def load_library():
     L.p2p_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.p2p_step_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _ip, _ip, C.c_int64, _dp,
                                 C.c_int64, C.c_int]
+    L.p2p_step_host_chunked.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _dp, C.c_int64, C.c_int64, _ip,
+                                        _ip, C.c_int, _ip, _ip, _lp, C.c_int, _dp, C.c_int64, C.c_int]
     L.p2p_device_particles.argtypes = [C.c_void_p]
     L.p2p_device_acc.argtypes = [C.c_void_p]
     _lib = L
@@ -221,6 +223,27 @@ class P2PContext:
                                         n.ctypes.data_as(_ip), i.ctypes.data_as(_ip), len(n), tt.ctypes.data_as(_ip),
                                         ts.ctypes.data_as(_ip), len(tt), acc.ctypes.data_as(_dp), acc.shape[1],
                                         1 if accumulate else 0))
+        self.npart, self.nleaf = pos.shape[0], len(n)
+        return acc
+
+    def step_host_chunked(self, pos, leaf_npart, leaf_ipart, tt, ts, chunk_off, ghost_pos=None, ghost_start=None,
+                          ghost_count=None, acc=None, accumulate=False):
+        """Chunk-pipelined host step: H2D + packing of chunk g+1 overlap the kernel of chunk g.
+        Arrays are used as given (no copies): pass pinned, contiguous arrays of the right dtype."""
+        assert pos.dtype == np.float64 and tt.dtype == np.int32 and ts.dtype == np.int32
+        off = np.ascontiguousarray(chunk_off, np.int64)
+        n, i = _i32(leaf_npart), _i32(leaf_ipart)
+        if ghost_pos is None or len(ghost_start) == 0:
+            gp, gs, gc = np.zeros((0, 3)), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        else:
+            gp, gs, gc = _f64(ghost_pos).reshape(-1, 3), _i32(ghost_start), _i32(ghost_count)
+        if acc is None:
+            acc = np.zeros((pos.shape[0], 3))
+        self._chk(self._L.p2p_step_host_chunked(
+            self._h, pos.ctypes.data_as(_dp), pos.shape[1], pos.shape[0], n.ctypes.data_as(_ip), i.ctypes.data_as(_ip), len(n),
+            gp.ctypes.data_as(_dp), 3, gp.shape[0], gs.ctypes.data_as(_ip), gc.ctypes.data_as(_ip), len(gs),
+            tt.ctypes.data_as(_ip), ts.ctypes.data_as(_ip), off.ctypes.data_as(_lp), len(off) - 1, acc.ctypes.data_as(_dp),
+            acc.shape[1], 1 if accumulate else 0))
         self.npart, self.nleaf = pos.shape[0], len(n)
         return acc
 

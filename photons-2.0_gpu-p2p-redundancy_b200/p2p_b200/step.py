@@ -38,11 +38,14 @@ class HostLists:
         self.ghost_count = np.zeros(0, np.int32)
         self.gtt = np.zeros(0, np.int32)         # ghost tasks: target leaf, ghost leaf (batch-relative id)
         self.gts = np.zeros(0, np.int32)
+        self.chunk_off = None                    # task offsets of the list groups (None: one group)
         self.timings = {}
 
 
-def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, domain_box=None, direct_start=0):
-    """Single-rank producer: local tree + local list + (optionally) the 26 periodic-image ghost lists."""
+def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, domain_box=None, direct_start=0, nchunks=0):
+    """Single-rank producer: local tree + local list + (optionally) the 26 periodic-image ghost lists.
+    nchunks > 0: the local list is produced by the chunked walk plan (same task multiset, grouped by target
+    chunk) and `chunk_off` gives the task offsets of the groups, for the chunk-pipelined device step."""
     rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
     out = HostLists()
     t0 = time.perf_counter()
@@ -52,7 +55,15 @@ def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, 
     out.tree = T
     if periodic:
         check_wrap_condition(T, box, rcut, "build_lists")
-    out.tt, out.ts = T.walk_task_p2p(theta, rcut, nthreads)
+    if nchunks > 0:
+        plan = T.walk_plan(theta, rcut, nchunks)
+        parts = [plan.run(c, nthreads) for c in range(plan.nchunks)]
+        out.tt = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.int32)
+        out.ts = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int32)
+        out.chunk_off = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])]).astype(np.int64)
+    else:
+        out.tt, out.ts = T.walk_task_p2p(theta, rcut, nthreads)
+        out.chunk_off = np.array([0, len(out.tt)], np.int64)
     t2 = time.perf_counter()
     if periodic:
         gp, gs, gc, gtt, gts = [], [], [], [], []
@@ -85,6 +96,19 @@ def build_lists(pos, box, maxleaf, nside, theta=0.4, periodic=True, nthreads=0, 
     out.timings = dict(build_s=t1 - t0, walk_s=t2 - t1, images_s=t3 - t2)
     out.params = dict(rs=rs, rcut=rcut, eps=eps, box=box)
     return out
+
+
+def chunked_task_arrays(lists):
+    """(tt, ts, chunk_off) for P2PContext.step_host_chunked: the local groups followed by ONE group holding
+    the ghost tasks, whose source ids are made absolute (ghost leaf g -> nleaf + g)."""
+    T = lists.tree
+    off0 = lists.chunk_off if lists.chunk_off is not None else np.array([0, len(lists.tt)], np.int64)
+    if len(lists.gtt) == 0:
+        return lists.tt, lists.ts, off0
+    tt = np.concatenate([lists.tt, lists.gtt]).astype(np.int32)
+    ts = np.concatenate([lists.ts, lists.gts + T.nleaf]).astype(np.int32)
+    off = np.concatenate([off0, [len(tt)]]).astype(np.int64)
+    return tt, ts, off
 
 
 class ShortRangeStep:

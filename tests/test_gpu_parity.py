@@ -202,3 +202,29 @@ def test_walk_compute_pipeline(demo_pos, pipelined):
     nr = np.linalg.norm(ref, axis=1)
     assert (np.linalg.norm(acc - ref, axis=1) / np.maximum(nr, nr.mean())).max() < TOL
     ctx.close()
+
+
+def test_chunk_pipelined_host_step(demo_pos):
+    """p2p_step_host_chunked (H2D + packing of group g+1 on a copy stream while the kernel of group g runs,
+    double-buffered lists) == oracle; also with the tasks in ONE group and with empty groups."""
+    L = step.build_lists(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, periodic=True, nchunks=8)
+    tt, ts, off = step.chunked_task_arrays(L)
+    assert len(off) - 1 >= 5
+    ref, rtask, rpairs = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, 1, True)
+    T = L.tree
+    ctx = p2p_b200.P2PContext(0)
+    for offs in (off, np.array([0, len(tt)], np.int64), np.array([0, 0, off[2], off[2], len(tt)], np.int64)):
+        ctx.set_physics(DEMO_MASS, L.params["eps"], L.params["rs"])
+        ctx.set_box([0.0, 0.0, 0.0], DEMO_BOX)
+        acc_t = ctx.step_host_chunked(T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, offs, L.ghost_pos, L.ghost_start, L.ghost_count)
+        assert ctx.accumulated_counts() == (rtask, rpairs)
+        acc = np.empty_like(acc_t)
+        acc[T.perm] = acc_t
+        nr = np.linalg.norm(ref, axis=1)
+        assert (np.linalg.norm(acc - ref, axis=1) / np.maximum(nr, nr.mean())).max() < TOL
+    # a bad task id is still reported
+    bad = ts.copy()
+    bad[5] = 10 ** 8
+    with pytest.raises(p2p_b200.P2PError):
+        ctx.step_host_chunked(T.pos, T.leaf_npart, T.leaf_ipart, tt, bad, off, L.ghost_pos, L.ghost_start, L.ghost_count)
+    ctx.close()
