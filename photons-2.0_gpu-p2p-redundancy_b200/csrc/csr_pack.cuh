@@ -17,27 +17,14 @@ namespace p2p {
 // Counts tasks per target leaf.  Task ids are validated HERE (the host never walks the list): a task
 // outside [0,nrow) x [0,nsrc) raises *bad and is dropped by the scatter as well.
 __global__ void csr_count_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
-                                 unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad,
-                                 unsigned int* __restrict__ row_min, unsigned int* __restrict__ row_max) {
+                                 unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    unsigned int lo = 0xffffffffu, hi = 0u;
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
-        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) {
-            atomicAdd(cnt + t, 1u);
-            lo = min(lo, (unsigned)t);
-            hi = max(hi, (unsigned)t);
-        } else {
-            atomicAdd(bad, 1u);
-        }
+        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) atomicAdd(cnt + t, 1u);
+        else atomicAdd(bad, 1u);
     }
-    // range of target rows this list touches: the force kernel only schedules rows in [row_min, row_max]
-    for (int d = 16; d >= 1; d >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-    }
-    if ((threadIdx.x & 31) == 0 && lo != 0xffffffffu) { atomicMin(row_min, lo); atomicMax(row_max, hi); }
 }
 
 // three-phase exclusive scan of unsigned counts into 64-bit offsets
@@ -166,10 +153,14 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
     }
 }
 
-// sum over tasks of n_t * n_s: the pair-interaction count of the metric
+// sum over tasks of n_t * n_s: the pair-interaction count of the metric; also records
+// every row's work and a histogram of the target occupancy n_t for the row schedule
+constexpr int kWorkBuckets = 64;
 __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col,
                                                          const int2* __restrict__ leaf, int nrow,
-                                                         unsigned long long* __restrict__ npairs) {
+                                                         unsigned long long* __restrict__ npairs,
+                                                         unsigned long long* __restrict__ row_work,
+                                                         unsigned int* __restrict__ hist) {
     unsigned long long s = 0;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -178,10 +169,38 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
         const unsigned long long nt = (unsigned long long)leaf[row].y;
         unsigned long long ns = 0;
         for (long long i = b + lane; i < e; i += 32) ns += (unsigned long long)leaf[col[i]].y;
-        s += nt * ns;
+        for (int d = 16; d >= 1; d >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, d);
+        const unsigned long long w = nt * ns;
+        if (lane == 0) {
+            row_work[row] = w;
+            if (w) atomicAdd(hist + min((int)nt, kWorkBuckets - 1), 1u);
+            s += w;
+        }
     }
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (lane == 0 && s) atomicAdd(npairs, s);
+}
+
+// Row schedule: only rows that have work, ordered by target occupancy n_t (fullest leaves first, row order
+// within one occupancy).  The force kernel instantiates its slice code per number of target pairs; with rows
+// in arbitrary order the 16 resident warps of an SM run up to 8 different ~7 KB code bodies at once and the
+// instruction cache thrashes (ncu on the clustered box: stall_no_instruction 9.5 per issue, issue rate
+// halved).  Grouping rows by n_t makes the whole chip run the same one or two bodies at any time; the
+// fullest (most expensive) rows go first, so the tail of the persistent kernel consists of cheap rows.
+__global__ void work_bucket_offsets_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor,
+                                           unsigned int* __restrict__ n_active) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned int run = 0;
+        for (int b = kWorkBuckets - 1; b >= 0; b--) { cursor[b] = run; run += hist[b]; }
+        *n_active = run;
+    }
+}
+__global__ void work_order_scatter_kernel(const unsigned long long* __restrict__ row_work, const int2* __restrict__ nt_of,
+                                          int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < nrow) {
+        const unsigned long long w = row_work[row];
+        if (w) order[atomicAdd(cursor + min(nt_of[row].y, kWorkBuckets - 1), 1u)] = row;
+    }
 }
 
 __global__ void add_counter_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst) {

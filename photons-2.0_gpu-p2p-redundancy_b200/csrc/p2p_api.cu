@@ -87,7 +87,9 @@ struct p2p_ctx {
     DevBuf<int> tt, ts, col, itmp;
     DevBuf<long long> row_ptr;
     DevBuf<unsigned int> cnt;
-    DevBuf<unsigned long long> cursor, tile;
+    DevBuf<unsigned long long> cursor, tile, row_work, row_work2;
+    DevBuf<int> order, order2;
+    DevBuf<unsigned int> whist, whist2;     // [0,64) histogram of log2(row work), [64,128) bucket cursors
     DevBuf<unsigned char> stage;
     unsigned int* d_counter = nullptr;      // [0] row scheduler, [1] unsorted rows
     unsigned long long* d_npairs = nullptr;      // [0] pairs of the current CSR, [1] pairs accumulated into acc
@@ -292,6 +294,7 @@ int p2p_destroy(p2p_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     c->acc64.release();
+    c->row_work.release(); c->row_work2.release(); c->order.release(); c->order2.release(); c->whist.release(); c->whist2.release();
     c->tt2.release(); c->ts2.release(); c->col2.release(); c->row_ptr2.release(); c->cnt2.release(); c->cursor2.release(); c->tile2.release();
     if (c->d_counter2) cudaFree(c->d_counter2);
     if (c->d_bad) cudaFree(c->d_bad);
@@ -483,13 +486,18 @@ struct ListSet {                       // one set of task / CSR buffers (the con
     DevBuf<int>*tt, *ts, *col;
     DevBuf<long long>* row_ptr;
     DevBuf<unsigned int>* cnt;
-    DevBuf<unsigned long long>*cursor, *tile;
-    unsigned int* d_counter;           // [0] row scheduler, [1] unsorted rows, [2] first row with tasks, [3] last row
+    DevBuf<unsigned long long>*cursor, *tile, *row_work;
+    DevBuf<int>* order;
+    DevBuf<unsigned int>* whist;
+    unsigned int* d_counter;           // [0] row scheduler, [1] unsorted rows, [2] rows in the work-ordered schedule
     unsigned long long* d_npairs;
 };
 ListSet list_set(p2p_ctx* c, int k) {
-    if (k == 0) return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, c->d_counter, c->d_npairs};
-    return ListSet{&c->tt2, &c->ts2, &c->col2, &c->row_ptr2, &c->cnt2, &c->cursor2, &c->tile2, c->d_counter2, c->d_npairs2};
+    if (k == 0)
+        return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, &c->row_work, &c->order, &c->whist,
+                       c->d_counter, c->d_npairs};
+    return ListSet{&c->tt2, &c->ts2, &c->col2, &c->row_ptr2, &c->cnt2, &c->cursor2, &c->tile2, &c->row_work2, &c->order2, &c->whist2,
+                   c->d_counter2, c->d_npairs2};
 }
 
 int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
@@ -499,6 +507,9 @@ int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     CU(L.cursor->reserve((size_t)nrow + 1, st));
     CU(L.col->reserve((size_t)n + 1, st));
     CU(L.tile->reserve((size_t)((nrow + p2p::kScanTile - 1) / p2p::kScanTile) + 1, st));
+    CU(L.row_work->reserve((size_t)nrow + 1, st));
+    CU(L.order->reserve((size_t)nrow + 1, st));
+    CU(L.whist->reserve(2 * p2p::kWorkBuckets, st));
     return 0;
 }
 
@@ -510,7 +521,7 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
     CU(cudaMemsetAsync(L.cnt->p, 0, ((size_t)nrow + 1) * 4, st));
     CU(cudaMemsetAsync(L.d_counter, 0, 4 * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(L.d_counter + 2, 0xff, sizeof(unsigned int), st));      // [2] first row with tasks, [3] last
+    CU(cudaMemsetAsync(L.whist->p, 0, 2 * p2p::kWorkBuckets * sizeof(unsigned int), st));
     CU(cudaMemsetAsync(L.d_npairs, 0, sizeof(unsigned long long), st));
     if (nrow == 0) {
         CU(cudaMemsetAsync(L.row_ptr->p, 0, sizeof(long long), st));
@@ -520,8 +531,7 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     const int G = c->num_sm * 8;
     const int nsrc = c->nleaf + c->nghostleaf;
     if (n) {
-        p2p::csr_count_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cnt->p, c->d_bad, L.d_counter + 2,
-                                                 L.d_counter + 3);
+        p2p::csr_count_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cnt->p, c->d_bad);
         CU(cudaGetLastError());
     }
     p2p::scan_tile_sums_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p);
@@ -531,7 +541,10 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     if (n) {
         p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p);
         p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p, nrow, L.col->p, L.d_counter + 1);
-        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs);
+        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p);
+        p2p::work_bucket_offsets_kernel<<<1, 32, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets, L.d_counter + 2);
+        p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p, c->leaf.p, nrow,
+                                                                          L.whist->p + p2p::kWorkBuckets, L.order->p);
         CU(cudaGetLastError());
     }
     return 0;
@@ -574,7 +587,7 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     p2p::KernelParams P;
     memset(&P, 0, sizeof P);
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = L.row_ptr->p; P.col = L.col->p; P.acc = c->acc.p;
-    P.counter = L.d_counter; P.row_range = L.d_counter + 2; P.nrow = c->nleaf;
+    P.counter = L.d_counter; P.n_active = L.d_counter + 2; P.row_order = L.order->p; P.nrow = c->nleaf;
     const bool trunc = c->rs > 0.0;
     // kernel length unit: 2 r_s / sqrt(log2 e) for the truncated kernel (then exp(-u^2) = 2^(-r'^2) and the
     // polynomial argument is r' = u sqrt(log2 e)), the box extent otherwise

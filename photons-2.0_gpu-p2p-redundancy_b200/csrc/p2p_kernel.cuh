@@ -50,7 +50,8 @@ struct KernelParams {
     const int* col;          // source leaf ids, ascending within a row
     float4* acc;             // per local particle, accumulated into
     unsigned int* counter;   // dynamic row scheduler
-    const unsigned int* row_range;  // {first, last} target row that has tasks (written by the list packing)
+    const unsigned int* n_active;   // number of rows that have work (written by the list packing)
+    const int* row_order;           // those rows, fullest target leaves first (see csr_pack.cuh)
     int nrow;
     float k_fix;             // fixed-point step in kernel length units (box / 2^32 / unit)
     float eps2;              // (eps / unit)^2
@@ -265,15 +266,17 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
     fence_proxy_async();
     __syncwarp();
     uint32_t phase0 = 0, phase1 = 0;
-    // a chunked list only touches a band of target rows: schedule that band, not all rows
-    const unsigned int row_first = __ldg(P.row_range), row_last = __ldg(P.row_range + 1);
-    if (row_first > row_last) return;                          // empty list (first = 0xffffffff)
+    // row schedule: only rows that have tasks, grouped by target occupancy (see csr_pack.cuh)
+    const unsigned int n_active = __ldg(P.n_active);
 
     for (;;) {
-        int row = 0;
-        if (lane == 0) row = (int)(atomicAdd(P.counter, 1u) + row_first);
+        int row = -1;
+        if (lane == 0) {
+            const unsigned int idx = atomicAdd(P.counter, 1u);
+            if (idx < n_active) row = __ldg(P.row_order + idx);
+        }
         row = __shfl_sync(0xffffffffu, row, 0);
-        if (row >= P.nrow || (unsigned)row > row_last) break;
+        if (row < 0) break;
         const int2 tl = __ldg(P.leaf + row);
         const int nt_all = tl.y;
         const long long e_begin = __ldg(P.row_ptr + row);

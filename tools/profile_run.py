@@ -7,10 +7,10 @@ sys.path.insert(0, os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200"))
 from p2p_b200 import step, synth
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 maxleaf = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-pos, box = synth.zeldovich_like(ns)
+pos, box = synth.clustered(ns) if 'clustered' in sys.argv else synth.zeldovich_like(ns)
 L = step.build_lists(pos, box, maxleaf, ns, periodic=False)
 st = step.ShortRangeStep(0)
-if len(sys.argv) > 6:
+if len(sys.argv) > 6 and sys.argv[3].isdigit():
     st.ctx.set_tuning(int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])); st.ctx.set_kernel_variant(int(sys.argv[6]))
 st.upload(L, synth.DEMO_MASS, True)
 for _ in range(3):
