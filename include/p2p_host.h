@@ -96,6 +96,10 @@ int p2p_domain_setup(int nproc, double box, double* split, double* center, doubl
 int p2p_domain_route(int nproc, const double* split, double* records, int64_t stride_doubles, int64_t* payload,
                      int64_t npart, int* sendcount);
 
+/* work-weighted relaxation of the splits (measure_domain_runtime + determine_split_domtree,
+ * 1_Indexing/src/domains.c:20-38,86-157); work[r] = task count of rank r; split[2P-1] updated in place */
+int p2p_domain_relax(int nproc, double box, double* split, const double* work);
+
 int p2p_host_max_threads(void);
 
 #ifdef __cplusplus

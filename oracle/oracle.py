@@ -202,5 +202,14 @@ def domain_partition(nproc, split, pos, payload):
     return send
 
 
+def domain_relax(nproc, box, split, work):
+    """New splits after the reference's load-balance feedback; work[r] = tasks of rank r (idxP2P + idxM2L)."""
+    work = np.asarray(work, np.float64)
+    frac = np.ascontiguousarray(work * nproc / (work.sum() + 0.0001))        # I/src/photoNs.c:303
+    out = np.array(split, np.float64, copy=True)
+    lib().oracle_domain_relax(int(nproc), C.c_double(box), _d(out), _d(frac))
+    return out
+
+
 def max_threads():
     return int(lib().oracle_max_threads())

@@ -538,6 +538,61 @@ void oracle_domain_setup(int nproc, double box, double* split, double* center, d
     free(son); free(tn); free(tl); free(tr);
 }
 
+/* I/src/domains.c:42-84 : ranks below the left / right son of a rank-tree node holding `size` ranks */
+static void rank_fraction(int size, int* l, int* r) {
+    int left, right;
+    if (size == 1) { left = 1; right = 0; }
+    else if (size == 2) { left = 1; right = 1; }
+    else if (size == 3) { left = 2; right = 1; }
+    else {
+        left = 1; right = 2;
+        while (size - left >= right - size) { left *= 2; right *= 2; }
+        left >>= 1;
+        right = size - left;
+        if (left < right) { left = right; right = size - left; }
+    }
+    *l = left; *r = right;
+}
+/* I/src/domains.c:86-144 (determine_split_node): only the last assignment to `shift` (:120) is live */
+static void relax_node(int P, int D, int nproc, int n, double* split, const double* tl, const double* tr,
+                       const double bl[3], const double br[3]) {
+    if (n >= P - 1) return;
+    int nleft, nright;
+    rank_fraction(nproc, &nleft, &nright);
+    const double relax = 0.3;
+    const double t1 = tl[n] / nleft, t2 = tr[n] / nright;
+    const double w0l = split[n] - bl[D], w0r = br[D] - split[n];
+    const double shift = 0.5 * relax * (t2 - t1) / (t1 * nleft / w0l + t2 * nright / w0r);
+    const double new_split = split[n] + shift;
+    double l[3] = {bl[0], bl[1], bl[2]}, r[3] = {br[0], br[1], br[2]};
+    r[D] = split[n];
+    relax_node(P, (D + 1) % 3, nleft, 2 * n + 1, split, tl, tr, l, r);
+    l[D] = split[n]; r[D] = br[D];
+    relax_node(P, (D + 1) % 3, nright, 2 * n + 2, split, tl, tr, l, r);
+    split[n] = new_split;
+}
+/* I/src/domains.c:20-38 (measure_domain_runtime) + :146-157 (determine_split_domtree): frac[r] is rank r's
+ * DTIME_FRACTION = W_r P / (sum W + 1e-4) (I/src/photoNs.c:303); split[2P-1] is updated in place */
+void oracle_domain_relax(int nproc, double box, double* split, const double* frac) {
+    if (nproc < 1 || nproc > (1 << 20)) return;
+    const int P = nproc, len = 2 * P - 1, ml = mostleft_of(P);
+    int* son = (int*)malloc(sizeof(int) * 2 * (size_t)len);
+    double* tn = (double*)calloc((size_t)len, sizeof(double));
+    double* tl = (double*)calloc((size_t)len, sizeof(double));
+    double* tr = (double*)calloc((size_t)len, sizeof(double));
+    for (int n = 0; n < P - 1; n++) { son[2 * n] = 2 * n + 1; son[2 * n + 1] = 2 * n + 2; }
+    for (int n = P - 1; n < len; n++) { son[2 * n] = son[2 * n + 1] = -1; tl[n] = tr[n] = 1.0; }
+    for (int r = 0; r < P; r++) {
+        int idom = r + ml;
+        if (idom > 2 * P - 2) idom -= P;
+        tn[idom] = frac[r];
+    }
+    fill_time(P, 0, son, tn, tl, tr);
+    const double bl[3] = {0, 0, 0}, br[3] = {box, box, box};
+    relax_node(P, 0, P, 0, split, tl, tr, bl, br);
+    free(son); free(tn); free(tl); free(tr);
+}
+
 typedef struct { double* pos; int64_t* payload; } Bodies;
 static void swap_b(Bodies* b, int base, int i, int j) {
     if (i == j) return;

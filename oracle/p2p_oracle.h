@@ -92,6 +92,8 @@ int oracle_domain_of_rank(int nproc, int rank);
  * rank-tree traversal order exactly as the reference leaves them. */
 void oracle_domain_partition(int nproc, const double* split, double* pos, int64_t* payload, int npart, int* sendcount,
                              int* sendorder);
+/* work-weighted relaxation of the rank-tree splits, I/src/domains.c:20-38,86-157 */
+void oracle_domain_relax(int nproc, double box, double* split, const double* frac);
 int oracle_max_threads(void);
 #ifdef __cplusplus
 }

@@ -191,6 +191,32 @@ static int run_rank(int rank, int nproc, const double* pos, long ntot, double bo
         put_d("t_fmm_ext_s", dtime() - t0);
         put_i("numRemoteInteractions", numRemoteInteractions);
         put_i("n_remote_calls", launch_no - 1);
+        /* Second decomposition with the reference's load-balance feedback (1_Indexing/src/photoNs.c:295-306:
+         * DTIME_FRACTION = W_r * P / (sum W + 1e-4), W = idxP2P + idxM2L set at 1_Indexing/src/fmm.c:1139),
+         * then domain_decomposition() as the next step of driver() would call it (photoNs.c:213). */
+        put_d("work_this_domain", DTIME_THIS_DOMAIN);
+        {
+            double* all = (double*)malloc(sizeof(double) * (size_t)nproc);
+            MPI_Allgather(&DTIME_THIS_DOMAIN, 1, MPI_DOUBLE, all, 1, MPI_DOUBLE, MPI_COMM_WORLD);
+            double tot = 0.0;
+            for (int r = 0; r < nproc; r++) tot += all[r];
+            DTIME_FRACTION = DTIME_THIS_DOMAIN * PROC_SIZE / (tot + 0.0001);
+            free(all);
+        }
+        put_d("dtime_fraction", DTIME_FRACTION);
+        fmm_deconstruct();
+        domain_decomposition();
+        {
+            double* sp = (double*)malloc(sizeof(double) * (size_t)(2 * nproc - 1));
+            for (int i = 0; i < 2 * nproc - 1; i++) sp[i] = domtree[i].split;
+            put("domtree_split_step2", 1, sp, (uint64_t)(2 * nproc - 1));
+            free(sp);
+            int64_t* perm = (int64_t*)malloc(sizeof(int64_t) * (size_t)(NPART ? NPART : 1));
+            for (int i = 0; i < NPART; i++) perm[i] = (int64_t)part[i].vel[0];
+            put_i("npart_step2", NPART);
+            put("part_orig_index_step2", 2, perm, (uint64_t)NPART);
+            free(perm);
+        }
     }
     fclose(fout);
     return 0;

@@ -686,6 +686,64 @@ int p2p_domain_setup(int nproc, double box, double* split, double* center, doubl
     return 0;
 }
 
+// Work-weighted relaxation of the splits: measure_domain_runtime + determine_split_domtree
+// (1_Indexing/src/domains.c:20-38,86-157).  work[r] is rank r's task count; the fractions are
+// W_r P / (sum W + 1e-4) as 1_Indexing/src/photoNs.c:303 forms them.  Every split moves by
+// 0.15 (t2 - t1) / (t1 nl / wl + t2 nr / wr), t = work per rank on either side, w = current widths, with the
+// bounds of the recursion taken from the OLD splits.
+int p2p_domain_relax(int nproc, double box, double* split, const double* work) {
+    if (nproc < 1 || !split || !work) return -2;
+    const int P = nproc, len = 2 * P - 1, ml = mostleft_of(P);
+    double tot = 0.0;
+    for (int r = 0; r < P; r++) tot += work[r];
+    std::vector<double> tn((size_t)len, 0.0), tl((size_t)len, 1.0), tr((size_t)len, 1.0);
+    for (int r = 0; r < P; r++) {
+        int idom = r + ml;
+        if (idom > 2 * P - 2) idom -= P;
+        tn[(size_t)idom] = work[r] * P / (tot + 0.0001);
+    }
+    for (int n = P - 2; n >= 0; n--) {              // heap order: sons have larger indices
+        tl[(size_t)n] = tn[2 * (size_t)n + 1];
+        tr[(size_t)n] = tn[2 * (size_t)n + 2];
+        tn[(size_t)n] = tl[(size_t)n] + tr[(size_t)n];
+    }
+    auto ranks_below = [](int size, int* l, int* r) {   // fraction(), 1_Indexing/src/domains.c:42-84
+        int left, right;
+        if (size == 1) { left = 1; right = 0; }
+        else if (size == 2) { left = 1; right = 1; }
+        else if (size == 3) { left = 2; right = 1; }
+        else {
+            left = 1; right = 2;
+            while (size - left >= right - size) { left *= 2; right *= 2; }
+            left >>= 1;
+            right = size - left;
+            if (left < right) { left = right; right = size - left; }
+        }
+        *l = left; *r = right;
+    };
+    struct Job { int n, D, np; double l[3], r[3]; };
+    std::vector<Job> st;
+    std::vector<double> fresh(split, split + len);
+    st.push_back(Job{0, 0, P, {0, 0, 0}, {box, box, box}});
+    while (!st.empty()) {
+        const Job j = st.back();
+        st.pop_back();
+        if (j.n >= P - 1) continue;
+        int nl, nr;
+        ranks_below(j.np, &nl, &nr);
+        const double t1 = tl[(size_t)j.n] / nl, t2 = tr[(size_t)j.n] / nr;
+        const double w0l = split[j.n] - j.l[j.D], w0r = j.r[j.D] - split[j.n];
+        fresh[(size_t)j.n] = split[j.n] + 0.5 * 0.3 * (t2 - t1) / (t1 * nl / w0l + t2 * nr / w0r);
+        Job a = j, b = j;
+        a.n = 2 * j.n + 1; a.D = (j.D + 1) % 3; a.np = nl; a.r[j.D] = split[j.n];
+        b.n = 2 * j.n + 2; b.D = (j.D + 1) % 3; b.np = nr; b.l[j.D] = split[j.n];
+        st.push_back(b);
+        st.push_back(a);
+    }
+    for (int n = 0; n < len; n++) split[n] = fresh[(size_t)n];
+    return 0;
+}
+
 // bksort_body_inplace + prepare_body_inOrderOf_domain, 1_Indexing/src/domains.c:163-296
 int p2p_domain_route(int nproc, const double* split, double* records, int64_t stride, int64_t* payload, int64_t npart,
                      int* sendcount) {

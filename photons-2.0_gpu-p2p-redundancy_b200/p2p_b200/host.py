@@ -53,6 +53,7 @@ def load_host_library():
                                             C.POINTER(_ip), C.POINTER(_ip), C.POINTER(C.c_int64)]
         L.p2p_host_free.argtypes = [C.c_void_p]
         L.p2p_domain_setup.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _ip]
+        L.p2p_domain_relax.argtypes = [C.c_int, C.c_double, _dp, _dp]
         L.p2p_domain_route.argtypes = [C.c_int, _dp, _dp, C.c_int64, _lp, C.c_int64, _ip]
         _lib = L
     return _lib
@@ -263,6 +264,16 @@ def domain_route(nproc, split, pos, payload):
     if rc != 0:
         raise P2PError(rc, "p2p_domain_route failed")
     return send
+
+
+def domain_relax(nproc, box, split, work):
+    """Splits of the next step from this step's per-rank task counts (the reference's load-balance feedback)."""
+    out = np.array(split, np.float64, copy=True)
+    w = np.ascontiguousarray(work, np.float64)
+    rc = load_host_library().p2p_domain_relax(int(nproc), float(box), out.ctypes.data_as(_dp), w.ctypes.data_as(_dp))
+    if rc != 0:
+        raise P2PError(rc, "p2p_domain_relax failed")
+    return out
 
 
 def max_threads():

@@ -87,6 +87,8 @@ def test_domain_setup_and_route(demo_pos, nproc):
     s2 = host.domain_route(nproc, sh, p2, i2)
     assert np.array_equal(s1, s2) and np.array_equal(p1, p2) and np.array_equal(i1, i2)
     assert s2.sum() == len(p1)
+    work = np.random.default_rng(nproc).integers(50000, 150000, nproc).astype(float)
+    assert np.array_equal(oracle.domain_relax(nproc, DEMO_BOX, so, work), host.domain_relax(nproc, DEMO_BOX, sh, work))
 
 
 def test_step_lists_equal_oracle_flow(demo_pos):

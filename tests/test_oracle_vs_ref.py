@@ -66,3 +66,29 @@ def test_random_inputs(kind, seed, n, maxleaf, nproc):
         pos = rng.uniform(0, box, (n, 3))
     pos = pos.astype(np.float32).astype(np.float64)
     _compare(pos, box, maxleaf, 16, nproc)
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_work_weighted_split_relaxation(demo_pos, nproc):
+    """Second domain_decomposition() of the reference, fed by its own load-balance feedback
+    (1_Indexing/src/photoNs.c:295-306, 1_Indexing/src/domains.c:20-38,86-157): new splits and the particle
+    sets after the second routing must be bit-identical in the oracle and in the product's host library."""
+    from p2p_b200 import host
+    rr = refrun.run(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, do_ext=True, nproc=nproc, timeout=120)
+    work = [float(r["work_this_domain"][0]) for r in rr]
+    s0 = oracle.domain_setup(nproc, DEMO_BOX)[0]
+    s1 = oracle.domain_relax(nproc, DEMO_BOX, s0, work)
+    assert np.array_equal(s1, rr[0]["domtree_split_step2"])
+    assert np.array_equal(host.domain_relax(nproc, DEMO_BOX, s0, work), s1)
+    oo = flow.short_range_lists(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, nproc, False, True)
+    assert [len(o["local"][0]) for o in oo] == [int(w) for w in work]      # work proxy = local task count (no M2L at this size)
+    blocks = [[None] * nproc for _ in range(nproc)]
+    for r in range(nproc):
+        T = oo[r]["tree"]
+        p, idx = T.pos.copy(), oo[r]["orig_index"].copy()
+        send = oracle.domain_partition(nproc, s1, p, idx)
+        off = np.concatenate([[0], np.cumsum(send)])
+        for d in range(nproc):
+            blocks[d][r] = idx[off[d]:off[d + 1]]
+    for d in range(nproc):
+        assert np.array_equal(np.concatenate(blocks[d]), rr[d]["part_orig_index_step2"])
