@@ -141,6 +141,44 @@ int p2p_step_host_chunked(p2p_ctx* ctx, const double* pos, int64_t pos_stride, i
 void* p2p_device_particles(p2p_ctx* ctx);   /* int4[npart + nghost], fixed-point */
 void* p2p_device_acc(p2p_ctx* ctx);         /* float4[npart], accelerations in .xyz */
 
+/* ---- device-resident tree build and dual-tree walk -------------------------------
+ * The list producers of the reference run on the host (1_Indexing/src/fmm.c:29-263 build_localtree, :402-534
+ * walk_task_p2p, 1_Indexing/src/remotes.c:337-446 prepare_sendtree2, :141-317 walk_task_p2p_ext).  These entry
+ * points produce the SAME tree (particle permutation, leaf / node ids, kd-cell boxes, split values -- bit for
+ * bit, including the sequential fp64 mean and the partition's tie rules) and the SAME task multiset on the
+ * device, so that a whole short-range step needs one upload of positions and one download of accelerations. */
+
+/* build_localtree on the device.  pos: host rows of 3 doubles (stride in doubles) in the caller's order; bdl/bdr:
+ * the domain box; direct_start: first split dimension.  Needs p2p_set_box and p2p_set_physics first.  On success
+ * the context holds the particles in tree order, the leaves and the tree; accelerations are zeroed.
+ * Fails with P2P_ERR_ARG where the reference would overrun its 2 NPART / MAXLEAF leaf / node capacity. */
+int p2p_tree_build(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
+                   const double bdr[3], int direct_start);
+/* boxes and sons of a tree built on the host (p2p_build_localtree, ids as in p2p_tree_view: node_son holds global
+ * ids) for p2p_tree_walk; particles and leaves must have been uploaded with p2p_upload_particles / _leaves */
+int p2p_tree_upload(p2p_ctx* ctx, int maxleaf, int nleaf, int nnode, int first_leaf, int first_node,
+                    const double* leaf_center, const double* leaf_width, const int* node_son, const double* node_center,
+                    const double* node_width);
+int p2p_tree_info(p2p_ctx* ctx, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items);
+/* copies of the device-built tree in the reference's layout (NULL pointers are skipped); perm[i] = index, in the
+ * array given to p2p_tree_build, of the particle now at tree position i; node_son holds global ids with
+ * first_leaf = npart and first_node = npart + 2 npart / maxleaf (1_Indexing/src/fmm.c:199-212) */
+int p2p_tree_download(p2p_ctx* ctx, int64_t* perm, double* pos_sorted, int* leaf_npart, int* leaf_ipart, double* leaf_center,
+                      double* leaf_width, int* node_npart, int* node_son, double* node_split, double* node_center,
+                      double* node_width);
+/* walk_task_p2p over the device tree; with period > 0 also the walks against the 26 periodic images of the same
+ * tree, pruned against the target box {tcenter, twidth} as prepare_sendtree2 does and walked as walk_task_p2p_ext
+ * does.  Image sources are listed under their LOCAL leaf id (the fixed-point coordinates wrap to the nearest
+ * image; needs box > 2 (r_cut + leaf size), see p2p_csr_duplicates).  Tasks are APPENDED to the context's list. */
+int p2p_tree_walk(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]);
+/* number of sources listed twice in a row of the packed list (0 unless the periodic box is too small) */
+int p2p_csr_duplicates(p2p_ctx* ctx, int64_t* ndup);
+/* accelerations in the ORDER OF THE POSITIONS GIVEN TO p2p_tree_build, packed rows of 3 doubles */
+int p2p_download_acc_original(p2p_ctx* ctx, double* acc);
+/* test knob: runs up to this length use the plain in-order fold for the split mean, longer ones the exact parallel
+ * evaluation of the same sequential sum (< 0 restores the default) */
+int p2p_tree_set_option(p2p_ctx* ctx, int seq_sum_plain_max);
+
 #ifdef __cplusplus
 }
 #endif

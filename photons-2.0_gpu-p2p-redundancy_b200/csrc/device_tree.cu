@@ -1,0 +1,426 @@
+// device_tree.cu -- host side of the device-resident tree build and dual-tree walk (see device_tree.cuh).
+// Compiled with -fmad=false and WITHOUT fast-math: the fp64 tree and MAC arithmetic must round exactly like
+// the reference's host build.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "device_tree.cuh"
+#include "p2p_ctx.h"
+
+#define fail p2p_fail
+using p2p::dt::ull;
+
+struct p2p_dtree {
+    // final tree
+    long long npart = 0;
+    int maxleaf = 0, nleaf = 0, nnode = 0, cap = 0, direct_start = 0, nlevel = 0;
+    bool valid = false, built_here = false;
+    DevBuf<double> box;
+    DevBuf<int> son, node_npart, leaf_npart, leaf_ipart;
+    DevBuf<double> node_split;
+    // build
+    DevBuf<double> x[3];
+    DevBuf<int> perm, seg, seg_next, slot;
+    DevBuf<unsigned char> flag;
+    DevBuf<unsigned int> G, tile;
+    DevBuf<int> t_start, t_len, t_parent, t_np0, t_child, t_nleaf, t_nnode, t_id, t_leafbase, child_cnt;
+    DevBuf<double> t_split, t_lo, t_hi;
+    int* d_scalar = nullptr;     // [0] next-level node count, [1] max leaf occupancy
+    int* h_scalar = nullptr;     // pinned
+    // walk
+    DevBuf<ull> frontier[2];
+    ull* d_wcount = nullptr;     // [0] next frontier, [1] tasks
+    ull* h_wcount = nullptr;     // pinned
+    unsigned int* d_dup = nullptr;
+    long long walk_tasks = 0, walk_items = 0;
+    int walk_levels = 0;
+    int plain_max = p2p::dt::kSeqPlainMax;
+    float ms_build = 0.f, ms_walk = 0.f;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+void p2p_dtree_release(p2p_dtree* t) {
+    if (!t) return;
+    t->box.release(); t->son.release(); t->node_npart.release(); t->leaf_npart.release(); t->leaf_ipart.release();
+    t->node_split.release();
+    for (int k = 0; k < 3; k++) t->x[k].release();
+    t->perm.release(); t->seg.release(); t->seg_next.release(); t->slot.release(); t->flag.release(); t->G.release(); t->tile.release();
+    t->t_start.release(); t->t_len.release(); t->t_parent.release(); t->t_np0.release(); t->t_child.release(); t->t_nleaf.release();
+    t->t_nnode.release(); t->t_id.release(); t->t_leafbase.release(); t->child_cnt.release(); t->t_split.release(); t->t_lo.release();
+    t->t_hi.release();
+    t->frontier[0].release(); t->frontier[1].release();
+    if (t->d_scalar) cudaFree(t->d_scalar);
+    if (t->h_scalar) cudaFreeHost(t->h_scalar);
+    if (t->d_wcount) cudaFree(t->d_wcount);
+    if (t->h_wcount) cudaFreeHost(t->h_wcount);
+    if (t->d_dup) cudaFree(t->d_dup);
+    if (t->e0) cudaEventDestroy(t->e0);
+    if (t->e1) cudaEventDestroy(t->e1);
+    delete t;
+}
+
+namespace {
+
+int get_tree(p2p_ctx* c, p2p_dtree** out) {
+    if (!c->dtree) {
+        p2p_dtree* t = new p2p_dtree();
+        c->dtree = t;
+        CU(cudaMalloc(&t->d_scalar, 4 * sizeof(int)));
+        CU(cudaMallocHost(&t->h_scalar, 4 * sizeof(int)));
+        CU(cudaMalloc(&t->d_wcount, 2 * sizeof(ull)));
+        CU(cudaMallocHost(&t->h_wcount, 2 * sizeof(ull)));
+        CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
+        CU(cudaEventCreate(&t->e0));
+        CU(cudaEventCreate(&t->e1));
+        static const int shifts[27][3] = {{0, 0, 0},
+            {-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1}, {-1, 1, 0}, {-1, 1, 1},
+            {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 0, -1}, {0, 0, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1},
+            {1, -1, -1}, {1, -1, 0}, {1, -1, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1}, {1, 1, -1}, {1, 1, 0}, {1, 1, 1}};
+        CU(cudaMemcpyToSymbol(p2p::dt::c_shift, shifts, sizeof shifts));
+    }
+    *out = c->dtree;
+    return 0;
+}
+
+inline unsigned blocks(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+}  // namespace
+
+extern "C" {
+
+int p2p_tree_set_option(p2p_ctx* c, int seq_sum_plain_max) {
+    USE(c);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    t->plain_max = seq_sum_plain_max < 0 ? p2p::dt::kSeqPlainMax : seq_sum_plain_max;
+    return 0;
+}
+
+// Tree built elsewhere (p2p_build_localtree): boxes and sons for the device walk.  Ids as in p2p_tree_view:
+// node_son holds the reference's global ids (leaf first_leaf + l, node first_node + n).
+int p2p_tree_upload(p2p_ctx* c, int maxleaf, int nleaf, int nnode, int first_leaf, int first_node, const double* leaf_center,
+                    const double* leaf_width, const int* node_son, const double* node_center, const double* node_width) {
+    USE(c);
+    if (nleaf < 0 || nnode < 1 || !node_son || !node_center || !node_width || (nleaf && (!leaf_center || !leaf_width)))
+        return fail(P2P_ERR_ARG, "bad tree arrays");
+    if (nleaf != c->nleaf) return fail(P2P_ERR_STATE, "tree has %d leaves, %d were uploaded with p2p_upload_leaves", nleaf, c->nleaf);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    const size_t nu = (size_t)nleaf + nnode;
+    std::vector<double> box(6 * nu);
+    for (int l = 0; l < nleaf; l++)
+        for (int k = 0; k < 3; k++) { box[6 * (size_t)l + k] = leaf_center[3 * (size_t)l + k]; box[6 * (size_t)l + 3 + k] = leaf_width[3 * (size_t)l + k]; }
+    for (int n = 0; n < nnode; n++)
+        for (int k = 0; k < 3; k++) {
+            box[6 * ((size_t)nleaf + n) + k] = node_center[3 * (size_t)n + k];
+            box[6 * ((size_t)nleaf + n) + 3 + k] = node_width[3 * (size_t)n + k];
+        }
+    std::vector<int> son(2 * (size_t)nnode);
+    for (size_t i = 0; i < son.size(); i++) {
+        const int g = node_son[i];
+        if (g < 0) son[i] = -1;
+        else if (g >= first_node) {
+            if (g - first_node >= nnode) return fail(P2P_ERR_ARG, "son id %d outside the node range", g);
+            son[i] = nleaf + (g - first_node);
+        } else {
+            if (g < first_leaf || g - first_leaf >= nleaf) return fail(P2P_ERR_ARG, "son id %d outside the leaf range", g);
+            son[i] = g - first_leaf;
+        }
+    }
+    CU(t->box.reserve(box.size(), c->stream));
+    CU(t->son.reserve(son.size(), c->stream));
+    CU(cudaMemcpyAsync(t->box.p, box.data(), box.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(t->son.p, son.data(), son.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));           // the staging vectors die here
+    t->npart = c->npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->valid = true; t->built_here = false;
+    return 0;
+}
+
+// build_localtree on the device.  pos: host rows of 3 doubles in the caller's order (stride in doubles).
+// On success the context holds the particles in tree order (fixed point), the leaves, and the tree for p2p_tree_walk.
+int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
+                   const double bdr[3], int direct_start) {
+    USE(c);
+    if (npart < 1 || !pos || stride < 3 || maxleaf < 1 || !bdl || !bdr || direct_start < 0 || direct_start > 2)
+        return fail(P2P_ERR_ARG, "bad arguments to p2p_tree_build");
+    if (maxleaf > P2P_MAX_LEAF) return fail(P2P_ERR_ARG, "maxleaf %d exceeds P2P_MAX_LEAF %d", maxleaf, P2P_MAX_LEAF);
+    if (npart > 0x7fffffffLL) return fail(P2P_ERR_ARG, "more than 2^31 particles per device");
+    if (!c->box_set) return fail(P2P_ERR_STATE, "p2p_set_box must precede p2p_tree_build");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    cudaStream_t st = c->stream;
+    t->valid = false;
+    int cap = (int)(2.0 * (double)npart / (double)maxleaf);   // the reference's NLEAF = NNODE capacity (fmm.c:203-209)
+    if (cap > npart) cap = (int)npart + 1;
+    const size_t ncap = (size_t)std::max(cap, 1) + 2;
+    // ---- upload and split into coordinate arrays
+    CU(c->stage.reserve((size_t)npart * 24, st));
+    if (stride == 3) CU(cudaMemcpyAsync(c->stage.p, pos, (size_t)npart * 24, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)stride * 8, 24, (size_t)npart, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(t->e0, st));
+    for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)npart, st));
+    CU(t->perm.reserve((size_t)npart, st)); CU(t->seg.reserve((size_t)npart, st)); CU(t->seg_next.reserve((size_t)npart, st));
+    CU(t->slot.reserve((size_t)npart, st)); CU(t->flag.reserve((size_t)npart, st)); CU(t->G.reserve((size_t)npart + 1, st));
+    const int ntile = (int)((npart + p2p::dt::kTile - 1) / p2p::dt::kTile);
+    CU(t->tile.reserve((size_t)ntile + 1, st));
+    CU(t->t_start.reserve(ncap, st)); CU(t->t_len.reserve(ncap, st)); CU(t->t_parent.reserve(ncap, st)); CU(t->t_np0.reserve(ncap, st));
+    CU(t->t_child.reserve(2 * ncap, st)); CU(t->t_nleaf.reserve(ncap, st)); CU(t->t_nnode.reserve(ncap, st)); CU(t->t_id.reserve(ncap, st));
+    CU(t->t_leafbase.reserve(ncap, st)); CU(t->child_cnt.reserve(ncap, st)); CU(t->t_split.reserve(ncap, st));
+    CU(t->t_lo.reserve(3 * ncap, st)); CU(t->t_hi.reserve(3 * ncap, st));
+    p2p::dt::BuildArrays A;
+    for (int k = 0; k < 3; k++) A.x[k] = t->x[k].p;
+    A.perm = t->perm.p; A.seg = t->seg.p; A.seg_next = t->seg_next.p; A.flag = t->flag.p; A.G = t->G.p; A.slot = t->slot.p;
+    A.t_start = t->t_start.p; A.t_len = t->t_len.p; A.t_parent = t->t_parent.p; A.t_np0 = t->t_np0.p; A.t_split = t->t_split.p;
+    A.t_child = t->t_child.p; A.t_nleaf = t->t_nleaf.p; A.t_nnode = t->t_nnode.p; A.t_id = t->t_id.p; A.t_leafbase = t->t_leafbase.p;
+    A.t_lo = t->t_lo.p; A.t_hi = t->t_hi.p;
+    p2p::dt::soa_from_aos_kernel<<<blocks(npart, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), npart, A.x[0], A.x[1],
+                                                                     A.x[2], A.perm, A.seg);
+    const int root[3] = {0, (int)npart, -1};
+    CU(cudaMemcpyAsync(A.t_start, &root[0], 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A.t_len, &root[1], 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A.t_parent, &root[2], 4, cudaMemcpyHostToDevice, st));
+    // ---- levels
+    std::vector<int> lvl_begin{0}, lvl_count{1};
+    int total_nodes = 1;
+    for (int lvl = 0;; lvl++) {
+        if (lvl > 256) return fail(P2P_ERR_ARG, "kd-tree deeper than 256 levels (more than maxleaf coincident particles?)");
+        const int b = lvl_begin[lvl], n = lvl_count[lvl], dir = (direct_start + lvl) % 3;
+        const int warps = std::min(n, c->num_sm * 64);
+        p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max);
+        p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
+        p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
+        p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
+        p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
+        p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
+        p2p::dt::child_scan_kernel<<<1, 1024, 0, st>>>(t->child_cnt.p, n, t->d_scalar);
+        p2p::dt::children_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p, b + n, (int)ncap);
+        p2p::dt::slot_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
+        p2p::dt::swap_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(t->h_scalar, t->d_scalar, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int nnext = t->h_scalar[0];
+        std::swap(A.seg, A.seg_next);
+        if (nnext == 0) { t->nlevel = lvl + 1; break; }
+        total_nodes += nnext;
+        if (total_nodes > cap)
+            return fail(P2P_ERR_ARG, "kd-tree needs more than the reference's capacity of %d nodes (2 NPART / MAXLEAF)", cap);
+        lvl_begin.push_back(b + n);
+        lvl_count.push_back(nnext);
+    }
+    // ---- ids and boxes
+    for (int lvl = t->nlevel - 1; lvl >= 0; lvl--) p2p::dt::count_up_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, lvl_begin[lvl], lvl_count[lvl]);
+    int counts[2];
+    CU(cudaMemcpyAsync(&counts[0], A.t_nleaf, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&counts[1], A.t_nnode, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int nleaf = counts[0], nnode = counts[1];
+    if (nleaf > cap) return fail(P2P_ERR_ARG, "kd-tree needs %d leaves, the reference's capacity is %d (2 NPART / MAXLEAF)", nleaf, cap);
+    CU(t->box.reserve(6 * ((size_t)nleaf + nnode), st));
+    CU(t->son.reserve(2 * (size_t)nnode, st));
+    CU(t->node_npart.reserve((size_t)nnode, st)); CU(t->node_split.reserve((size_t)nnode, st));
+    CU(t->leaf_npart.reserve((size_t)nleaf + 1, st)); CU(t->leaf_ipart.reserve((size_t)nleaf + 1, st));
+    p2p::dt::TreeOut O;
+    O.nleaf = nleaf; O.box = t->box.p; O.son = t->son.p; O.node_npart = t->node_npart.p; O.node_split = t->node_split.p;
+    O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p;
+    for (int lvl = 0; lvl < t->nlevel; lvl++)
+        p2p::dt::assign_down_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, O, lvl_begin[lvl], lvl_count[lvl], (direct_start + lvl) % 3,
+                                                                               bdl[0], bdl[1], bdl[2], bdr[0], bdr[1], bdr[2]);
+    CU(cudaGetLastError());
+    // ---- hand over to the force path: fixed-point particles in tree order, leaves, zeroed accelerations
+    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false; c->nleaf = nleaf;
+    CU(c->part.reserve((size_t)npart + 1, st));
+    CU(c->acc.reserve((size_t)npart + 1, st));
+    CU(c->leaf.reserve((size_t)nleaf + 1, st));
+    p2p::dt::pack_fixed_kernel<<<blocks(npart, 256), 256, 0, st>>>(A.x[0], A.x[1], A.x[2], npart, c->origin[0], c->origin[1], c->origin[2],
+                                                                   4294967296.0 / c->extent, (float)c->mass, c->part.p);
+    CU(cudaMemsetAsync(t->d_scalar + 1, 0, sizeof(int), st));
+    if (nleaf) p2p::dt::leaf_pack_kernel<<<blocks(nleaf, 256), 256, 0, st>>>(O.leaf_npart, O.leaf_ipart, nleaf, c->leaf.p, t->d_scalar + 1);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), st));
+    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), st));
+    c->acc_tasks = 0;
+    c->max_target_leaf = maxleaf;
+    CU(cudaEventRecord(t->e1, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
+    t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
+    t->valid = true; t->built_here = true;
+    return 0;
+}
+
+int p2p_tree_info(p2p_ctx* c, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items) {
+    if (!c || !c->dtree || !c->dtree->valid) return fail(P2P_ERR_STATE, "no device tree");
+    if (nleaf) *nleaf = c->dtree->nleaf;
+    if (nnode) *nnode = c->dtree->nnode;
+    if (nlevel) *nlevel = c->dtree->nlevel;
+    if (ms_build) *ms_build = c->dtree->ms_build;
+    if (ms_walk) *ms_walk = c->dtree->ms_walk;
+    if (walk_items) *walk_items = c->dtree->walk_items;
+    return 0;
+}
+
+// Copies of the device-built tree in the layout of p2p_tree_view / the reference (node_son: global ids with
+// first_leaf = npart, first_node = npart + 2 npart / maxleaf); NULL pointers are skipped.
+int p2p_tree_download(p2p_ctx* c, int64_t* perm, double* pos_sorted, int* leaf_npart, int* leaf_ipart, double* leaf_center,
+                      double* leaf_width, int* node_npart, int* node_son, double* node_split, double* node_center, double* node_width) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "no device-built tree");
+    cudaStream_t st = c->stream;
+    const long long np = t->npart;
+    const int nl = t->nleaf, nn = t->nnode;
+    if (perm) {
+        std::vector<int> p((size_t)np);
+        CU(cudaMemcpyAsync(p.data(), t->perm.p, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (long long i = 0; i < np; i++) perm[i] = p[(size_t)i];
+    }
+    if (pos_sorted) {
+        std::vector<double> x((size_t)np);
+        for (int k = 0; k < 3; k++) {
+            CU(cudaMemcpyAsync(x.data(), t->x[k].p, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (long long i = 0; i < np; i++) pos_sorted[3 * i + k] = x[(size_t)i];
+        }
+    }
+    if (leaf_npart && nl) CU(cudaMemcpyAsync(leaf_npart, t->leaf_npart.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+    if (leaf_ipart && nl) CU(cudaMemcpyAsync(leaf_ipart, t->leaf_ipart.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+    if (node_npart) CU(cudaMemcpyAsync(node_npart, t->node_npart.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+    if (node_split) CU(cudaMemcpyAsync(node_split, t->node_split.p, (size_t)nn * 8, cudaMemcpyDeviceToHost, st));
+    if (leaf_center || leaf_width || node_center || node_width) {
+        std::vector<double> box(6 * ((size_t)nl + nn));
+        CU(cudaMemcpyAsync(box.data(), t->box.p, box.size() * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int l = 0; l < nl; l++)
+            for (int k = 0; k < 3; k++) {
+                if (leaf_center) leaf_center[3 * (size_t)l + k] = box[6 * (size_t)l + k];
+                if (leaf_width) leaf_width[3 * (size_t)l + k] = box[6 * (size_t)l + 3 + k];
+            }
+        for (int n = 0; n < nn; n++)
+            for (int k = 0; k < 3; k++) {
+                if (node_center) node_center[3 * (size_t)n + k] = box[6 * ((size_t)nl + n) + k];
+                if (node_width) node_width[3 * (size_t)n + k] = box[6 * ((size_t)nl + n) + 3 + k];
+            }
+    }
+    if (node_son) {
+        std::vector<int> son(2 * (size_t)nn);
+        CU(cudaMemcpyAsync(son.data(), t->son.p, son.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int first_leaf = (int)np, first_node = (int)np + t->cap;
+        for (size_t i = 0; i < son.size(); i++) node_son[i] = son[i] < 0 ? -1 : (son[i] < nl ? first_leaf + son[i] : first_node + (son[i] - nl));
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// walk_task_p2p over the device tree, plus (period > 0) the walks against the 26 periodic images of the same tree
+// pruned against the target box {tcenter, twidth} exactly as prepare_sendtree2 / walk_task_p2p_ext do.  Image sources
+// are listed under their LOCAL leaf id: the fixed-point coordinates wrap to the nearest image.  Tasks are appended to
+// the context's list (p2p_build_csr packs them).
+int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid) return fail(P2P_ERR_STATE, "p2p_tree_walk needs p2p_tree_build or p2p_tree_upload");
+    if (t->nleaf != c->nleaf) return fail(P2P_ERR_STATE, "device tree and uploaded leaves differ");
+    if (!(theta > 0.0) || !(rcut > 0.0)) return fail(P2P_ERR_ARG, "bad theta / rcut");
+    if (period > 0.0 && (!tcenter || !twidth)) return fail(P2P_ERR_ARG, "periodic walk needs the target box");
+    if ((long long)t->nleaf + t->nnode >= (1LL << 29)) return fail(P2P_ERR_ARG, "tree too large for the walk item encoding");
+    cudaStream_t st = c->stream;
+    const int nleaf = t->nleaf;
+    if (nleaf == 0) return 0;
+    if (period > 0.0 && t->npart <= t->maxleaf)
+        return fail(P2P_ERR_ARG, "image walk of a tree whose root holds <= maxleaf particles is undefined in the reference");
+    p2p::dt::WalkParams P;
+    P.box = t->box.p; P.son = t->son.p; P.nleaf = nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
+    for (int k = 0; k < 3; k++) { P.tc[k] = tcenter ? tcenter[k] : 0.0; P.tw[k] = twidth ? twidth[k] : 0.0; }
+    // initial frontier
+    std::vector<ull> init;
+    const int root = nleaf;
+    init.push_back(p2p::dt::item(root, root, 0));
+    if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, s));
+    size_t fcap = std::max<size_t>((size_t)nleaf * 96, 1 << 16);
+    size_t tcap = std::max<size_t>((size_t)nleaf * (period > 0.0 ? 192 : 160), 1 << 16);
+    CU(t->frontier[0].reserve(fcap, st)); CU(t->frontier[1].reserve(fcap, st));
+    CU(c->tt.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
+    CU(c->ts.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
+    CU(cudaEventRecord(t->e0, st));
+    CU(cudaMemcpyAsync(t->frontier[0].p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(t->d_wcount, 0, 2 * sizeof(ull), st));
+    ull n_in = init.size(), ntask = 0, items = 0;
+    int cur = 0, levels = 0;
+    while (n_in) {
+        if (++levels > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
+        for (;;) {
+            const ull cap_out = t->frontier[cur ^ 1].cap;
+            const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
+            const unsigned grid = (unsigned)std::min<ull>((n_in + 255) / 256, (ull)c->num_sm * 16);
+            p2p::dt::walk_level_kernel<<<grid, 256, 0, st>>>(t->frontier[cur].p, n_in, t->frontier[cur ^ 1].p, cap_out, t->d_wcount,
+                                                             c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, P);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const ull n_out = t->h_wcount[0], nt = t->h_wcount[1];
+            if (n_out <= cap_out && nt <= cap_task) { items += n_in; n_in = n_out; ntask = nt; break; }
+            // a buffer was too small: grow it and repeat this level from the same input
+            if (n_out > cap_out) CU(t->frontier[cur ^ 1].reserve((size_t)(n_out + n_out / 4), st));
+            if (nt > cap_task) {
+                const size_t want = (size_t)c->ntask + (size_t)(nt + nt / 2);
+                CU(c->tt.reserve(want, st, (size_t)(c->ntask + ntask)));
+                CU(c->ts.reserve(want, st, (size_t)(c->ntask + ntask)));
+            }
+            const ull reset[2] = {0, ntask};
+            CU(cudaMemcpyAsync(t->d_wcount, reset, sizeof reset, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        cur ^= 1;
+        CU(cudaMemsetAsync(t->d_wcount, 0, sizeof(ull), st));
+    }
+    CU(cudaEventRecord(t->e1, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&t->ms_walk, t->e0, t->e1));
+    c->ntask += (long long)ntask;
+    c->csr_valid = false;
+    t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
+    return 0;
+}
+
+// number of (row, source) duplicates in the packed list: non-zero means two images of one leaf reached the same
+// target, i.e. the periodic box is too small for minimal-image sources (needs box > 2 (r_cut + leaf sizes))
+int p2p_csr_duplicates(p2p_ctx* c, int64_t* ndup) {
+    USE(c);
+    if (!c->csr_valid) return fail(P2P_ERR_STATE, "no CSR built");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    CU(cudaMemsetAsync(t->d_dup, 0, sizeof(unsigned int), c->stream));
+    if (c->nleaf) p2p::dt::csr_duplicate_kernel<<<blocks(c->nleaf, 256), 256, 0, c->stream>>>(c->row_ptr.p, c->col.p, c->nleaf, t->d_dup);
+    CU(cudaGetLastError());
+    unsigned int d = 0;
+    CU(cudaMemcpyAsync(&d, t->d_dup, sizeof d, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (ndup) *ndup = d;
+    return 0;
+}
+
+// accelerations back in the ORDER OF THE POSITIONS GIVEN TO p2p_tree_build (packed rows of 3 doubles)
+int p2p_download_acc_original(p2p_ctx* c, double* acc) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "no device-built tree");
+    if (!acc) return fail(P2P_ERR_ARG, "null acc");
+    const long long n = c->npart;
+    CU(c->acc64.reserve((size_t)n * 3, c->stream));
+    p2p::dt::acc_unpermute_kernel<<<blocks(n, 256), 256, 0, c->stream>>>(c->acc.p, t->perm.p, n, c->acc64.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(acc, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+    return p2p_synchronize(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,679 @@
+// device_tree.cuh -- kd-tree build and dual-tree walk ON THE DEVICE, with the
+// reference's results bit for bit:
+//   build : bksort_inplace / build_kdtree / center_kdtree / build_localtree   1_Indexing/src/fmm.c:29-263
+//   walk  : acceptance :266-325, walk_task_p2p :402-534, and for the periodic images prepare_sendtree2 +
+//           walk_task_p2p_ext   1_Indexing/src/remotes.c:337-446,141-317
+// This translation unit is compiled with -fmad=false and without fast-math: every fp64 operation below rounds
+// exactly like the reference's gcc build (x86-64, no FMA contraction).
+//
+// Build, level-synchronous.  All nodes of one tree level are processed by the same kernels:
+//   1. split value = the reference's SEQUENTIAL fp64 mean of the split coordinate in the current particle order
+//      (mean_kernel: one warp per node; large nodes use an exact parallel evaluation of the sequential sum, see
+//      seq_sum_warp),
+//   2. "big" flags (x > mean) and one global exclusive scan of them,
+//   3. the reference's Hoare-like partition expressed in closed form: with ns = number of elements <= mean, the
+//      k-th big element (from the left) of [0, ns) changes place with the k-th small element (from the right) of
+//      [ns, len); nothing else moves.  The one quirk of the reference loop -- its last element is never examined,
+//      so a run without any big element still sends one element to the right -- is kept.
+//   4. children: a side with <= maxleaf particles becomes a leaf, the others are the nodes of the next level.
+// Ids in the reference's recursion order (leaves left to right, nodes in pre-order) and the kd-cell boxes are
+// assigned afterwards by one bottom-up and one top-down sweep over the levels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace p2p {
+namespace dt {
+
+typedef unsigned long long ull;
+
+// ------------------------------------------------------------------------------------------------ scan
+constexpr int kTile = 2048;   // elements per block of the flag scan (256 threads x 8)
+
+__global__ void flag_tile_sums_kernel(const unsigned char* __restrict__ flag, long long n, unsigned int* __restrict__ tile) {
+    __shared__ unsigned int ws[8];
+    const long long base = (long long)blockIdx.x * kTile;
+    unsigned int s = 0;
+    for (int k = 0; k < 8; k++) {
+        long long i = base + k * 256 + threadIdx.x;
+        if (i < n) s += flag[i];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; w++) t += ws[w];
+        tile[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile sums by one block; tile[ntile] receives the total
+__global__ void flag_tile_offsets_kernel(unsigned int* __restrict__ tile, int ntile) {
+    __shared__ unsigned int ws[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntile; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned int v = i < ntile ? tile[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = ws[threadIdx.x], z = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int y = __shfl_up_sync(0xffffffffu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            ws[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        const unsigned int excl = carry + ws[threadIdx.x >> 5] + x - v;
+        if (i < ntile) tile[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile[ntile] = carry;
+}
+
+// G[i] = number of flags in [0, i); G[n] = total
+__global__ void flag_scan_apply_kernel(const unsigned char* __restrict__ flag, long long n, const unsigned int* __restrict__ tile,
+                                       unsigned int* __restrict__ G) {
+    __shared__ unsigned int ws[8];
+    const long long base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * 8;
+    unsigned int f[8], s = 0;
+    for (int k = 0; k < 8; k++) {
+        f[k] = (base + k < n) ? flag[base + k] : 0;
+        s += f[k];
+    }
+    unsigned int x = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned int off = tile[blockIdx.x];
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += ws[w];
+    unsigned int run = off + x - s;
+    for (int k = 0; k < 8; k++) {
+        if (base + k < n) G[base + k] = run;
+        run += f[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) G[n] = tile[gridDim.x];
+}
+
+// ------------------------------------------------------------------------------------------------ build
+struct BuildArrays {
+    // particles in the current order (SoA) and their original indices
+    double* x[3];
+    int* perm;
+    int* seg;            // temp node that owns position i at the current level, -1 once it is inside a leaf
+    int* seg_next;
+    unsigned char* flag;
+    unsigned int* G;     // exclusive scan of flag, [npart + 1]
+    int* slot;           // right-zone small elements by rank from the right
+    // temp nodes, breadth first
+    int* t_start;
+    int* t_len;
+    int* t_parent;       // parent temp id * 2 + side, -1 for the root
+    int* t_np0;
+    double* t_split;
+    int* t_child;        // [2]: temp id of a child node, or -1 - (its particle count) for a leaf
+    int* t_nleaf;        // leaves / nodes of the subtree
+    int* t_nnode;
+    int* t_id;           // final node id (pre-order) and first leaf id of the subtree
+    int* t_leafbase;
+    double* t_lo;        // [3] kd cell of the node
+    double* t_hi;
+};
+
+// The reference's sequential sum  s = (((x0 + x1) + x2) + ...)  of one warp's run, evaluated exactly.
+// Plain version: lanes load 32 values, every lane folds them in order (uniform result).
+__device__ __forceinline__ double seq_sum_warp_plain(const double* __restrict__ x, long long start, int len) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int base = 0; base < len; base += 32) {
+        const double v = (base + lane < len) ? x[start + base + lane] : 0.0;
+        const int m = min(32, len - base);
+        for (int k = 0; k < m; k++) s += __shfl_sync(0xffffffffu, v, k);
+    }
+    return s;
+}
+
+// Exact parallel evaluation of the same sequential sum for long runs of non-negative values.
+// While the running sum S stays inside one binade [2^e, 2^(e+1)), S = k u with u = 2^(e-52) and k an integer in
+// [2^52, 2^53), and  fl(S + x) = (k + q + c) u  where x = (q + r) u, q integer, 0 <= r < 1, and the round-to-
+// nearest-even carry c is 1 if r > 1/2, 0 if r < 1/2 and the parity of k + q if r = 1/2.  The only state that
+// crosses an addition besides the sum is therefore ONE BIT (the parity of k), so a run of additions is a
+// two-state transducer {parity in -> (integer increment, parity out)} and transducers compose associatively:
+// each lane folds 8 consecutive values for both input parities, a warp scan composes the 32 lanes, and the tile
+// of 256 values costs O(8 + log 32) steps instead of 256 dependent additions.  A lane whose values would carry
+// the sum out of the binade (or that are negative / not finite / larger than the binade) stops the tile: the
+// lanes before it are applied, its own 8 values are added natively, and the next tile starts behind it with the
+// new binade.  Every path produces the bits of the sequential loop.
+__device__ __forceinline__ double seq_sum_warp(const double* __restrict__ x, long long start, int len) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    double S = 0.0;
+    int pos = 0;
+    while (pos < len) {
+        const int e = (int)((__double_as_longlong(S) >> 52) & 0x7ff) - 1023;       // binade of S (S >= 0)
+        const bool okS = S > 0.0 && e >= -900 && e <= 900;
+        const int my = pos + lane * 8;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (my + k < len) ? x[start + my + k] : 0.0;
+        // fold my 8 values for both input parities
+        long long d0 = 0, d1 = 0;
+        int p0 = 0, p1 = 1;
+        bool hard = !okS;
+        const double scale = okS ? __longlong_as_double((long long)(1023 + 52 - e) << 52) : 1.0;   // 2^(52-e)
+        const double top = okS ? __longlong_as_double((long long)(1023 + e + 1) << 52) : 0.0;      // 2^(e+1)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double xv = v[k];
+            if (!(xv >= 0.0 && xv < top)) hard = true;
+            const double y = xv * scale;                 // exact: power-of-two scaling, no underflow for xv >= 0 normal or 0
+            const double qf = floor(y);
+            const double r = y - qf;                     // exact
+            const long long q = (long long)qf;
+            const int gt = r > 0.5, tie = r == 0.5;
+            int t0 = p0 ^ (int)(q & 1), t1 = p1 ^ (int)(q & 1);
+            const int c0 = gt | (tie & t0), c1 = gt | (tie & t1);
+            d0 += q + c0;
+            d1 += q + c1;
+            p0 = t0 ^ c0;
+            p1 = t1 ^ c1;
+        }
+        // a denormal input would lose bits in the scaling only if the product were denormal too; xv * 2^(52-e)
+        // with e <= 900 is >= xv, so it is exact.
+        // inclusive warp scan of the transducers (compose: first A then B)
+        long long a0 = d0, a1 = d1;
+        int q0 = p0, q1 = p1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long b0 = __shfl_up_sync(full, a0, o), b1 = __shfl_up_sync(full, a1, o);
+            const int r0 = __shfl_up_sync(full, q0, o), r1 = __shfl_up_sync(full, q1, o);
+            if (lane >= o) {
+                // earlier lanes (b, r) first, then mine (a, q)
+                const long long n0 = b0 + (r0 ? a1 : a0), n1 = b1 + (r1 ? a1 : a0);
+                const int m0 = r0 ? q1 : q0, m1 = r1 ? q1 : q0;
+                a0 = n0; a1 = n1; q0 = m0; q1 = m1;
+            }
+        }
+        const long long kS = okS ? ((__double_as_longlong(S) & 0xfffffffffffffLL) | (1LL << 52)) : 0;   // integer mantissa
+        const int parS = (int)(kS & 1);
+        const long long incl = parS ? a1 : a0;                       // increment after my lane
+        const bool cross = hard || (kS + incl >= (1LL << 53));
+        const unsigned bad = __ballot_sync(full, cross);
+        if (bad == 0) {
+            const long long tot = __shfl_sync(full, incl, 31);
+            S = __longlong_as_double((long long)(1023 + e - 52) << 52) * (double)(kS + tot);          // (k + tot) u, exact
+            pos += 256;
+            continue;
+        }
+        const int f = __ffs(bad) - 1;
+        if (f > 0) {
+            const long long before = __shfl_sync(full, incl, f - 1);
+            S = __longlong_as_double((long long)(1023 + e - 52) << 52) * (double)(kS + before);
+        }
+        // lane f's own values, natively and in order
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double xv = __shfl_sync(full, v[k], f);
+            S += xv;                                                   // beyond the run: + 0.0
+        }
+        pos += 8 * (f + 1);
+    }
+    return S;
+}
+
+constexpr int kSeqPlainMax = 4096;   // runs up to this length use the plain fold
+
+// one warp per node of the level: split value
+__global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int plain_max) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ X = A.x[dir];
+    for (int n = w; n < lvl_count; n += nw) {
+        const int t = lvl_begin + n;
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t];
+        double split = 0.0;
+        if (len == 2) {
+            split = 0.5 * (X[start] + X[start + 1]);
+        } else if (len > 2) {
+            const double s = len <= plain_max ? seq_sum_warp_plain(X, start, len) : seq_sum_warp(X, start, len);
+            split = s / (double)len;
+        }
+        if ((threadIdx.x & 31) == 0) A.t_split[t] = split;
+    }
+}
+
+__global__ void flag_kernel(BuildArrays A, long long npart, int dir) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npart) return;
+    const int t = A.seg[i];
+    unsigned char f = 0;
+    if (t >= 0) {
+        const int len = A.t_len[t];
+        const double* __restrict__ X = A.x[dir];
+        if (len == 2) {
+            const long long s = A.t_start[t];
+            const bool swap = X[s] > X[s + 1];
+            f = (i == s) ? swap : !swap;
+        } else if (len > 2) {
+            f = X[i] > A.t_split[t];
+        }
+    }
+    A.flag[i] = f;
+}
+
+// per node: left count (with the reference's quirks) and the children
+__global__ void split_kernel(BuildArrays A, int lvl_begin, int lvl_count, int maxleaf, int* __restrict__ nchild_nodes) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    const long long start = A.t_start[t];
+    const int len = A.t_len[t];
+    int np0;
+    if (len < 2) np0 = 0;
+    else if (len == 2) np0 = 1;
+    else {
+        const int nbig = (int)(A.G[start + len] - A.G[start]);
+        np0 = nbig == 0 ? len - 1 : len - nbig;
+    }
+    A.t_np0[t] = np0;
+    const int np1 = len - np0;
+    nchild_nodes[n] = (np0 > maxleaf) + (np1 > maxleaf);
+}
+
+// exclusive scan of the per-node child counts of one level by a single block (levels hold at most a few 10^5 nodes)
+__global__ void child_scan_kernel(int* __restrict__ cnt, int n, int* __restrict__ total) {
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < n ? cnt[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int wv = ws[threadIdx.x], z = wv;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            ws[threadIdx.x] = z - wv;
+        }
+        __syncthreads();
+        const int excl = carry + ws[threadIdx.x >> 5] + x - v;
+        if (i < n) cnt[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void children_kernel(BuildArrays A, int lvl_begin, int lvl_count, int maxleaf, const int* __restrict__ child_off,
+                                int next_begin, int node_cap) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    const int start = A.t_start[t], len = A.t_len[t], np0 = A.t_np0[t], np1 = len - np0;
+    int next = next_begin + child_off[n];
+    int c0, c1;
+    if (np0 > maxleaf) {
+        c0 = next++;
+        if (c0 < node_cap) { A.t_start[c0] = start; A.t_len[c0] = np0; A.t_parent[c0] = 2 * t; }
+    } else c0 = -1 - np0;
+    if (np1 > maxleaf) {
+        c1 = next++;
+        if (c1 < node_cap) { A.t_start[c1] = start + np0; A.t_len[c1] = np1; A.t_parent[c1] = 2 * t + 1; }
+    } else c1 = -1 - np1;
+    A.t_child[2 * t] = c0;
+    A.t_child[2 * t + 1] = c1;
+}
+
+// positions of the right-zone small elements by rank from the right, and the owner of every position at the next level
+__global__ void slot_kernel(BuildArrays A, long long npart) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npart) return;
+    const int t = A.seg[i];
+    int next = -1;
+    if (t >= 0) {
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t], np0 = A.t_np0[t];
+        const int rel = (int)(i - start);
+        const int c = A.t_child[2 * t + (rel >= np0)];
+        next = c >= 0 ? c : -1;
+        if (rel >= np0 && !A.flag[i]) {
+            const int cb = (int)(A.G[i] - A.G[start]);                         // big elements left of i
+            const int nbig = (int)(A.G[start + len] - A.G[start]);
+            const int r = (len - nbig) - (rel - cb) - 1;                       // small elements right of i
+            A.slot[start + r] = (int)i;
+        }
+    }
+    A.seg_next[i] = next;
+}
+
+__global__ void swap_kernel(BuildArrays A, long long npart) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npart) return;
+    const int t = A.seg[i];
+    if (t < 0 || !A.flag[i]) return;
+    const long long start = A.t_start[t];
+    const int np0 = A.t_np0[t];
+    if (i - start >= np0) return;
+    const int k = (int)(A.G[i] - A.G[start]);
+    const long long j = A.slot[start + k];
+    for (int d = 0; d < 3; d++) {
+        const double a = A.x[d][i], b = A.x[d][j];
+        A.x[d][i] = b;
+        A.x[d][j] = a;
+    }
+    const int pa = A.perm[i], pb = A.perm[j];
+    A.perm[i] = pb;
+    A.perm[j] = pa;
+}
+
+// bottom-up: subtree leaf / node counts
+__global__ void count_up_kernel(BuildArrays A, int lvl_begin, int lvl_count) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    int nl = 0, nn = 1;
+    for (int s = 0; s < 2; s++) {
+        const int c = A.t_child[2 * t + s];
+        if (A.t_len[t] == 0) continue;             // an empty root has no children at all
+        if (c >= 0) { nl += A.t_nleaf[c]; nn += A.t_nnode[c]; }
+        else nl += 1;
+    }
+    A.t_nleaf[t] = nl;
+    A.t_nnode[t] = nn;
+}
+
+struct TreeOut {
+    int nleaf;               // offset of the nodes in the unified box array
+    double* box;             // [(nleaf + nnode)][6] centre, width
+    int* son;                // [nnode][2] unified ids (leaf l -> l, node n -> nleaf + n), -1 none
+    int* node_npart;
+    double* node_split;
+    int* leaf_npart;
+    int* leaf_ipart;
+};
+
+// top-down: final ids, kd cells, output arrays
+__global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int lvl_count, int dir, double l0, double l1, double l2,
+                                   double h0, double h1, double h2) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    double lo[3], hi[3];
+    int id, leafbase;
+    const int par = A.t_parent[t];
+    if (par < 0) {
+        lo[0] = l0; lo[1] = l1; lo[2] = l2; hi[0] = h0; hi[1] = h1; hi[2] = h2;
+        id = 0;
+        leafbase = 0;
+    } else {
+        const int p = par >> 1, side = par & 1;
+        const int pd = (dir + 2) % 3;                         // the parent's split direction
+        for (int k = 0; k < 3; k++) { lo[k] = A.t_lo[3 * p + k]; hi[k] = A.t_hi[3 * p + k]; }
+        const double ps = A.t_split[p];
+        if (side == 0) hi[pd] = ps; else lo[pd] = ps;
+        const int c0 = A.t_child[2 * p];
+        id = A.t_id[p] + 1;
+        leafbase = A.t_leafbase[p];
+        if (side == 1) {
+            if (c0 >= 0) { id += A.t_nnode[c0]; leafbase += A.t_nleaf[c0]; }
+            else leafbase += 1;
+        }
+    }
+    for (int k = 0; k < 3; k++) { A.t_lo[3 * t + k] = lo[k]; A.t_hi[3 * t + k] = hi[k]; }
+    A.t_id[t] = id;
+    A.t_leafbase[t] = leafbase;
+    double nwid[3], ncen[3];
+    for (int k = 0; k < 3; k++) { nwid[k] = hi[k] - lo[k]; ncen[k] = 0.5 * (hi[k] + lo[k]); }
+    double* nb = O.box + 6 * (size_t)(O.nleaf + id);
+    for (int k = 0; k < 3; k++) { nb[k] = ncen[k]; nb[3 + k] = nwid[k]; }
+    O.node_npart[id] = A.t_len[t];
+    const double split = A.t_split[t];
+    O.node_split[id] = split;
+    if (A.t_len[t] == 0) { O.son[2 * id] = O.son[2 * id + 1] = -1; return; }
+    int lb = leafbase, nid = id + 1, ip = A.t_start[t];
+    for (int s = 0; s < 2; s++) {
+        const int c = A.t_child[2 * t + s];
+        if (c >= 0) {
+            O.son[2 * id + s] = O.nleaf + nid;
+            nid += A.t_nnode[c];
+            lb += A.t_nleaf[c];
+            ip += A.t_len[c];
+        } else {
+            const int cnt = -1 - c;
+            O.son[2 * id + s] = lb;
+            O.leaf_npart[lb] = cnt;
+            O.leaf_ipart[lb] = ip;
+            double* b = O.box + 6 * (size_t)lb;
+            for (int k = 0; k < 3; k++) { b[k] = ncen[k]; b[3 + k] = nwid[k]; }
+            if (s == 0) { b[3 + dir] = split - lo[dir]; b[dir] = 0.5 * (lo[dir] + split); }
+            else        { b[3 + dir] = hi[dir] - split; b[dir] = 0.5 * (hi[dir] + split); }
+            lb += 1;
+            ip += cnt;
+        }
+    }
+}
+
+__global__ void soa_from_aos_kernel(const double* __restrict__ pos, long long n, double* __restrict__ x, double* __restrict__ y,
+                                    double* __restrict__ z, int* __restrict__ perm, int* __restrict__ seg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = pos[3 * i];
+    y[i] = pos[3 * i + 1];
+    z[i] = pos[3 * i + 2];
+    perm[i] = (int)i;
+    seg[i] = 0;
+}
+
+__global__ void pack_fixed_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, long long n,
+                                  double ox, double oy, double oz, double scale, float mass, int4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 o;
+    o.x = (int)(unsigned int)(__double2ll_rn((x[i] - ox) * scale) & 0xffffffffLL);     // same conversion as csr_pack.cuh:to_fixed
+    o.y = (int)(unsigned int)(__double2ll_rn((y[i] - oy) * scale) & 0xffffffffLL);
+    o.z = (int)(unsigned int)(__double2ll_rn((z[i] - oz) * scale) & 0xffffffffLL);
+    o.w = __float_as_int(mass);
+    out[i] = o;
+}
+
+__global__ void leaf_pack_kernel(const int* __restrict__ npart, const int* __restrict__ ipart, int n, int2* __restrict__ out,
+                                 int* __restrict__ maxocc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_int2(ipart[i], npart[i]);
+    atomicMax(maxocc, npart[i]);
+}
+
+__global__ void acc_unpermute_kernel(const float4* __restrict__ acc, const int* __restrict__ perm, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = acc[i];
+    double* o = out + 3 * (size_t)perm[i];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z;
+}
+
+// ------------------------------------------------------------------------------------------------ walk
+struct WalkParams {
+    const double* box;   // unified [id][6]
+    const int* son;      // [node][2] unified ids
+    int nleaf;
+    double theta, rcut;
+    double period;       // displacement unit of the images (BOXSIZE)
+    double tc[3], tw[3]; // the target domain box the images are pruned against (1_Indexing/src/remotes.c:374-386)
+};
+
+__constant__ int c_shift[27][3];
+
+// 1_Indexing/src/fmm.c:266-325
+__device__ __forceinline__ int acceptance(const double wi[3], const double wj[3], const double dist[3], double theta, double rcut) {
+    double w[3], mn[3];
+    for (int k = 0; k < 3; k++) w[k] = (wi[k] + wj[k]) * 0.5;
+    const double dd2 = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+    for (int k = 0; k < 3; k++) {
+        double m = dist[k];
+        if (m < 0.0) m = -m;
+        m -= w[k];
+        if (m <= 0.0) m = 0.0;
+        mn[k] = m;
+    }
+    if (mn[0] + mn[1] + mn[2] < 0.0001) return 0;
+    const double dm2 = mn[0] * mn[0] + mn[1] * mn[1] + mn[2] * mn[2];
+    const double c2 = rcut * rcut;
+    if (dm2 >= c2) return -1;
+    if (dd2 > 1.0 * c2) return 0;
+    double wmax = w[0];
+    if (w[1] > wmax) wmax = w[1];
+    if (w[2] > wmax) wmax = w[2];
+    wmax *= 2;
+    if (wmax * wmax < theta * theta * dd2) return 1;
+    return 0;
+}
+
+// would prepare_sendtree2 have cut this node out of the image sent for displacement `disp`? (remotes.c:374-399)
+__device__ __forceinline__ bool image_pruned(const WalkParams& P, const double nc[3], const double nw[3], const double disp[3]) {
+    double dr = 0.0;
+    for (int k = 0; k < 3; k++) {
+        double d = P.tc[k] - nc[k] - disp[k];
+        if (d < 0.0) d = -d;
+        d -= (P.tw[k] + nw[k]) * 0.5;
+        if (d > 0.0) dr += d * d;
+    }
+    dr = sqrt(dr);
+    double wmax = nw[0];
+    if (wmax < nw[1]) wmax = nw[1];
+    if (wmax < nw[2]) wmax = nw[2];
+    return dr >= P.rcut || wmax < 0.95 * P.theta * dr;
+}
+
+__host__ __device__ __forceinline__ ull item(int im, int jm, int sh) { return ((ull)(unsigned)im << 34) | ((ull)(unsigned)jm << 5) | (ull)sh; }
+
+// One level of the breadth-first dual-tree walk.  Items are (target id, source id, image); an item either emits a
+// leaf-leaf task, opens one side (2 items), opens both (self pair, 4 items) or dies.  Output slots are claimed per
+// warp.  counters[0] = items written to `out`, counters[1] = tasks emitted so far; writes beyond the capacities are
+// dropped (the host sees the counts, grows the buffers and repeats the level).
+__global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
+                                                         ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
+                                                         ull cap_task, WalkParams P) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ull stride = (ull)gridDim.x * blockDim.x;
+    const ull n_round = (n_in + 31) & ~31ull;
+    for (ull idx = (ull)blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+        int nchild = 0;
+        bool emit = false;
+        int ci[4], cj[4];
+        int im = 0, jm = 0, sh = 0;
+        if (idx < n_in) {
+            const ull it = in[idx];
+            im = (int)(it >> 34);
+            jm = (int)((it >> 5) & 0x1fffffffu);
+            sh = (int)(it & 31);
+            const bool ileaf = im < P.nleaf, jleaf = jm < P.nleaf;
+            if (sh == 0 && im == jm) {
+                if (ileaf) emit = true;
+                else {
+                    const int a0 = P.son[2 * (im - P.nleaf)], a1 = P.son[2 * (im - P.nleaf) + 1];
+                    ci[0] = a0; cj[0] = a0; ci[1] = a0; cj[1] = a1; ci[2] = a1; cj[2] = a0; ci[3] = a1; cj[3] = a1;
+                    nchild = 4;
+                }
+            } else if (ileaf && jleaf) {
+                emit = true;
+            } else {
+                const double* bi = P.box + 6 * (size_t)im;
+                const double* bj = P.box + 6 * (size_t)jm;
+                double wi[3], wj[3], cjd[3], dist[3], disp[3];
+                for (int k = 0; k < 3; k++) {
+                    disp[k] = (double)c_shift[sh][k] * P.period;
+                    wi[k] = bi[3 + k];
+                    wj[k] = bj[3 + k];
+                    cjd[k] = sh ? bj[k] + disp[k] : bj[k];
+                    dist[k] = bi[k] - cjd[k];
+                }
+                const int flag = acceptance(wi, wj, dist, P.theta, P.rcut);
+                int open = 0;     // 1: target side, 2: source side
+                if (sh == 0) {
+                    if (flag == 0) {
+                        if (ileaf) open = 2;
+                        else if (jleaf) open = 1;
+                        else open = (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2]) ? 1 : 2;
+                    }
+                } else if (flag != -1) {
+                    bool pruned = false;
+                    if (!jleaf) {
+                        const double nc[3] = {bj[0], bj[1], bj[2]};
+                        pruned = image_pruned(P, nc, wj, disp);
+                    }
+                    if (ileaf) { if (flag != 1 && !pruned) open = 2; }
+                    else if (jleaf) { if (flag != 1) open = 1; }
+                    else if (flag != 1) open = (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2] || pruned) ? 1 : 2;
+                }
+                if (open == 1) {
+                    ci[0] = P.son[2 * (im - P.nleaf)]; ci[1] = P.son[2 * (im - P.nleaf) + 1];
+                    cj[0] = cj[1] = jm;
+                    nchild = 2;
+                } else if (open == 2) {
+                    cj[0] = P.son[2 * (jm - P.nleaf)]; cj[1] = P.son[2 * (jm - P.nleaf) + 1];
+                    ci[0] = ci[1] = im;
+                    nchild = 2;
+                }
+            }
+        }
+        // claim output slots per warp
+        int incl = nchild;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(full, incl, 31);
+        ull base = 0;
+        if (total) {
+            if (lane == 0) base = atomicAdd(&counters[0], (ull)total);
+            base = __shfl_sync(full, base, 0) + (ull)(incl - nchild);
+            if (base + nchild <= cap_out)
+                for (int k = 0; k < nchild; k++) out[base + k] = item(ci[k], cj[k], sh);
+        }
+        const unsigned em = __ballot_sync(full, emit);
+        if (em) {
+            ull tb = 0;
+            if (lane == 0) tb = atomicAdd(&counters[1], (ull)__popc(em));
+            tb = __shfl_sync(full, tb, 0) + (ull)__popc(em & ((1u << lane) - 1));
+            if (emit && tb < cap_task) { tt[tb] = im; ts[tb] = jm; }
+        }
+    }
+}
+
+// after sorting: a source listed twice in a row (the same leaf reached through two different images) cannot be
+// represented with minimal-image sources
+__global__ void csr_duplicate_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col, int nrow, unsigned int* __restrict__ dup) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    unsigned int d = 0;
+    for (long long k = row_ptr[r] + 1; k < row_ptr[r + 1]; k++) d += col[k] == col[k - 1];
+    if (d) atomicAdd(dup, d);
+}
+
+}  // namespace dt
+}  // namespace p2p

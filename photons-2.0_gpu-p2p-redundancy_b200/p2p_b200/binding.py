@@ -67,6 +67,14 @@ def load_library():
     L.p2p_step_host_chunked.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _dp, C.c_int64, C.c_int64, _ip,
                                         _ip, C.c_int, _ip, _ip, _lp, C.c_int, _dp, C.c_int64, C.c_int]
     L.p2p_device_particles.argtypes = [C.c_void_p]
+    L.p2p_tree_build.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int]
+    L.p2p_tree_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp, _dp]
+    L.p2p_tree_info.argtypes = [C.c_void_p, _ip, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float), _lp]
+    L.p2p_tree_download.argtypes = [C.c_void_p, _lp, _dp, _ip, _ip, _dp, _dp, _ip, _ip, _dp, _dp, _dp]
+    L.p2p_tree_walk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp]
+    L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
+    L.p2p_download_acc_original.argtypes = [C.c_void_p, _dp]
+    L.p2p_tree_set_option.argtypes = [C.c_void_p, C.c_int]
     L.p2p_device_acc.argtypes = [C.c_void_p]
     _lib = L
     return L
@@ -246,6 +254,69 @@ class P2PContext:
             acc.shape[1], 1 if accumulate else 0))
         self.npart, self.nleaf = pos.shape[0], len(n)
         return acc
+
+    # ---- device-resident tree build / dual-tree walk
+    def tree_build(self, pos, maxleaf, bdl, bdr, direct_start=0):
+        """build_localtree on the device from positions in the caller's order (no copy: pass a contiguous float64 array)."""
+        pos = _f64(pos)
+        bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)
+        self._chk(self._L.p2p_tree_build(self._h, pos.ctypes.data_as(_dp), pos.shape[1], pos.shape[0], int(maxleaf),
+                                         bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start)))
+        self.npart = pos.shape[0]
+        self.nleaf = self.tree_info()["nleaf"]
+        self._tree_maxleaf = int(maxleaf)
+
+    def tree_upload(self, tree):
+        """Boxes and sons of a host-built tree (host.LocalTree, or any object with the same attributes) for tree_walk."""
+        nl, nn = int(tree.nleaf), int(tree.nnode)
+        lc, lw = _f64(tree.leaf_center[:nl]), _f64(tree.leaf_width[:nl])
+        son, nc, nw = _i32(tree.node_son[:nn]), _f64(tree.node_center[:nn]), _f64(tree.node_width[:nn])
+        self._chk(self._L.p2p_tree_upload(self._h, int(tree.maxleaf), nl, nn, int(tree.first_leaf), int(tree.first_node),
+                                          lc.ctypes.data_as(_dp), lw.ctypes.data_as(_dp), son.ctypes.data_as(_ip),
+                                          nc.ctypes.data_as(_dp), nw.ctypes.data_as(_dp)))
+
+    def tree_info(self):
+        nl, nn, nv = C.c_int(), C.c_int(), C.c_int()
+        mb, mw, it = C.c_float(), C.c_float(), C.c_int64()
+        self._chk(self._L.p2p_tree_info(self._h, C.byref(nl), C.byref(nn), C.byref(nv), C.byref(mb), C.byref(mw), C.byref(it)))
+        return dict(nleaf=nl.value, nnode=nn.value, nlevel=nv.value, ms_build=mb.value, ms_walk=mw.value, walk_items=it.value)
+
+    def tree_download(self):
+        """The device-built tree in the reference's layout (same keys as oracle.Tree / host.LocalTree)."""
+        info = self.tree_info()
+        nl, nn, n = info["nleaf"], info["nnode"], self.npart
+        out = dict(nleaf=nl, nnode=nn, perm=np.zeros(n, np.int64), pos=np.zeros((n, 3)),
+                   leaf_npart=np.zeros(nl, np.int32), leaf_ipart=np.zeros(nl, np.int32), leaf_center=np.zeros((nl, 3)),
+                   leaf_width=np.zeros((nl, 3)), node_npart=np.zeros(nn, np.int32), node_son=np.zeros((nn, 2), np.int32),
+                   node_split=np.zeros(nn), node_center=np.zeros((nn, 3)), node_width=np.zeros((nn, 3)))
+        self._chk(self._L.p2p_tree_download(
+            self._h, out["perm"].ctypes.data_as(_lp), out["pos"].ctypes.data_as(_dp), out["leaf_npart"].ctypes.data_as(_ip),
+            out["leaf_ipart"].ctypes.data_as(_ip), out["leaf_center"].ctypes.data_as(_dp), out["leaf_width"].ctypes.data_as(_dp),
+            out["node_npart"].ctypes.data_as(_ip), out["node_son"].ctypes.data_as(_ip), out["node_split"].ctypes.data_as(_dp),
+            out["node_center"].ctypes.data_as(_dp), out["node_width"].ctypes.data_as(_dp)))
+        return out
+
+    def tree_walk(self, theta, rcut, period=0.0, tcenter=None, twidth=None):
+        """Dual-tree walk on the device (local list, plus the 26 periodic images when period > 0); appends tasks."""
+        tc = np.ascontiguousarray(tcenter if tcenter is not None else np.zeros(3), np.float64)
+        tw = np.ascontiguousarray(twidth if twidth is not None else np.zeros(3), np.float64)
+        self._chk(self._L.p2p_tree_walk(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp),
+                                        tw.ctypes.data_as(_dp)))
+
+    def csr_duplicates(self):
+        d = C.c_int64()
+        self._chk(self._L.p2p_csr_duplicates(self._h, C.byref(d)))
+        return d.value
+
+    def download_acc_original(self, out=None):
+        if out is None:
+            out = np.zeros((self.npart, 3))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.npart, 3)
+        self._chk(self._L.p2p_download_acc_original(self._h, out.ctypes.data_as(_dp)))
+        return out
+
+    def tree_set_option(self, seq_sum_plain_max=-1):
+        self._chk(self._L.p2p_tree_set_option(self._h, int(seq_sum_plain_max)))
 
     @property
     def device_particles_ptr(self):

@@ -1,0 +1,187 @@
+"""CPU models of the two non-obvious steps of the device tree build (csrc/device_tree.cuh), checked against the
+reference's sequential loops as restated in oracle/p2p_oracle.c (mean_split, 1_Indexing/src/fmm.c:29-77):
+
+  * the closed form of the Hoare-like partition (which elements change place, and the left count with its quirk);
+  * the exact parallel evaluation of the SEQUENTIAL fp64 sum (parity transducers composed by a scan).
+
+The CUDA kernels implement exactly these models; their bit-for-bit agreement with the oracle's tree is checked on
+the GPU in tests/test_gpu_device_tree.py.
+"""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+
+def ref_partition(x):
+    """The reference loop on one coordinate array; returns (permutation applied, np0, mean)."""
+    x = list(x)
+    idx = list(range(len(x)))
+    n = len(x)
+    mean = 0.0
+    for v in x:
+        mean += v
+    mean /= float(n)
+    but = n - 1
+    i = 0
+    while i < but:
+        if x[i] > mean:
+            while x[but] > mean and but > i:
+                but -= 1
+            x[i], x[but] = x[but], x[i]
+            idx[i], idx[but] = idx[but], idx[i]
+        i += 1
+    return idx, but, mean
+
+
+def model_partition(x, mean):
+    """Closed form used by flag_kernel / split_kernel / slot_kernel / swap_kernel."""
+    x = np.asarray(x)
+    n = len(x)
+    big = x > mean
+    G = np.concatenate([[0], np.cumsum(big)])
+    nbig = int(G[n])
+    np0 = n - 1 if nbig == 0 else n - nbig
+    slot = {}
+    for i in range(n):
+        if i >= np0 and not big[i]:
+            cb = int(G[i])
+            r = (n - nbig) - (i - cb) - 1
+            slot[r] = i
+    idx = list(range(n))
+    for i in range(np0):
+        if big[i]:
+            j = slot[int(G[i])]
+            idx[i], idx[j] = idx[j], idx[i]
+    return idx, np0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_partition_closed_form(seed):
+    rng = np.random.default_rng(seed)
+    for trial in range(400):
+        n = int(rng.integers(3, 120))
+        kind = trial % 5
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = rng.integers(0, 4, n).astype(np.float64)          # many ties
+        elif kind == 2:
+            x = np.full(n, 3.25)                                    # all equal: the unexamined-last-element quirk
+        elif kind == 3:
+            x = np.sort(rng.random(n))[::-1].copy()                # descending
+        else:
+            x = np.sort(rng.random(n))
+            x[-1] = x[0]                                            # small last element
+        ref_idx, ref_np0, mean = ref_partition(x)
+        idx, np0 = model_partition(x, mean)
+        assert np0 == ref_np0
+        assert idx == ref_idx
+
+
+def seq_sum(x):
+    s = 0.0
+    for v in x:
+        s += float(v)
+    return s
+
+
+def dbits(x):
+    return struct.unpack("<q", struct.pack("<d", x))[0]
+
+
+def from_bits(b):
+    return struct.unpack("<d", struct.pack("<q", b))[0]
+
+
+def model_seq_sum(x, lanes=32, per_lane=8):
+    """seq_sum_warp of device_tree.cuh, lane by lane, with Python integers standing in for the int64 registers."""
+    x = [float(v) for v in x]
+    n = len(x)
+    S = 0.0
+    pos = 0
+    rounds = 0
+    while pos < n:
+        rounds += 1
+        e = ((dbits(S) >> 52) & 0x7FF) - 1023
+        okS = S > 0.0 and -900 <= e <= 900
+        scale = 2.0 ** (52 - e) if okS else 1.0
+        top = 2.0 ** (e + 1) if okS else 0.0
+        lane_t = []
+        vals = []
+        for lane in range(lanes):
+            v = [x[pos + lane * per_lane + k] if pos + lane * per_lane + k < n else 0.0 for k in range(per_lane)]
+            vals.append(v)
+            d = [0, 0]
+            p = [0, 1]
+            hard = not okS
+            for xv in v:
+                if not (xv >= 0.0 and xv < top):
+                    hard = True
+                y = xv * scale
+                if not math.isfinite(y):
+                    hard = True
+                    continue
+                qf = math.floor(y)
+                r = y - qf
+                q = int(qf)
+                gt, tie = r > 0.5, r == 0.5
+                for s in range(2):
+                    t = p[s] ^ (q & 1)
+                    c = 1 if (gt or (tie and t)) else 0
+                    d[s] += q + c
+                    p[s] = t ^ c
+            lane_t.append((d, p, hard))
+        kS = ((dbits(S) & 0xFFFFFFFFFFFFF) | (1 << 52)) if okS else 0
+        par = kS & 1
+        # inclusive composition lane by lane (the warp scan computes the same thing in log steps)
+        inc = []
+        cur_d, cur_p = 0, par
+        first_bad = None
+        for lane in range(lanes):
+            d, p, hard = lane_t[lane]
+            cur_d += d[cur_p]
+            cur_p = p[cur_p]
+            inc.append(cur_d)
+            if first_bad is None and (hard or kS + cur_d >= (1 << 53)):
+                first_bad = lane
+        u = 2.0 ** (e - 52) if okS else 0.0
+        if first_bad is None:
+            S = u * float(kS + inc[-1])
+            pos += lanes * per_lane
+            continue
+        if first_bad > 0:
+            S = u * float(kS + inc[first_bad - 1])
+        for xv in vals[first_bad]:
+            S += xv
+        pos += per_lane * (first_bad + 1)
+    return S, rounds
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sequential_sum_transducer(seed):
+    rng = np.random.default_rng(100 + seed)
+    cases = []
+    for n in (1, 7, 255, 256, 257, 3000, 20000):
+        cases.append(rng.random(n) * 8.0e5)                                             # generic doubles in a box
+        cases.append((rng.random(n) * 8.0e5).astype(np.float32).astype(np.float64))    # float32-exact (ties are common)
+        cases.append(np.round(rng.random(n) * 64.0) / 64.0)                             # coarse grid: exact ties everywhere
+        cases.append(rng.random(n) * 1e-3 + (rng.random(n) < 0.01) * 1e5)               # wide dynamic range
+    cases.append(np.zeros(100))
+    cases.append(np.concatenate([np.zeros(20), rng.random(600)]))
+    cases.append(np.array([5e-324, 1e-310, 3.0, 1e-300] * 100))                         # denormals mixed in
+    cases.append(np.array([-1.0, 2.0, 3.0] * 50))                                       # negative values: native path
+    for x in cases:
+        ref = seq_sum(x)
+        got, rounds = model_seq_sum(x)
+        assert dbits(got) == dbits(ref), (len(x), got, ref)
+
+
+def test_transducer_is_parallel_for_long_runs():
+    """long runs must mostly take the 256-per-round path, not the 8-per-round fallback"""
+    rng = np.random.default_rng(7)
+    x = (rng.random(100000) * 8.0e5).astype(np.float32).astype(np.float64)
+    got, rounds = model_seq_sum(x)
+    assert dbits(got) == dbits(seq_sum(x))
+    assert rounds < 100000 / 256 + 80

@@ -1,0 +1,44 @@
+"""Times the device-resident short-range step (tree build, dual-tree walk, packing, forces) on one GPU.
+usage: python tools/device_step.py [nside] [maxleaf] [reps] [--clustered]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200"))
+import p2p_b200  # noqa: E402
+from p2p_b200 import host, synth  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+nside = int(args[0]) if len(args) > 0 else 128
+maxleaf = int(args[1]) if len(args) > 1 else 32
+reps = int(args[2]) if len(args) > 2 else 3
+pos, box = (synth.clustered(nside) if "--clustered" in sys.argv else synth.zeldovich_like(nside))
+rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
+ctx = p2p_b200.P2PContext(0)
+ctx.set_physics(1.0, eps, rs)
+ctx.set_box([0.0, 0.0, 0.0], box)
+bdl, bdr = np.zeros(3), np.full(3, box)
+import torch  # noqa: E402  (pinned host buffers)
+ppos = torch.from_numpy(pos).pin_memory().numpy()
+acc = torch.empty((pos.shape[0], 3), dtype=torch.float64).pin_memory().numpy()
+for r in range(reps):
+    t0 = time.perf_counter()
+    ctx.tree_build(ppos, maxleaf, bdl, bdr, 0)
+    t1 = time.perf_counter()
+    ctx.clear_tasks()
+    ctx.tree_walk(0.4, rcut, box, 0.5 * (bdr + bdl), bdr - bdl)
+    t2 = time.perf_counter()
+    ctx.build_csr()
+    ctx.compute()
+    ctx.download_acc_original(acc)
+    t3 = time.perf_counter()
+    info = ctx.tree_info()
+    ms_k, ms_csr = ctx.last_timings()
+    nt, npairs = ctx.counts()
+    print(f"rep {r}: total {1e3 * (t3 - t0):.1f} ms | build {1e3 * (t1 - t0):.1f} (device {info['ms_build']:.1f}) "
+          f"walk {1e3 * (t2 - t1):.1f} (device {info['ms_walk']:.1f}, {info['walk_items']} items) "
+          f"csr {ms_csr:.1f} force {ms_k:.1f} rest {1e3 * (t3 - t2) - ms_csr - ms_k:.1f} | "
+          f"{info['nleaf']} leaves {info['nlevel']} levels {nt} tasks {npairs} pairs dup {ctx.csr_duplicates()}", flush=True)
