@@ -38,6 +38,7 @@ struct p2p_dtree {
     long long walk_tasks = 0, walk_items = 0;
     int walk_levels = 0;
     int plain_max = p2p::dt::kSeqPlainMax;
+    bool block_mode = true;
     float ms_build = 0.f, ms_walk = 0.f;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
@@ -96,6 +97,8 @@ int p2p_tree_set_option(p2p_ctx* c, int seq_sum_plain_max) {
     p2p_dtree* t;
     int r = get_tree(c, &t);
     if (r) return r;
+    // -2: default thresholds but every node through the warp kernel (no block-per-node variant)
+    t->block_mode = seq_sum_plain_max != -2;
     t->plain_max = seq_sum_plain_max < 0 ? p2p::dt::kSeqPlainMax : seq_sum_plain_max;
     return 0;
 }
@@ -187,25 +190,31 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     CU(cudaMemcpyAsync(A.t_parent, &root[2], 4, cudaMemcpyHostToDevice, st));
     // ---- levels
     std::vector<int> lvl_begin{0}, lvl_count{1};
-    int total_nodes = 1;
+    int total_nodes = 1, longest = (int)npart;
     for (int lvl = 0;; lvl++) {
         if (lvl > 256) return fail(P2P_ERR_ARG, "kd-tree deeper than 256 levels (more than maxleaf coincident particles?)");
         const int b = lvl_begin[lvl], n = lvl_count[lvl], dir = (direct_start + lvl) % 3;
+        // few, long nodes: a block each; many nodes: a warp each
+        const int block_min = (t->block_mode && n <= c->num_sm * 4) ? 2048 : 0x7fffffff;
+        if (longest > block_min)
+            p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min);
         const int warps = std::min(n, c->num_sm * 64);
-        p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max);
+        p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max, block_min);
         p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
         p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
         p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
         p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
         p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
         p2p::dt::child_scan_kernel<<<1, 1024, 0, st>>>(t->child_cnt.p, n, t->d_scalar);
-        p2p::dt::children_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p, b + n, (int)ncap);
+        CU(cudaMemsetAsync(t->d_scalar + 2, 0, sizeof(int), st));
+        p2p::dt::children_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p, b + n, (int)ncap, t->d_scalar + 2);
         p2p::dt::slot_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
         p2p::dt::swap_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(t->h_scalar, t->d_scalar, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(t->h_scalar, t->d_scalar, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         const int nnext = t->h_scalar[0];
+        longest = t->h_scalar[2];
         std::swap(A.seg, A.seg_next);
         if (nnext == 0) { t->nlevel = lvl + 1; break; }
         total_nodes += nnext;

@@ -234,10 +234,11 @@ __device__ __forceinline__ double seq_sum_warp(const double* __restrict__ x, lon
     return S;
 }
 
-constexpr int kSeqPlainMax = 4096;   // runs up to this length use the plain fold
+constexpr int kSeqPlainMax = 256;    // runs up to this length use the plain fold
+constexpr int kBlockWarps = 32;      // warps of the block-per-node variant (tile = 32 x 256 values)
 
-// one warp per node of the level: split value
-__global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int plain_max) {
+// one warp per node of the level: split value.  Nodes longer than skip_above are left to mean_block_kernel.
+__global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int plain_max, int skip_above) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     const double* __restrict__ X = A.x[dir];
@@ -245,6 +246,7 @@ __global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir
         const int t = lvl_begin + n;
         const long long start = A.t_start[t];
         const int len = A.t_len[t];
+        if (len > skip_above) continue;
         double split = 0.0;
         if (len == 2) {
             split = 0.5 * (X[start] + X[start + 1]);
@@ -253,6 +255,123 @@ __global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir
             split = s / (double)len;
         }
         if ((threadIdx.x & 31) == 0) A.t_split[t] = split;
+    }
+}
+
+// The same transducer evaluation with a whole block per node (the top levels of the tree have fewer nodes than
+// the device has SMs): every thread folds 8 values, warps scan, warp 0 scans the warp summaries, and the first
+// thread whose values leave the binade ends the tile exactly as in seq_sum_warp.
+__global__ void __launch_bounds__(kBlockWarps * 32) mean_block_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int min_len) {
+    constexpr int NW = kBlockWarps;
+    __shared__ long long s_a0[NW], s_a1[NW], s_pre[NW];
+    __shared__ int s_q0[NW], s_q1[NW], s_par[NW], s_bad[NW];
+    __shared__ long long s_tot;
+    __shared__ double s_v[8];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double* __restrict__ X = A.x[dir];
+    for (int n = blockIdx.x; n < lvl_count; n += gridDim.x) {
+        const int t = lvl_begin + n;
+        const int len = A.t_len[t];
+        if (len <= min_len) continue;
+        const long long start = A.t_start[t];
+        double S = 0.0;
+        int pos = 0;
+        while (pos < len) {
+            const int e = (int)((__double_as_longlong(S) >> 52) & 0x7ff) - 1023;
+            const bool okS = S > 0.0 && e >= -900 && e <= 900;
+            const int my = pos + tid * 8;
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (my + k < len) ? X[start + my + k] : 0.0;
+            long long d0 = 0, d1 = 0;
+            int p0 = 0, p1 = 1;
+            bool hard = !okS;
+            const double scale = okS ? __longlong_as_double((long long)(1023 + 52 - e) << 52) : 1.0;
+            const double top = okS ? __longlong_as_double((long long)(1023 + e + 1) << 52) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double xv = v[k];
+                if (!(xv >= 0.0 && xv < top)) hard = true;
+                const double y = xv * scale;
+                const double qf = floor(y);
+                const double r = y - qf;
+                const long long q = (long long)qf;
+                const int gt = r > 0.5, tie = r == 0.5;
+                int t0 = p0 ^ (int)(q & 1), t1 = p1 ^ (int)(q & 1);
+                const int c0 = gt | (tie & t0), c1 = gt | (tie & t1);
+                d0 += q + c0;
+                d1 += q + c1;
+                p0 = t0 ^ c0;
+                p1 = t1 ^ c1;
+            }
+            long long a0 = d0, a1 = d1;
+            int q0 = p0, q1 = p1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long b0 = __shfl_up_sync(full, a0, o), b1 = __shfl_up_sync(full, a1, o);
+                const int r0 = __shfl_up_sync(full, q0, o), r1 = __shfl_up_sync(full, q1, o);
+                if (lane >= o) {
+                    const long long n0 = b0 + (r0 ? a1 : a0), n1 = b1 + (r1 ? a1 : a0);
+                    const int m0 = r0 ? q1 : q0, m1 = r1 ? q1 : q0;
+                    a0 = n0; a1 = n1; q0 = m0; q1 = m1;
+                }
+            }
+            if (lane == 31) { s_a0[w] = a0; s_a1[w] = a1; s_q0[w] = q0; s_q1[w] = q1; }
+            const long long kS = okS ? ((__double_as_longlong(S) & 0xfffffffffffffLL) | (1LL << 52)) : 0;
+            const int parS = (int)(kS & 1);
+            __syncthreads();
+            if (w == 0) {
+                long long A0 = s_a0[lane], A1 = s_a1[lane];
+                int Q0 = s_q0[lane], Q1 = s_q1[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long b0 = __shfl_up_sync(full, A0, o), b1 = __shfl_up_sync(full, A1, o);
+                    const int r0 = __shfl_up_sync(full, Q0, o), r1 = __shfl_up_sync(full, Q1, o);
+                    if (lane >= o) {
+                        const long long n0 = b0 + (r0 ? A1 : A0), n1 = b1 + (r1 ? A1 : A0);
+                        const int m0 = r0 ? Q1 : Q0, m1 = r1 ? Q1 : Q0;
+                        A0 = n0; A1 = n1; Q0 = m0; Q1 = m1;
+                    }
+                }
+                const long long inc = parS ? A1 : A0;
+                const int par = parS ? Q1 : Q0;
+                long long ex = __shfl_up_sync(full, inc, 1);
+                int exp_ = __shfl_up_sync(full, par, 1);
+                if (lane == 0) { ex = 0; exp_ = parS; }
+                s_pre[lane] = ex;
+                s_par[lane] = exp_;
+            }
+            __syncthreads();
+            const long long incl = s_pre[w] + (s_par[w] ? a1 : a0);
+            const bool cross = hard || (kS + incl >= (1LL << 53));
+            const unsigned bad = __ballot_sync(full, cross);
+            if (lane == 0) s_bad[w] = bad ? (w * 32 + __ffs(bad) - 1) : 0x7fffffff;
+            __syncthreads();
+            int f = s_bad[lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) f = min(f, __shfl_xor_sync(full, f, o));
+            const double u = __longlong_as_double((long long)(1023 + (okS ? e : 0) - 52) << 52);
+            if (f == 0x7fffffff) {
+                if (tid == NW * 32 - 1) s_tot = incl;
+                __syncthreads();
+                S = u * (double)(kS + s_tot);
+                pos += NW * 256;
+            } else {
+                if (tid == f - 1) s_tot = incl;
+                if (tid == f) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s_v[k] = v[k];
+                }
+                __syncthreads();
+                if (f > 0) S = u * (double)(kS + s_tot);
+#pragma unroll
+                for (int k = 0; k < 8; k++) S += s_v[k];
+                pos += 8 * (f + 1);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) A.t_split[t] = S / (double)len;
     }
 }
 
@@ -328,7 +447,7 @@ __global__ void child_scan_kernel(int* __restrict__ cnt, int n, int* __restrict_
 }
 
 __global__ void children_kernel(BuildArrays A, int lvl_begin, int lvl_count, int maxleaf, const int* __restrict__ child_off,
-                                int next_begin, int node_cap) {
+                                int next_begin, int node_cap, int* __restrict__ longest) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= lvl_count) return;
     const int t = lvl_begin + n;
@@ -345,6 +464,8 @@ __global__ void children_kernel(BuildArrays A, int lvl_begin, int lvl_count, int
     } else c1 = -1 - np1;
     A.t_child[2 * t] = c0;
     A.t_child[2 * t + 1] = c1;
+    const int mx = max(np0 > maxleaf ? np0 : 0, np1 > maxleaf ? np1 : 0);
+    if (mx) atomicMax(longest, mx);
 }
 
 // positions of the right-zone small elements by rank from the right, and the owner of every position at the next level
