@@ -319,9 +319,23 @@ def main():
             barrier()
             res[mode] = (time.perf_counter() - t0, tp)
             assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
-        full_step = {"what": "tree build + H2D + dual-tree walk (32 target chunks) + CSR + P2P + 26 image walks + D2H, one rank",
-                     "pipelined_s": res[True][0], "pipelined_breakdown": res[True][1],
-                     "sequential_s": res[False][0], "sequential_breakdown": res[False][1], "host_threads": nthreads}
+        # the same step with the list producers on the device (tree build + dual-tree walk kernels)
+        ppos = torch.from_numpy(pos).pin_memory().numpy()
+        dev = None
+        for _ in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            _, td, n_t, n_p = step.run_device_step(ctx2, ppos, box, args.maxleaf, args.nside, mass, THETA, periodic=True, acc_out=acc2)
+            barrier()
+            dev = (time.perf_counter() - t0, td)
+            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
+        del ppos
+        full_step = {"what": "positions in, accelerations out: tree build + dual-tree walk + 26 periodic-image walks + CSR + P2P, one rank",
+                     "device_resident_s": dev[0], "device_resident_breakdown": dev[1],
+                     "host_pipelined_s": res[True][0], "host_pipelined_breakdown": res[True][1],
+                     "host_sequential_s": res[False][0], "host_sequential_breakdown": res[False][1], "host_threads": nthreads,
+                     "note": "device_resident: list producers as CUDA kernels (p2p_step_device); host_*: list producers on the host "
+                             "cores (libp2p_host.so), pipelined = host walks chunk c+1 while the device computes chunk c"}
         ctx2.close()
     del pos
 

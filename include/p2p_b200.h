@@ -159,7 +159,8 @@ int p2p_tree_build(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npar
 int p2p_tree_upload(p2p_ctx* ctx, int maxleaf, int nleaf, int nnode, int first_leaf, int first_node,
                     const double* leaf_center, const double* leaf_width, const int* node_son, const double* node_center,
                     const double* node_width);
-int p2p_tree_info(p2p_ctx* ctx, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items);
+int p2p_tree_info(p2p_ctx* ctx, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items,
+                  double* max_leaf_width);
 /* copies of the device-built tree in the reference's layout (NULL pointers are skipped); perm[i] = index, in the
  * array given to p2p_tree_build, of the particle now at tree position i; node_son holds global ids with
  * first_leaf = npart and first_node = npart + 2 npart / maxleaf (1_Indexing/src/fmm.c:199-212) */
@@ -175,6 +176,12 @@ int p2p_tree_walk(p2p_ctx* ctx, double theta, double rcut, double period, const 
 int p2p_csr_duplicates(p2p_ctx* ctx, int64_t* ndup);
 /* accelerations in the ORDER OF THE POSITIONS GIVEN TO p2p_tree_build, packed rows of 3 doubles */
 int p2p_download_acc_original(p2p_ctx* ctx, double* acc);
+/* The whole short-range P2P step of one rank in one call (replaces fmm_prepare + fmm_task + fmm_ext for the P2P part,
+ * 1_Indexing/src/photoNs.c:97-123): host positions in the caller's order in, host accelerations in the same order out;
+ * tree build, walk (26 periodic images when period > 0), packing and forces on the device.  Fails with P2P_ERR_ARG
+ * when r_cut + 2 x (largest leaf width) reaches period / 2 (minimal-image sources would be ambiguous). */
+int p2p_step_device(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
+                    const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc);
 /* test knob: runs up to this length use the plain in-order fold for the split mean, longer ones the exact parallel
  * evaluation of the same sequential sum (< 0 restores the default) */
 int p2p_tree_set_option(p2p_ctx* ctx, int seq_sum_plain_max);

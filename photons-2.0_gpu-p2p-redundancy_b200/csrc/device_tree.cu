@@ -35,6 +35,8 @@ struct p2p_dtree {
     ull* d_wcount = nullptr;     // [0] next frontier, [1] tasks
     ull* h_wcount = nullptr;     // pinned
     unsigned int* d_dup = nullptr;
+    unsigned long long* d_maxw = nullptr;
+    double max_leaf_width = 0.0;
     long long walk_tasks = 0, walk_items = 0;
     int walk_levels = 0;
     int plain_max = p2p::dt::kSeqPlainMax;
@@ -58,6 +60,7 @@ void p2p_dtree_release(p2p_dtree* t) {
     if (t->d_wcount) cudaFree(t->d_wcount);
     if (t->h_wcount) cudaFreeHost(t->h_wcount);
     if (t->d_dup) cudaFree(t->d_dup);
+    if (t->d_maxw) cudaFree(t->d_maxw);
     if (t->e0) cudaEventDestroy(t->e0);
     if (t->e1) cudaEventDestroy(t->e1);
     delete t;
@@ -74,6 +77,7 @@ int get_tree(p2p_ctx* c, p2p_dtree** out) {
         CU(cudaMalloc(&t->d_wcount, 2 * sizeof(ull)));
         CU(cudaMallocHost(&t->h_wcount, 2 * sizeof(ull)));
         CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
+        CU(cudaMalloc(&t->d_maxw, sizeof(unsigned long long)));
         CU(cudaEventCreate(&t->e0));
         CU(cudaEventCreate(&t->e1));
         static const int shifts[27][3] = {{0, 0, 0},
@@ -237,7 +241,8 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     CU(t->leaf_npart.reserve((size_t)nleaf + 1, st)); CU(t->leaf_ipart.reserve((size_t)nleaf + 1, st));
     p2p::dt::TreeOut O;
     O.nleaf = nleaf; O.box = t->box.p; O.son = t->son.p; O.node_npart = t->node_npart.p; O.node_split = t->node_split.p;
-    O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p;
+    O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p; O.max_width = t->d_maxw;
+    CU(cudaMemsetAsync(t->d_maxw, 0, sizeof(unsigned long long), st));
     for (int lvl = 0; lvl < t->nlevel; lvl++)
         p2p::dt::assign_down_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, O, lvl_begin[lvl], lvl_count[lvl], (direct_start + lvl) % 3,
                                                                                bdl[0], bdl[1], bdl[2], bdr[0], bdr[1], bdr[2]);
@@ -257,14 +262,18 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     c->acc_tasks = 0;
     c->max_target_leaf = maxleaf;
     CU(cudaEventRecord(t->e1, st));
+    unsigned long long wbits = 0;
+    CU(cudaMemcpyAsync(&wbits, t->d_maxw, sizeof wbits, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    memcpy(&t->max_leaf_width, &wbits, sizeof wbits);
     CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
     t->valid = true; t->built_here = true;
     return 0;
 }
 
-int p2p_tree_info(p2p_ctx* c, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items) {
+int p2p_tree_info(p2p_ctx* c, int* nleaf, int* nnode, int* nlevel, float* ms_build, float* ms_walk, int64_t* walk_items,
+                  double* max_leaf_width) {
     if (!c || !c->dtree || !c->dtree->valid) return fail(P2P_ERR_STATE, "no device tree");
     if (nleaf) *nleaf = c->dtree->nleaf;
     if (nnode) *nnode = c->dtree->nnode;
@@ -272,6 +281,7 @@ int p2p_tree_info(p2p_ctx* c, int* nleaf, int* nnode, int* nlevel, float* ms_bui
     if (ms_build) *ms_build = c->dtree->ms_build;
     if (ms_walk) *ms_walk = c->dtree->ms_walk;
     if (walk_items) *walk_items = c->dtree->walk_items;
+    if (max_leaf_width) *max_leaf_width = c->dtree->built_here ? c->dtree->max_leaf_width : -1.0;
     return 0;
 }
 
@@ -430,6 +440,24 @@ int p2p_download_acc_original(p2p_ctx* c, double* acc) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(acc, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
     return p2p_synchronize(c);
+}
+
+// The whole short-range P2P step of one rank in one call: positions (caller's order) in, accelerations (same order)
+// out; tree build, walk (with the 26 periodic images when period > 0), packing and forces on the device.
+int p2p_step_device(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
+                    const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc) {
+    int r;
+    if ((r = p2p_tree_build(c, pos, stride, npart, maxleaf, bdl, bdr, direct_start))) return r;
+    if (period > 0.0 && !(rcut + 2.0 * c->dtree->max_leaf_width < 0.5 * period))
+        return fail(P2P_ERR_ARG, "r_cut (%g) + 2 x largest leaf width (%g) reaches half the period (%g): the box is too small for "
+                    "minimal-image sources", rcut, c->dtree->max_leaf_width, 0.5 * period);
+    if ((r = p2p_clear_tasks(c))) return r;
+    double tc[3], tw[3];
+    for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }   // the local root cell (toptree.c:18-45)
+    if ((r = p2p_tree_walk(c, theta, rcut, period, tc, tw))) return r;
+    if ((r = p2p_build_csr(c))) return r;
+    if ((r = p2p_compute(c))) return r;
+    return p2p_download_acc_original(c, acc);
 }
 
 }  // extern "C"

@@ -534,6 +534,7 @@ struct TreeOut {
     double* node_split;
     int* leaf_npart;
     int* leaf_ipart;
+    unsigned long long* max_width;   // bits of the largest leaf width (non-negative doubles order like integers)
 };
 
 // top-down: final ids, kd cells, output arrays
@@ -591,6 +592,8 @@ __global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int 
             for (int k = 0; k < 3; k++) { b[k] = ncen[k]; b[3 + k] = nwid[k]; }
             if (s == 0) { b[3 + dir] = split - lo[dir]; b[dir] = 0.5 * (lo[dir] + split); }
             else        { b[3 + dir] = hi[dir] - split; b[dir] = 0.5 * (hi[dir] + split); }
+            const double wm = fmax(b[3], fmax(b[4], b[5]));
+            if (wm > 0.0) atomicMax(O.max_width, (unsigned long long)__double_as_longlong(wm));
             lb += 1;
             ip += cnt;
         }

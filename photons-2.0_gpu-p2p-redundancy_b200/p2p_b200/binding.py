@@ -69,7 +69,8 @@ def load_library():
     L.p2p_device_particles.argtypes = [C.c_void_p]
     L.p2p_tree_build.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int]
     L.p2p_tree_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp, _dp]
-    L.p2p_tree_info.argtypes = [C.c_void_p, _ip, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float), _lp]
+    L.p2p_tree_info.argtypes = [C.c_void_p, _ip, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float), _lp, _dp]
+    L.p2p_step_device.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp]
     L.p2p_tree_download.argtypes = [C.c_void_p, _lp, _dp, _ip, _ip, _dp, _dp, _ip, _ip, _dp, _dp, _dp]
     L.p2p_tree_walk.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp]
     L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
@@ -277,9 +278,11 @@ class P2PContext:
 
     def tree_info(self):
         nl, nn, nv = C.c_int(), C.c_int(), C.c_int()
-        mb, mw, it = C.c_float(), C.c_float(), C.c_int64()
-        self._chk(self._L.p2p_tree_info(self._h, C.byref(nl), C.byref(nn), C.byref(nv), C.byref(mb), C.byref(mw), C.byref(it)))
-        return dict(nleaf=nl.value, nnode=nn.value, nlevel=nv.value, ms_build=mb.value, ms_walk=mw.value, walk_items=it.value)
+        mb, mw, it, wd = C.c_float(), C.c_float(), C.c_int64(), C.c_double()
+        self._chk(self._L.p2p_tree_info(self._h, C.byref(nl), C.byref(nn), C.byref(nv), C.byref(mb), C.byref(mw), C.byref(it),
+                                        C.byref(wd)))
+        return dict(nleaf=nl.value, nnode=nn.value, nlevel=nv.value, ms_build=mb.value, ms_walk=mw.value, walk_items=it.value,
+                    max_leaf_width=wd.value)
 
     def tree_download(self):
         """The device-built tree in the reference's layout (same keys as oracle.Tree / host.LocalTree)."""
@@ -314,6 +317,21 @@ class P2PContext:
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.npart, 3)
         self._chk(self._L.p2p_download_acc_original(self._h, out.ctypes.data_as(_dp)))
         return out
+
+    def step_device(self, pos, maxleaf, bdl, bdr, theta, rcut, period=0.0, direct_start=0, acc=None):
+        """Positions (caller's order) in, accelerations (same order) out; everything in between on the device.
+        No copies: pass contiguous float64 arrays (pinned for full PCIe rate)."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous and pos.ndim == 2 and pos.shape[1] >= 3
+        if acc is None:
+            acc = np.zeros((pos.shape[0], 3))
+        assert acc.dtype == np.float64 and acc.flags.c_contiguous and acc.shape == (pos.shape[0], 3)
+        bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)
+        self._chk(self._L.p2p_step_device(self._h, pos.ctypes.data_as(_dp), pos.shape[1], pos.shape[0], int(maxleaf),
+                                          bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start), float(theta),
+                                          float(rcut), float(period), acc.ctypes.data_as(_dp)))
+        self.npart = pos.shape[0]
+        self.nleaf = self.tree_info()["nleaf"]
+        return acc
 
     def tree_set_option(self, seq_sum_plain_max=-1):
         self._chk(self._L.p2p_tree_set_option(self._h, int(seq_sum_plain_max)))

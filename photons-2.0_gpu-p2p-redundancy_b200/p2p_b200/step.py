@@ -248,3 +248,22 @@ def run_full_step(ctx, pos, box, maxleaf, nside, mass, theta=0.4, nchunks=16, pe
     t["download_s"] = time.perf_counter() - t4
     t["total_s"] = time.perf_counter() - t0
     return acc, T, t, ntask, npairs
+
+
+def run_device_step(ctx, pos, box, maxleaf, nside, mass, theta=0.4, periodic=True, truncated=True, acc_out=None):
+    """The whole short-range step with the list producers ON THE DEVICE (csrc/device_tree.cuh): one upload of
+    the positions, tree build, dual-tree walk incl. the 26 periodic images, packing, forces, one download.
+    Same tree, same task multiset and the same forces (up to FP32 summation order) as run_full_step.
+    Returns (acc in the ORDER OF `pos`, timings dict, ntask, npairs)."""
+    t0 = time.perf_counter()
+    rs, rcut, eps = host.derived_params(box, nside, pos.shape[0])
+    ctx.set_physics(mass, eps, rs if truncated else 0.0)
+    ctx.set_box([0.0, 0.0, 0.0], box)
+    acc = ctx.step_device(pos, maxleaf, [0.0] * 3, [box] * 3, theta, rcut, box if periodic else 0.0, 0, acc_out)
+    total = time.perf_counter() - t0
+    info = ctx.tree_info()
+    ms_force, ms_csr = ctx.last_timings()
+    ntask, npairs = ctx.counts()
+    t = dict(total_s=total, build_ms=info["ms_build"], walk_ms=info["ms_walk"], csr_ms=ms_csr, force_ms=ms_force,
+             tree_levels=info["nlevel"], walk_items=info["walk_items"], leaves=info["nleaf"])
+    return acc, t, ntask, npairs
