@@ -182,6 +182,28 @@ int p2p_download_acc_original(p2p_ctx* ctx, double* acc);
  * when r_cut + 2 x (largest leaf width) reaches period / 2 (minimal-image sources would be ambiguous). */
 int p2p_step_device(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
                     const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc);
+/* ---- multi-rank device path: one tree per rank, every rank walks its own tree against all of them -----------
+ * Replaces fmm_ext / fmm_remote (1_Indexing/src/fmm.c:1026-1145, 1_Indexing/src/remotes.c:740-809): instead of
+ * pruning, shipping and re-walking 27 x P halo images, the ranks all-gather their tree TOPOLOGY (boxes + sons, a few
+ * MB), each rank walks against every peer tree with the sender-side cuts of prepare_sendtree2 evaluated on the fly,
+ * and only the particles of the leaves the lists actually reference travel afterwards (one all-to-all-v).
+ * All pointers below are DEVICE pointers owned by the caller (e.g. torch tensors used with torch.distributed). */
+/* box [(nleaf + nnode)][6] doubles {centre, width}, son [nnode][2] ints (leaf l -> l, node n -> nleaf + n),
+ * leaf [nleaf] {first particle, count} */
+int p2p_tree_export(p2p_ctx* ctx, void* d_box, void* d_son, void* d_leaf);
+/* peers' exports concatenated in rank order; sources of rank `me` are listed under local leaf ids, those of rank p
+ * under nleaf_local + (leaves of the ranks before p, skipping me) + leaf */
+int p2p_tree_walk_peers(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
+                        const void* d_son_all);
+/* marks[g] = 1 (uint8) for every ghost leaf g (0-based behind the local leaves) that the task list references */
+int p2p_ghost_marks(p2p_ctx* ctx, void* d_marks);
+/* out[offset[l] ...) = fixed-point particles (int4) of every LOCAL leaf l with marks[l] != 0; offset: int64 per leaf */
+int p2p_gather_leaves(p2p_ctx* ctx, const void* d_marks, const void* d_offset, void* d_out);
+/* ghost particles as p2p_gather_leaves of their owners produced them, and the table of ALL ghost leaves
+ * (int32 start relative to d_part, int32 count; count 0 for leaves nobody references) */
+int p2p_set_ghosts_device(p2p_ctx* ctx, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf);
+
 /* test knob: runs up to this length use the plain in-order fold for the split mean, longer ones the exact parallel
  * evaluation of the same sequential sum (< 0 restores the default) */
 int p2p_tree_set_option(p2p_ctx* ctx, int seq_sum_plain_max);

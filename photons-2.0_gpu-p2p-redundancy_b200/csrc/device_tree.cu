@@ -339,34 +339,15 @@ int p2p_tree_download(p2p_ctx* c, int64_t* perm, double* pos_sorted, int* leaf_n
     return 0;
 }
 
-// walk_task_p2p over the device tree, plus (period > 0) the walks against the 26 periodic images of the same tree
-// pruned against the target box {tcenter, twidth} exactly as prepare_sendtree2 / walk_task_p2p_ext do.  Image sources
-// are listed under their LOCAL leaf id: the fixed-point coordinates wrap to the nearest image.  Tasks are appended to
-// the context's list (p2p_build_csr packs them).
-int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]) {
-    USE(c);
-    p2p_dtree* t = c->dtree;
-    if (!t || !t->valid) return fail(P2P_ERR_STATE, "p2p_tree_walk needs p2p_tree_build or p2p_tree_upload");
-    if (t->nleaf != c->nleaf) return fail(P2P_ERR_STATE, "device tree and uploaded leaves differ");
-    if (!(theta > 0.0) || !(rcut > 0.0)) return fail(P2P_ERR_ARG, "bad theta / rcut");
-    if (period > 0.0 && (!tcenter || !twidth)) return fail(P2P_ERR_ARG, "periodic walk needs the target box");
-    if ((long long)t->nleaf + t->nnode >= (1LL << 29)) return fail(P2P_ERR_ARG, "tree too large for the walk item encoding");
+}  // extern "C"
+
+namespace {
+// breadth-first walk from the given items; appends the tasks to the context's list
+int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std::vector<ull>& init, size_t task_guess) {
     cudaStream_t st = c->stream;
-    const int nleaf = t->nleaf;
-    if (nleaf == 0) return 0;
-    if (period > 0.0 && t->npart <= t->maxleaf)
-        return fail(P2P_ERR_ARG, "image walk of a tree whose root holds <= maxleaf particles is undefined in the reference");
-    p2p::dt::WalkParams P;
-    P.box = t->box.p; P.son = t->son.p; P.nleaf = nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
-    for (int k = 0; k < 3; k++) { P.tc[k] = tcenter ? tcenter[k] : 0.0; P.tw[k] = twidth ? twidth[k] : 0.0; }
-    // initial frontier
-    std::vector<ull> init;
-    const int root = nleaf;
-    init.push_back(p2p::dt::item(root, root, 0));
-    if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, s));
-    size_t fcap = std::max<size_t>((size_t)nleaf * 96, 1 << 16);
-    size_t tcap = std::max<size_t>((size_t)nleaf * (period > 0.0 ? 192 : 160), 1 << 16);
-    CU(t->frontier[0].reserve(fcap, st)); CU(t->frontier[1].reserve(fcap, st));
+    size_t fcap = std::max<size_t>(task_guess / 2, 1 << 16);
+    size_t tcap = std::max<size_t>(task_guess, 1 << 16);
+    CU(t->frontier[0].reserve(std::max(fcap, init.size()), st)); CU(t->frontier[1].reserve(fcap, st));
     CU(c->tt.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
     CU(c->ts.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
     CU(cudaEventRecord(t->e0, st));
@@ -407,6 +388,139 @@ int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const do
     c->ntask += (long long)ntask;
     c->csr_valid = false;
     t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
+    return 0;
+}
+
+int walk_checks(p2p_ctx* c, double theta, double rcut, double period, const double* tcenter, const double* twidth) {
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid) return fail(P2P_ERR_STATE, "the device walk needs p2p_tree_build or p2p_tree_upload");
+    if (t->nleaf != c->nleaf) return fail(P2P_ERR_STATE, "device tree and uploaded leaves differ");
+    if (!(theta > 0.0) || !(rcut > 0.0)) return fail(P2P_ERR_ARG, "bad theta / rcut");
+    if (period > 0.0 && (!tcenter || !twidth)) return fail(P2P_ERR_ARG, "periodic walk needs the target box");
+    if ((long long)t->nleaf + t->nnode >= (1LL << 27)) return fail(P2P_ERR_ARG, "tree too large for the walk item encoding");
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// walk_task_p2p over the device tree, plus (period > 0) the walks against the 26 periodic images of the same tree
+// pruned against the target box {tcenter, twidth} exactly as prepare_sendtree2 / walk_task_p2p_ext do.  Image sources
+// are listed under their LOCAL leaf id: the fixed-point coordinates wrap to the nearest image.  Tasks are appended to
+// the context's list (p2p_build_csr packs them).
+int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]) {
+    USE(c);
+    int r = walk_checks(c, theta, rcut, period, tcenter, twidth);
+    if (r) return r;
+    p2p_dtree* t = c->dtree;
+    const int nleaf = t->nleaf;
+    if (nleaf == 0) return 0;
+    if (period > 0.0 && t->npart <= t->maxleaf)
+        return fail(P2P_ERR_ARG, "image walk of a tree whose root holds <= maxleaf particles is undefined in the reference");
+    p2p::dt::WalkParams P;
+    memset(&P, 0, sizeof P);
+    P.box = t->box.p; P.son = t->son.p; P.nleaf = nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
+    for (int k = 0; k < 3; k++) { P.tc[k] = tcenter ? tcenter[k] : 0.0; P.tw[k] = twidth ? twidth[k] : 0.0; }
+    P.sbox = t->box.p; P.sson = t->son.p; P.me = 0; P.npeer = 1; P.snleaf[0] = nleaf;
+    std::vector<ull> init;
+    const int root = nleaf;
+    init.push_back(p2p::dt::item(root, root, 0, 0));
+    if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, 0, s));
+    return walk_impl(c, t, P, init, (size_t)nleaf * (period > 0.0 ? 192 : 160));
+}
+
+// ---- multi-rank: one tree per rank, every rank walks its tree against all of them --------------------------------
+// copies of the device tree's walk arrays into caller-owned DEVICE memory (e.g. torch tensors that an all-gather
+// will send): box [(nleaf + nnode)][6] doubles, son [nnode][2] ints (unified ids), leaf [nleaf] {first particle, count}
+int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid) return fail(P2P_ERR_STATE, "no device tree");
+    const size_t nu = (size_t)t->nleaf + t->nnode;
+    if (d_box) CU(cudaMemcpyAsync(d_box, t->box.p, nu * 48, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_son) CU(cudaMemcpyAsync(d_son, t->son.p, (size_t)t->nnode * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_leaf && t->nleaf) CU(cudaMemcpyAsync(d_leaf, c->leaf.p, (size_t)t->nleaf * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+// The local tree against the trees of ALL ranks (device arrays concatenated in rank order; peer `me` must be this
+// rank's own export) for the zero displacement and, with period > 0, the 26 periodic displacements: what
+// fmm_task + fmm_ext do through 27 P ring exchanges (1_Indexing/src/fmm.c:1026-1145, remotes.c:740-809), without
+// moving a single halo particle first.  Sources of rank `me` are listed under local leaf ids, those of rank p under
+// nleaf_local + (leaves of the ranks before p, skipping me) + leaf: the ghost leaf table p2p_set_ghosts_device expects.
+int p2p_tree_walk_peers(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all, const void* d_son_all) {
+    USE(c);
+    int r = walk_checks(c, theta, rcut, period, tcenter, twidth);
+    if (r) return r;
+    p2p_dtree* t = c->dtree;
+    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || me < 0 || me >= npeer || !peer_nleaf || !peer_nnode || !d_box_all || !d_son_all ||
+        !tcenter || !twidth)
+        return fail(P2P_ERR_ARG, "bad peer arrays (at most %d ranks)", p2p::dt::kMaxPeers);
+    if (peer_nleaf[me] != t->nleaf || peer_nnode[me] != t->nnode) return fail(P2P_ERR_ARG, "peer %d is not this rank's tree", me);
+    p2p::dt::WalkParams P;
+    memset(&P, 0, sizeof P);
+    P.box = t->box.p; P.son = t->son.p; P.nleaf = t->nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
+    for (int k = 0; k < 3; k++) { P.tc[k] = tcenter[k]; P.tw[k] = twidth[k]; }
+    P.sbox = reinterpret_cast<const double*>(d_box_all); P.sson = reinterpret_cast<const int*>(d_son_all); P.me = me; P.npeer = npeer;
+    long long ub = 0, nb = 0;
+    int ghost = t->nleaf;
+    std::vector<ull> init;
+    for (int p = 0; p < npeer; p++) {
+        if (peer_nleaf[p] < 0 || peer_nnode[p] < 1) return fail(P2P_ERR_ARG, "peer %d has no tree", p);
+        if ((long long)peer_nleaf[p] + peer_nnode[p] >= (1LL << 27)) return fail(P2P_ERR_ARG, "peer tree too large for the walk item encoding");
+        P.sbox_base[p] = ub; P.sson_base[p] = nb; P.snleaf[p] = peer_nleaf[p];
+        P.ts_base[p] = p == me ? 0 : ghost;
+        if (p != me) ghost += peer_nleaf[p];
+        ub += (long long)peer_nleaf[p] + peer_nnode[p];
+        nb += peer_nnode[p];
+        for (int s = 0; s < (period > 0.0 ? 27 : 1); s++) init.push_back(p2p::dt::item(t->nleaf, peer_nleaf[p], p, s));
+    }
+    c->nghostleaf = ghost - t->nleaf;          // the ghost leaf table must follow (p2p_set_ghosts_device) before p2p_build_csr
+    c->nghost = 0;
+    return walk_impl(c, t, P, init, (size_t)t->nleaf * 224);
+}
+
+// marks[g] = 1 for every ghost leaf g (0-based behind the local leaves) that the task list references
+int p2p_ghost_marks(p2p_ctx* c, void* d_marks) {
+    USE(c);
+    if (!d_marks && c->nghostleaf) return fail(P2P_ERR_ARG, "null marks");
+    if (c->nghostleaf) CU(cudaMemsetAsync(d_marks, 0, (size_t)c->nghostleaf, c->stream));
+    if (c->ntask && c->nghostleaf) {
+        p2p::dt::ghost_mark_kernel<<<blocks(c->ntask, 256), 256, 0, c->stream>>>(c->ts.p, c->ntask, c->nleaf,
+                                                                               reinterpret_cast<unsigned char*>(d_marks));
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+// out[offset[l] ...) = the fixed-point particles of every LOCAL leaf l with marks[l] != 0 (what a peer asked for)
+int p2p_gather_leaves(p2p_ctx* c, const void* d_marks, const void* d_offset, void* d_out) {
+    USE(c);
+    if (c->nleaf == 0) return 0;
+    if (!d_marks || !d_offset || !d_out) return fail(P2P_ERR_ARG, "null device pointer");
+    p2p::dt::gather_leaves_kernel<<<blocks((long long)c->nleaf * 32, 256), 256, 0, c->stream>>>(
+        c->leaf.p, c->nleaf, reinterpret_cast<const unsigned char*>(d_marks), reinterpret_cast<const long long*>(d_offset), c->part.p,
+        reinterpret_cast<int4*>(d_out));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ghost particles (fixed point, as p2p_gather_leaves of the owner produced them) and the table of ALL ghost leaves
+// ({first ghost particle, count}, count 0 for leaves nobody references), everything already on the device
+int p2p_set_ghosts_device(p2p_ctx* c, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf) {
+    USE(c);
+    if (nbody < 0 || nghostleaf < 0 || (nbody && !d_part) || (nghostleaf && (!d_start || !d_count))) return fail(P2P_ERR_ARG, "bad ghost arrays");
+    const long long base = c->npart;
+    CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
+    CU(c->leaf.reserve((size_t)c->nleaf + nghostleaf + 1, c->stream, (size_t)c->nleaf));
+    if (nbody) CU(cudaMemcpyAsync(c->part.p + base, d_part, (size_t)nbody * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
+    if (nghostleaf) {
+        p2p::dt::ghost_leaf_table_kernel<<<blocks(nghostleaf, 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const int*>(d_start), reinterpret_cast<const int*>(d_count), nghostleaf, (int)base, c->leaf.p + c->nleaf);
+        CU(cudaGetLastError());
+    }
+    c->nghost = nbody; c->nghostleaf = nghostleaf; c->csr_valid = false;
     return 0;
 }
 

@@ -640,13 +640,23 @@ __global__ void acc_unpermute_kernel(const float4* __restrict__ acc, const int* 
 }
 
 // ------------------------------------------------------------------------------------------------ walk
+constexpr int kMaxPeers = 16;
+
 struct WalkParams {
-    const double* box;   // unified [id][6]
+    const double* box;   // target (local) tree: unified [id][6] centre, width; leaves [0, nleaf), nodes nleaf + n
     const int* son;      // [node][2] unified ids
     int nleaf;
     double theta, rcut;
     double period;       // displacement unit of the images (BOXSIZE)
-    double tc[3], tw[3]; // the target domain box the images are pruned against (1_Indexing/src/remotes.c:374-386)
+    double tc[3], tw[3]; // the local domain box the images / halos are pruned against (1_Indexing/src/remotes.c:374-386)
+    // source trees: the local tree again (peer == me) and, in a multi-rank run, every other rank's tree
+    const double* sbox;  // concatenated unified box arrays of all peers
+    const int* sson;     // concatenated son arrays (peer-local unified ids)
+    int me, npeer;
+    long long sbox_base[kMaxPeers];   // first unified id of peer p in sbox
+    long long sson_base[kMaxPeers];   // first node of peer p in sson
+    int snleaf[kMaxPeers];
+    int ts_base[kMaxPeers];           // task source id = ts_base[p] + leaf: 0 for me (local ids), ghost leaf ids otherwise
 };
 
 __constant__ int c_shift[27][3];
@@ -692,12 +702,17 @@ __device__ __forceinline__ bool image_pruned(const WalkParams& P, const double n
     return dr >= P.rcut || wmax < 0.95 * P.theta * dr;
 }
 
-__host__ __device__ __forceinline__ ull item(int im, int jm, int sh) { return ((ull)(unsigned)im << 34) | ((ull)(unsigned)jm << 5) | (ull)sh; }
+// item = target id (27 bits) | source id (27) | peer (4) | image (5)
+__host__ __device__ __forceinline__ ull item(int im, int jm, int peer, int sh) {
+    return ((ull)(unsigned)im << 36) | ((ull)(unsigned)jm << 9) | ((ull)(unsigned)peer << 5) | (ull)sh;
+}
 
-// One level of the breadth-first dual-tree walk.  Items are (target id, source id, image); an item either emits a
-// leaf-leaf task, opens one side (2 items), opens both (self pair, 4 items) or dies.  Output slots are claimed per
-// warp.  counters[0] = items written to `out`, counters[1] = tasks emitted so far; writes beyond the capacities are
-// dropped (the host sees the counts, grows the buffers and repeats the level).
+// One level of the breadth-first dual-tree walk.  Items are (target id, source id, source rank, image); an item
+// either emits a leaf-leaf task, opens one side (2 items), opens both (self pair, 4 items) or dies.  The local
+// tree against itself without displacement follows walk_task_p2p; every other (rank, image) combination follows
+// walk_task_p2p_ext on the image prepare_sendtree2 would have sent, whose cut nodes are recognised on the fly.
+// Output slots are claimed per warp.  counters[0] = items written to `out`, counters[1] = tasks emitted so far;
+// writes beyond the capacities are dropped (the host sees the counts, grows the buffers and repeats the level).
 __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
                                                          ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
                                                          ull cap_task, WalkParams P) {
@@ -709,14 +724,19 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
         int nchild = 0;
         bool emit = false;
         int ci[4], cj[4];
-        int im = 0, jm = 0, sh = 0;
+        int im = 0, jm = 0, sh = 0, peer = 0, tsid = 0;
         if (idx < n_in) {
             const ull it = in[idx];
-            im = (int)(it >> 34);
-            jm = (int)((it >> 5) & 0x1fffffffu);
+            im = (int)(it >> 36);
+            jm = (int)((it >> 9) & 0x7ffffffu);
+            peer = (int)((it >> 5) & 15);
             sh = (int)(it & 31);
-            const bool ileaf = im < P.nleaf, jleaf = jm < P.nleaf;
-            if (sh == 0 && im == jm) {
+            const int snl = P.snleaf[peer];
+            const bool ileaf = im < P.nleaf, jleaf = jm < snl;
+            const bool local = sh == 0 && peer == P.me;
+            const int* __restrict__ sson = P.sson + 2 * P.sson_base[peer];
+            tsid = P.ts_base[peer] + jm;
+            if (local && im == jm) {
                 if (ileaf) emit = true;
                 else {
                     const int a0 = P.son[2 * (im - P.nleaf)], a1 = P.son[2 * (im - P.nleaf) + 1];
@@ -727,7 +747,7 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 emit = true;
             } else {
                 const double* bi = P.box + 6 * (size_t)im;
-                const double* bj = P.box + 6 * (size_t)jm;
+                const double* bj = P.sbox + 6 * (size_t)(P.sbox_base[peer] + jm);
                 double wi[3], wj[3], cjd[3], dist[3], disp[3];
                 for (int k = 0; k < 3; k++) {
                     disp[k] = (double)c_shift[sh][k] * P.period;
@@ -738,7 +758,7 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 }
                 const int flag = acceptance(wi, wj, dist, P.theta, P.rcut);
                 int open = 0;     // 1: target side, 2: source side
-                if (sh == 0) {
+                if (local) {
                     if (flag == 0) {
                         if (ileaf) open = 2;
                         else if (jleaf) open = 1;
@@ -759,7 +779,7 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                     cj[0] = cj[1] = jm;
                     nchild = 2;
                 } else if (open == 2) {
-                    cj[0] = P.son[2 * (jm - P.nleaf)]; cj[1] = P.son[2 * (jm - P.nleaf) + 1];
+                    cj[0] = sson[2 * (jm - snl)]; cj[1] = sson[2 * (jm - snl) + 1];
                     ci[0] = ci[1] = im;
                     nchild = 2;
                 }
@@ -777,16 +797,38 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
             if (lane == 0) base = atomicAdd(&counters[0], (ull)total);
             base = __shfl_sync(full, base, 0) + (ull)(incl - nchild);
             if (base + nchild <= cap_out)
-                for (int k = 0; k < nchild; k++) out[base + k] = item(ci[k], cj[k], sh);
+                for (int k = 0; k < nchild; k++) out[base + k] = item(ci[k], cj[k], peer, sh);
         }
         const unsigned em = __ballot_sync(full, emit);
         if (em) {
             ull tb = 0;
             if (lane == 0) tb = atomicAdd(&counters[1], (ull)__popc(em));
             tb = __shfl_sync(full, tb, 0) + (ull)__popc(em & ((1u << lane) - 1));
-            if (emit && tb < cap_task) { tt[tb] = im; ts[tb] = jm; }
+            if (emit && tb < cap_task) { tt[tb] = im; ts[tb] = tsid; }
         }
     }
+}
+
+// ---- multi-rank helpers: which ghost leaves does the list reference, and the particles of requested leaves
+__global__ void ghost_mark_kernel(const int* __restrict__ ts, long long ntask, int nleaf_local, unsigned char* __restrict__ marks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntask) return;
+    const int s = ts[i];
+    if (s >= nleaf_local) marks[s - nleaf_local] = 1;
+}
+
+// one warp per requested leaf: copy its particles to out[offset[leaf] ...)
+__global__ void gather_leaves_kernel(const int2* __restrict__ leaf, int nleaf, const unsigned char* __restrict__ marks,
+                                     const long long* __restrict__ offset, const int4* __restrict__ part, int4* __restrict__ out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nleaf || !marks[w]) return;
+    const int2 L = leaf[w];
+    for (int k = lane; k < L.y; k += 32) out[offset[w] + k] = part[L.x + k];
+}
+
+__global__ void ghost_leaf_table_kernel(const int* __restrict__ start, const int* __restrict__ count, int n, int start_off, int2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_int2(start[i] + start_off, count[i]);
 }
 
 // after sorting: a source listed twice in a row (the same leaf reached through two different images) cannot be

@@ -76,6 +76,12 @@ def load_library():
     L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
     L.p2p_download_acc_original.argtypes = [C.c_void_p, _dp]
     L.p2p_tree_set_option.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.p2p_tree_walk_peers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
+                                      C.c_void_p, C.c_void_p]
+    L.p2p_ghost_marks.argtypes = [C.c_void_p, C.c_void_p]
+    L.p2p_gather_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.p2p_set_ghosts_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
     L.p2p_device_acc.argtypes = [C.c_void_p]
     _lib = L
     return L
@@ -101,6 +107,7 @@ class P2PContext:
         h = C.c_void_p()
         self._chk(self._L.p2p_create(C.byref(h), int(device)))
         self._h = h
+        self.device = int(device)
         self.npart = 0
         self.nleaf = 0
         self.stream_ptr = 0                          # externally owned stream, 0 = the context's own
@@ -332,6 +339,26 @@ class P2PContext:
         self.npart = pos.shape[0]
         self.nleaf = self.tree_info()["nleaf"]
         return acc
+
+    # ---- multi-rank device path (device pointers, e.g. tensor.data_ptr())
+    def tree_export(self, d_box, d_son, d_leaf):
+        self._chk(self._L.p2p_tree_export(self._h, d_box, d_son, d_leaf))
+
+    def tree_walk_peers(self, theta, rcut, period, tcenter, twidth, me, peer_nleaf, peer_nnode, d_box_all, d_son_all):
+        tc, tw = np.ascontiguousarray(tcenter, np.float64), np.ascontiguousarray(twidth, np.float64)
+        nl, nn = _i32(peer_nleaf), _i32(peer_nnode)
+        self._chk(self._L.p2p_tree_walk_peers(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp),
+                                              tw.ctypes.data_as(_dp), len(nl), int(me), nl.ctypes.data_as(_ip),
+                                              nn.ctypes.data_as(_ip), d_box_all, d_son_all))
+
+    def ghost_marks(self, d_marks):
+        self._chk(self._L.p2p_ghost_marks(self._h, d_marks))
+
+    def gather_leaves(self, d_marks, d_offset, d_out):
+        self._chk(self._L.p2p_gather_leaves(self._h, d_marks, d_offset, d_out))
+
+    def set_ghosts_device(self, d_part, nbody, d_start, d_count, nghostleaf):
+        self._chk(self._L.p2p_set_ghosts_device(self._h, d_part, int(nbody), d_start, d_count, int(nghostleaf)))
 
     def tree_set_option(self, seq_sum_plain_max=-1):
         self._chk(self._L.p2p_tree_set_option(self._h, int(seq_sum_plain_max)))

@@ -1,0 +1,82 @@
+"""Multi-rank device path (p2p_b200/dist_device.py): every rank builds its tree and walks it against the trees of
+all ranks on the GPU; per-rank task and pair counts must equal the oracle's restatement of the reference flow
+(itself pinned against the reference run with P ranks) and the forces must agree with the fp64 oracle.
+The ranks share GPU 0 and exchange through gloo here; on a multi-GPU box the same code runs over NCCL (bench.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+from conftest import DEMO_BOX, DEMO_MASS, DEMO_NSIDE, ROOT, THETA
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, pos, q):
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import p2p_b200
+    from p2p_b200 import dist as pdist
+    from p2p_b200 import dist_device
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    lp, lidx, tcenter, twidth, direct, dom = pdist.decompose(pos, DEMO_BOX, None)
+    c, w = tcenter[dom], twidth[dom]
+    ctx = p2p_b200.P2PContext(0)
+    tm = {}
+    acc, ntask, npairs = dist_device.run_device_step(ctx, lp, pos.shape[0], DEMO_BOX, 16, DEMO_NSIDE, DEMO_MASS, c - 0.5 * w,
+                                                     c + 0.5 * w, int(direct[dom]), THETA, periodic=True, truncated=True, timings=tm)
+    dup = ctx.csr_duplicates()
+    q.put((rank, lidx, acc, ntask, npairs, dup))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_device_multirank_matches_oracle(demo_pos, world):
+    import flow
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, demo_pos, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        item = q.get(timeout=600)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = flow.short_range_lists(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, world, True, literal_d6=False)
+    acc = np.zeros((len(demo_pos), 3))
+    for r in range(world):
+        lidx, a, ntask, npairs, dup = got[r]
+        T = ref[r]["tree"]
+        want_tasks = len(ref[r]["local"][0]) + sum(len(x["tt"]) for x in ref[r]["remote"])
+        want_pairs = int((T.leaf_npart[ref[r]["local"][0]].astype(np.int64) * T.leaf_npart[ref[r]["local"][1]]).sum())
+        for x in ref[r]["remote"]:
+            want_pairs += int((T.leaf_npart[x["tt"]].astype(np.int64) * x["image"]["npart"][x["ts"]]).sum())
+        assert (ntask, npairs) == (want_tasks, want_pairs)
+        assert dup == 0
+        acc[lidx] = a
+    want, _, _ = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, world, True)
+    absr, _, _ = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, world, True, absterms=True)
+    d = np.linalg.norm(acc - want, axis=1)
+    na = np.linalg.norm(want, axis=1)
+    e1 = (d / np.maximum(na, na.mean())).max()
+    e2 = (d / np.maximum(np.linalg.norm(absr, axis=1), 1e-300)).max()
+    assert e1 < 1e-5 and e2 < 1e-5, (e1, e2)
