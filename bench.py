@@ -337,6 +337,31 @@ def main():
                      "note": "device_resident: list producers as CUDA kernels (p2p_step_device); host_*: list producers on the host "
                              "cores (libp2p_host.so), pipelined = host walks chunk c+1 while the device computes chunk c"}
         ctx2.close()
+    elif not args.no_full_step:
+        # multi-rank: every rank builds its tree and walks it against the trees of all ranks on its GPU; halo particles
+        # travel leaf-granular over NCCL (p2p_b200/dist_device.py)
+        from p2p_b200 import dist_device
+        lp, _, tcenter, twidth, direct, dom = pdist.decompose(pos, box)
+        c_, w_ = tcenter[dom], twidth[dom]
+        lp_t, lp_pin = pin(lp)
+        ctx2 = step.ShortRangeStep(local_rank).ctx
+        ctx2.set_stream(stream.cuda_stream)
+        acc2 = torch.empty((lp.shape[0], 3), dtype=torch.float64).pin_memory().numpy()
+        dev = None
+        for _ in range(4):
+            tm = {}
+            barrier()
+            t0 = time.perf_counter()
+            _, n_t, n_p = dist_device.run_device_step(ctx2, lp_pin, pos.shape[0], box, args.maxleaf, args.nside, mass, c_ - 0.5 * w_,
+                                                      c_ + 0.5 * w_, int(direct[dom]), THETA, periodic=True, truncated=True,
+                                                      acc_out=acc2, timings=tm)
+            barrier()
+            dev = (time.perf_counter() - t0, tm)
+            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
+        full_step = {"what": "per-rank positions in, accelerations out: tree build + topology all-gather + walk against every rank's tree "
+                             "(27 displacements) + leaf-granular halo fetch (NCCL all-to-all-v) + CSR + P2P; wall time between barriers",
+                     "device_resident_s": dev[0], "rank0_breakdown": dev[1]}
+        ctx2.close()
     del pos
 
     # ---------------------------------------------------------------- reduce over ranks
