@@ -28,6 +28,10 @@ struct p2p_dtree {
     DevBuf<unsigned int> G, tile;
     DevBuf<int> t_start, t_len, t_parent, t_np0, t_child, t_nleaf, t_nnode, t_id, t_leafbase, child_cnt;
     DevBuf<double> t_split, t_lo, t_hi;
+    DevBuf<int> choff, cmeta;
+    DevBuf<double> capprox, capprox_end;
+    DevBuf<long long> cinc;
+    int spec_min = 32768;        // nodes longer than this use the speculative chunked evaluation of the split mean
     int* d_scalar = nullptr;     // [0] next-level node count, [1] max leaf occupancy
     int* h_scalar = nullptr;     // pinned
     // walk
@@ -54,6 +58,7 @@ void p2p_dtree_release(p2p_dtree* t) {
     t->t_start.release(); t->t_len.release(); t->t_parent.release(); t->t_np0.release(); t->t_child.release(); t->t_nleaf.release();
     t->t_nnode.release(); t->t_id.release(); t->t_leafbase.release(); t->child_cnt.release(); t->t_split.release(); t->t_lo.release();
     t->t_hi.release();
+    t->choff.release(); t->cmeta.release(); t->capprox.release(); t->capprox_end.release(); t->cinc.release();
     t->frontier[0].release(); t->frontier[1].release();
     if (t->d_scalar) cudaFree(t->d_scalar);
     if (t->h_scalar) cudaFreeHost(t->h_scalar);
@@ -101,8 +106,10 @@ int p2p_tree_set_option(p2p_ctx* c, int seq_sum_plain_max) {
     p2p_dtree* t;
     int r = get_tree(c, &t);
     if (r) return r;
-    // -2: default thresholds but every node through the warp kernel (no block-per-node variant)
+    // -2: default thresholds but every node through the warp kernel (no block-per-node variant);
+    // -3: block-per-node but no speculative chunked evaluation; -4: speculative evaluation for every node above one chunk
     t->block_mode = seq_sum_plain_max != -2;
+    t->spec_min = seq_sum_plain_max == -3 ? 0 : (seq_sum_plain_max == -4 ? 2048 : 32768);
     t->plain_max = seq_sum_plain_max < 0 ? p2p::dt::kSeqPlainMax : seq_sum_plain_max;
     return 0;
 }
@@ -198,10 +205,23 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     for (int lvl = 0;; lvl++) {
         if (lvl > 256) return fail(P2P_ERR_ARG, "kd-tree deeper than 256 levels (more than maxleaf coincident particles?)");
         const int b = lvl_begin[lvl], n = lvl_count[lvl], dir = (direct_start + lvl) % 3;
-        // few, long nodes: a block each; many nodes: a warp each
-        const int block_min = (t->block_mode && n <= c->num_sm * 4) ? 2048 : 0x7fffffff;
+        // few, long nodes: chunks on all SMs (speculative binade) or a block each; many nodes: a warp each
+        const bool few = t->block_mode && n <= c->num_sm * 4;
+        const int block_min = few ? 2048 : 0x7fffffff;
+        const int spec_min = (few && t->spec_min > 0) ? std::max(t->spec_min, block_min) : 0x7fffffff;
+        if (longest > spec_min) {
+            const int maxchunks = (int)(npart / p2p::dt::kChunk) + n + 1;
+            CU(t->choff.reserve((size_t)n + 2, st)); CU(t->cmeta.reserve((size_t)maxchunks, st)); CU(t->capprox.reserve((size_t)maxchunks, st));
+            CU(t->capprox_end.reserve((size_t)maxchunks, st)); CU(t->cinc.reserve(2 * (size_t)maxchunks, st));
+            p2p::dt::SpecArrays Sp{t->choff.p, t->capprox.p, t->capprox_end.p, t->cinc.p, t->cmeta.p};
+            p2p::dt::chunk_offsets_kernel<<<1, 1024, 0, st>>>(A, Sp, b, n, spec_min);
+            p2p::dt::chunk_sum_kernel<<<std::min(maxchunks, c->num_sm * 8), 256, 0, st>>>(A, Sp, b, n, dir);
+            p2p::dt::chunk_prefix_kernel<<<blocks((long long)n * 32, 128), 128, 0, st>>>(Sp, n);
+            p2p::dt::chunk_transducer_kernel<<<std::min(maxchunks, c->num_sm * 4), p2p::dt::kBlockWarps * 32, 0, st>>>(A, Sp, b, n, dir);
+            p2p::dt::chunk_combine_kernel<<<std::min(n, c->num_sm), p2p::dt::kBlockWarps * 32, 0, st>>>(A, Sp, b, n, dir);
+        }
         if (longest > block_min)
-            p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min);
+            p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min, spec_min);
         const int warps = std::min(n, c->num_sm * 64);
         p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max, block_min);
         p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);

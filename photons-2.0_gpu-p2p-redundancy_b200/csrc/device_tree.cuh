@@ -258,120 +258,299 @@ __global__ void mean_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir
     }
 }
 
-// The same transducer evaluation with a whole block per node (the top levels of the tree have fewer nodes than
-// the device has SMs): every thread folds 8 values, warps scan, warp 0 scans the warp summaries, and the first
-// thread whose values leave the binade ends the tile exactly as in seq_sum_warp.
-__global__ void __launch_bounds__(kBlockWarps * 32) mean_block_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int min_len) {
+// Shared memory of the block-cooperative transducer evaluation.
+struct BlockSum {
+    long long a0[kBlockWarps], a1[kBlockWarps], pre[kBlockWarps];
+    int q0[kBlockWarps], q1[kBlockWarps], par[kBlockWarps], bad[kBlockWarps];
+    long long tot;
+    double v[8];
+};
+
+// fold 8 values for both input parities (binade exponent e of the running sum); hard: a value outside [0, 2^(e+1))
+__device__ __forceinline__ void fold8(const double v[8], bool okS, int e, long long& d0, long long& d1, int& p0, int& p1, bool& hard) {
+    d0 = 0; d1 = 0; p0 = 0; p1 = 1;
+    hard = !okS;
+    const double scale = okS ? __longlong_as_double((long long)(1023 + 52 - e) << 52) : 1.0;
+    const double top = okS ? __longlong_as_double((long long)(1023 + e + 1) << 52) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const double xv = v[k];
+        if (!(xv >= 0.0 && xv < top)) hard = true;
+        const double y = xv * scale;
+        const double qf = floor(y);
+        const double r = y - qf;
+        const long long q = (long long)qf;
+        const int gt = r > 0.5, tie = r == 0.5;
+        int t0 = p0 ^ (int)(q & 1), t1 = p1 ^ (int)(q & 1);
+        const int c0 = gt | (tie & t0), c1 = gt | (tie & t1);
+        d0 += q + c0;
+        d1 += q + c1;
+        p0 = t0 ^ c0;
+        p1 = t1 ^ c1;
+    }
+}
+
+// inclusive warp scan of transducers (earlier lanes first)
+__device__ __forceinline__ void scan_transducers(long long& a0, long long& a1, int& q0, int& q1) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long b0 = __shfl_up_sync(full, a0, o), b1 = __shfl_up_sync(full, a1, o);
+        const int r0 = __shfl_up_sync(full, q0, o), r1 = __shfl_up_sync(full, q1, o);
+        if (lane >= o) {
+            const long long n0 = b0 + (r0 ? a1 : a0), n1 = b1 + (r1 ? a1 : a0);
+            const int m0 = r0 ? q1 : q0, m1 = r1 ? q1 : q0;
+            a0 = n0; a1 = n1; q0 = m0; q1 = m1;
+        }
+    }
+}
+
+// The transducer evaluation with a whole block (32 warps, tile = 8192 values): continues the sequential sum S over
+// X[start + lo .. start + hi); every thread folds 8 values, warps scan, warp 0 scans the warp summaries, and the
+// first thread whose values leave the binade ends the tile exactly as in seq_sum_warp.  Uniform result.
+__device__ double block_seq_sum(const double* __restrict__ X, long long start, int lo, int hi, double S, BlockSum& sm) {
     constexpr int NW = kBlockWarps;
-    __shared__ long long s_a0[NW], s_a1[NW], s_pre[NW];
-    __shared__ int s_q0[NW], s_q1[NW], s_par[NW], s_bad[NW];
-    __shared__ long long s_tot;
-    __shared__ double s_v[8];
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int pos = lo;
+    while (pos < hi) {
+        const int e = (int)((__double_as_longlong(S) >> 52) & 0x7ff) - 1023;
+        const bool okS = S > 0.0 && e >= -900 && e <= 900;
+        const int my = pos + tid * 8;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (my + k < hi) ? X[start + my + k] : 0.0;
+        long long a0, a1;
+        int q0, q1;
+        bool hard;
+        fold8(v, okS, e, a0, a1, q0, q1, hard);
+        scan_transducers(a0, a1, q0, q1);
+        if (lane == 31) { sm.a0[w] = a0; sm.a1[w] = a1; sm.q0[w] = q0; sm.q1[w] = q1; }
+        const long long kS = okS ? ((__double_as_longlong(S) & 0xfffffffffffffLL) | (1LL << 52)) : 0;
+        const int parS = (int)(kS & 1);
+        __syncthreads();
+        if (w == 0) {
+            long long A0 = sm.a0[lane], A1 = sm.a1[lane];
+            int Q0 = sm.q0[lane], Q1 = sm.q1[lane];
+            scan_transducers(A0, A1, Q0, Q1);
+            const long long inc = parS ? A1 : A0;
+            const int par = parS ? Q1 : Q0;
+            long long ex = __shfl_up_sync(full, inc, 1);
+            int exp_ = __shfl_up_sync(full, par, 1);
+            if (lane == 0) { ex = 0; exp_ = parS; }
+            sm.pre[lane] = ex;
+            sm.par[lane] = exp_;
+        }
+        __syncthreads();
+        const long long incl = sm.pre[w] + (sm.par[w] ? a1 : a0);
+        const bool cross = hard || (kS + incl >= (1LL << 53));
+        const unsigned bad = __ballot_sync(full, cross);
+        if (lane == 0) sm.bad[w] = bad ? (w * 32 + __ffs(bad) - 1) : 0x7fffffff;
+        __syncthreads();
+        int f = sm.bad[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) f = min(f, __shfl_xor_sync(full, f, o));
+        const double u = __longlong_as_double((long long)(1023 + (okS ? e : 0) - 52) << 52);
+        if (f == 0x7fffffff) {
+            if (tid == NW * 32 - 1) sm.tot = incl;
+            __syncthreads();
+            S = u * (double)(kS + sm.tot);
+            pos += NW * 256;
+        } else {
+            if (tid == f - 1) sm.tot = incl;
+            if (tid == f) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) sm.v[k] = v[k];
+            }
+            __syncthreads();
+            if (f > 0) S = u * (double)(kS + sm.tot);
+#pragma unroll
+            for (int k = 0; k < 8; k++) S += sm.v[k];
+            pos += 8 * (f + 1);
+        }
+        __syncthreads();
+    }
+    return S;
+}
+
+// one block per node (nodes with min_len < len <= max_len)
+__global__ void __launch_bounds__(kBlockWarps * 32) mean_block_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int min_len,
+                                                                      int max_len) {
+    __shared__ BlockSum sm;
     const double* __restrict__ X = A.x[dir];
     for (int n = blockIdx.x; n < lvl_count; n += gridDim.x) {
         const int t = lvl_begin + n;
         const int len = A.t_len[t];
-        if (len <= min_len) continue;
+        if (len <= min_len || len > max_len) continue;
+        const double S = block_seq_sum(X, A.t_start[t], 0, len, 0.0, sm);
+        if (threadIdx.x == 0) A.t_split[t] = S / (double)len;
+    }
+}
+
+// ---- speculative evaluation for the longest nodes: all SMs work on ONE sequential sum ---------------------------
+// The node is cut into chunks of 8192 values.  A plain (tree-order) sum per chunk and a prefix over the chunks give
+// the running sum at every chunk start to ~1e-13 -- enough to know its BINADE unless it is within 1e-6 of a power
+// of two.  Every such "safe" chunk then computes its transducer {parity in -> (increment, parity out)} for that
+// binade independently, on any SM; one block per node finally chains the chunk transducers in order, checking for
+// every chunk that the exact running sum really is in the predicted binade and stays in it, and evaluates the few
+// chunks where that fails (binade crossings) cooperatively from the exact running sum.  Bits identical to the loop.
+constexpr int kChunk = kBlockWarps * 256;
+
+struct SpecArrays {
+    int* choff;          // [nodes of the level + 1] first chunk of each node (0 chunks for nodes not treated here)
+    double* approx;      // [chunk] plain sum, then (prefix kernel) approximate running sum at the chunk start
+    double* approx_end;
+    long long* inc;      // [chunk][2]
+    int* meta;           // [chunk] bit 0 safe, bits 1-2 parity out for parity in 0 / 1, bits 8.. binade exponent + 2048
+};
+
+__global__ void chunk_offsets_kernel(BuildArrays A, SpecArrays Sp, int lvl_begin, int lvl_count, int min_len) {
+    // single block; levels treated here have at most a few hundred nodes
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < lvl_count; base += blockDim.x) {
+        const int n = base + threadIdx.x;
+        int c = 0;
+        if (n < lvl_count) { const int len = A.t_len[lvl_begin + n]; c = len > min_len ? (len + kChunk - 1) / kChunk : 0; }
+        // serial prefix by thread 0 over this batch (tiny)
+        __shared__ int tmp[1024];
+        tmp[threadIdx.x] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = carry;
+            for (int k = 0; k < (int)blockDim.x && base + k < lvl_count; k++) { const int v = tmp[k]; tmp[k] = run; run += v; }
+            carry = run;
+        }
+        __syncthreads();
+        if (n < lvl_count) Sp.choff[n] = tmp[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) Sp.choff[lvl_count] = carry;
+}
+
+__device__ __forceinline__ int node_of_chunk(const int* __restrict__ choff, int lvl_count, int b) {
+    int lo = 0, hi = lvl_count;              // last n with choff[n] <= b
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (choff[mid] <= b) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) chunk_sum_kernel(BuildArrays A, SpecArrays Sp, int lvl_begin, int lvl_count, int dir) {
+    __shared__ double ws[8];
+    const double* __restrict__ X = A.x[dir];
+    const int total = Sp.choff[lvl_count];
+    for (int b = blockIdx.x; b < total; b += gridDim.x) {
+        const int n = node_of_chunk(Sp.choff, lvl_count, b);
+        const int t = lvl_begin + n, c = b - Sp.choff[n];
         const long long start = A.t_start[t];
-        double S = 0.0;
-        int pos = 0;
-        while (pos < len) {
-            const int e = (int)((__double_as_longlong(S) >> 52) & 0x7ff) - 1023;
-            const bool okS = S > 0.0 && e >= -900 && e <= 900;
-            const int my = pos + tid * 8;
-            double v[8];
+        const int len = A.t_len[t], lo = c * kChunk, hi = min(len, lo + kChunk);
+        double s = 0.0;
+        for (int i = lo + threadIdx.x; i < hi; i += 256) s += X[start + i];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { double r = 0.0; for (int k = 0; k < 8; k++) r += ws[k]; Sp.approx[b] = r; }
+        __syncthreads();
+    }
+}
+
+// one warp per node: approximate running sum at the start / end of each of its chunks
+__global__ void chunk_prefix_kernel(SpecArrays Sp, int lvl_count) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= lvl_count) return;
+    const int b0 = Sp.choff[w], b1 = Sp.choff[w + 1];
+    double run = 0.0;
+    for (int base = b0; base < b1; base += 32) {
+        const int b = base + lane;
+        const double v = b < b1 ? Sp.approx[b] : 0.0;
+        double x = v;
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (b < b1) { Sp.approx[b] = run + (x - v); Sp.approx_end[b] = run + x; }
+        run += __shfl_sync(0xffffffffu, x, 31);
+    }
+}
+
+__global__ void __launch_bounds__(kBlockWarps * 32) chunk_transducer_kernel(BuildArrays A, SpecArrays Sp, int lvl_begin, int lvl_count, int dir) {
+    __shared__ long long s_a0[kBlockWarps], s_a1[kBlockWarps];
+    __shared__ int s_q0[kBlockWarps], s_q1[kBlockWarps], s_hard;
+    const double* __restrict__ X = A.x[dir];
+    const int total = Sp.choff[lvl_count];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int b = blockIdx.x; b < total; b += gridDim.x) {
+        const double Sa = Sp.approx[b], Sb = Sp.approx_end[b];
+        const int e = (int)((__double_as_longlong(Sa) >> 52) & 0x7ff) - 1023;
+        bool safe = Sa > 0.0 && e >= -900 && e <= 900;
+        if (safe) {
+            const double lo2 = __longlong_as_double((long long)(1023 + e) << 52), hi2 = lo2 * 2.0;
+            safe = Sa > lo2 * (1.0 + 1e-6) && Sb < hi2 * (1.0 - 1e-6);
+        }
+        if (!safe) { if (tid == 0) Sp.meta[b] = 0; continue; }          // uniform branch: Sa, Sb are the same for the block
+        const int n = node_of_chunk(Sp.choff, lvl_count, b);
+        const int t = lvl_begin + n, c = b - Sp.choff[n];
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t], lo = c * kChunk, hi = min(len, lo + kChunk);
+        if (tid == 0) s_hard = 0;
+        __syncthreads();
+        const int my = lo + tid * 8;
+        double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (my + k < len) ? X[start + my + k] : 0.0;
-            long long d0 = 0, d1 = 0;
-            int p0 = 0, p1 = 1;
-            bool hard = !okS;
-            const double scale = okS ? __longlong_as_double((long long)(1023 + 52 - e) << 52) : 1.0;
-            const double top = okS ? __longlong_as_double((long long)(1023 + e + 1) << 52) : 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const double xv = v[k];
-                if (!(xv >= 0.0 && xv < top)) hard = true;
-                const double y = xv * scale;
-                const double qf = floor(y);
-                const double r = y - qf;
-                const long long q = (long long)qf;
-                const int gt = r > 0.5, tie = r == 0.5;
-                int t0 = p0 ^ (int)(q & 1), t1 = p1 ^ (int)(q & 1);
-                const int c0 = gt | (tie & t0), c1 = gt | (tie & t1);
-                d0 += q + c0;
-                d1 += q + c1;
-                p0 = t0 ^ c0;
-                p1 = t1 ^ c1;
+        for (int k = 0; k < 8; k++) v[k] = (my + k < hi) ? X[start + my + k] : 0.0;
+        long long a0, a1;
+        int q0, q1;
+        bool hard;
+        fold8(v, true, e, a0, a1, q0, q1, hard);
+        if (hard) s_hard = 1;
+        scan_transducers(a0, a1, q0, q1);
+        if (lane == 31) { s_a0[w] = a0; s_a1[w] = a1; s_q0[w] = q0; s_q1[w] = q1; }
+        __syncthreads();
+        if (w == 0) {
+            long long A0 = s_a0[lane], A1 = s_a1[lane];
+            int Q0 = s_q0[lane], Q1 = s_q1[lane];
+            scan_transducers(A0, A1, Q0, Q1);
+            if (lane == 31) {
+                Sp.inc[2 * (size_t)b] = A0;
+                Sp.inc[2 * (size_t)b + 1] = A1;
+                Sp.meta[b] = s_hard ? 0 : (1 | (Q0 << 1) | (Q1 << 2) | ((e + 2048) << 8));
             }
-            long long a0 = d0, a1 = d1;
-            int q0 = p0, q1 = p1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long b0 = __shfl_up_sync(full, a0, o), b1 = __shfl_up_sync(full, a1, o);
-                const int r0 = __shfl_up_sync(full, q0, o), r1 = __shfl_up_sync(full, q1, o);
-                if (lane >= o) {
-                    const long long n0 = b0 + (r0 ? a1 : a0), n1 = b1 + (r1 ? a1 : a0);
-                    const int m0 = r0 ? q1 : q0, m1 = r1 ? q1 : q0;
-                    a0 = n0; a1 = n1; q0 = m0; q1 = m1;
-                }
-            }
-            if (lane == 31) { s_a0[w] = a0; s_a1[w] = a1; s_q0[w] = q0; s_q1[w] = q1; }
-            const long long kS = okS ? ((__double_as_longlong(S) & 0xfffffffffffffLL) | (1LL << 52)) : 0;
-            const int parS = (int)(kS & 1);
-            __syncthreads();
-            if (w == 0) {
-                long long A0 = s_a0[lane], A1 = s_a1[lane];
-                int Q0 = s_q0[lane], Q1 = s_q1[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const long long b0 = __shfl_up_sync(full, A0, o), b1 = __shfl_up_sync(full, A1, o);
-                    const int r0 = __shfl_up_sync(full, Q0, o), r1 = __shfl_up_sync(full, Q1, o);
-                    if (lane >= o) {
-                        const long long n0 = b0 + (r0 ? A1 : A0), n1 = b1 + (r1 ? A1 : A0);
-                        const int m0 = r0 ? Q1 : Q0, m1 = r1 ? Q1 : Q0;
-                        A0 = n0; A1 = n1; Q0 = m0; Q1 = m1;
+        }
+        __syncthreads();
+    }
+}
+
+// one block per node: chain the chunk transducers in order from the exact running sum; unsafe or mispredicted chunks
+// are evaluated cooperatively
+__global__ void __launch_bounds__(kBlockWarps * 32) chunk_combine_kernel(BuildArrays A, SpecArrays Sp, int lvl_begin, int lvl_count, int dir) {
+    __shared__ BlockSum sm;
+    const double* __restrict__ X = A.x[dir];
+    for (int n = blockIdx.x; n < lvl_count; n += gridDim.x) {
+        const int b0 = Sp.choff[n], b1 = Sp.choff[n + 1];
+        if (b1 == b0) continue;
+        const int t = lvl_begin + n;
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t];
+        double S = 0.0;                                   // every thread carries the same value
+        for (int b = b0; b < b1; b++) {
+            const int meta = Sp.meta[b];
+            bool done = false;
+            if (meta & 1) {
+                const int e = (meta >> 8) - 2048;
+                const int eS = (int)((__double_as_longlong(S) >> 52) & 0x7ff) - 1023;
+                if (S > 0.0 && eS == e) {
+                    const long long kS = (__double_as_longlong(S) & 0xfffffffffffffLL) | (1LL << 52);
+                    const long long inc = Sp.inc[2 * (size_t)b + (int)(kS & 1)];
+                    if (kS + inc < (1LL << 53)) {
+                        S = __longlong_as_double((long long)(1023 + e - 52) << 52) * (double)(kS + inc);
+                        done = true;
                     }
                 }
-                const long long inc = parS ? A1 : A0;
-                const int par = parS ? Q1 : Q0;
-                long long ex = __shfl_up_sync(full, inc, 1);
-                int exp_ = __shfl_up_sync(full, par, 1);
-                if (lane == 0) { ex = 0; exp_ = parS; }
-                s_pre[lane] = ex;
-                s_par[lane] = exp_;
             }
-            __syncthreads();
-            const long long incl = s_pre[w] + (s_par[w] ? a1 : a0);
-            const bool cross = hard || (kS + incl >= (1LL << 53));
-            const unsigned bad = __ballot_sync(full, cross);
-            if (lane == 0) s_bad[w] = bad ? (w * 32 + __ffs(bad) - 1) : 0x7fffffff;
-            __syncthreads();
-            int f = s_bad[lane];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) f = min(f, __shfl_xor_sync(full, f, o));
-            const double u = __longlong_as_double((long long)(1023 + (okS ? e : 0) - 52) << 52);
-            if (f == 0x7fffffff) {
-                if (tid == NW * 32 - 1) s_tot = incl;
-                __syncthreads();
-                S = u * (double)(kS + s_tot);
-                pos += NW * 256;
-            } else {
-                if (tid == f - 1) s_tot = incl;
-                if (tid == f) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) s_v[k] = v[k];
-                }
-                __syncthreads();
-                if (f > 0) S = u * (double)(kS + s_tot);
-#pragma unroll
-                for (int k = 0; k < 8; k++) S += s_v[k];
-                pos += 8 * (f + 1);
+            if (!done) {                                  // uniform: S and meta are the same for every thread
+                const int lo = (b - b0) * kChunk;
+                S = block_seq_sum(X, start, lo, min(len, lo + kChunk), S, sm);
             }
-            __syncthreads();
         }
-        if (tid == 0) A.t_split[t] = S / (double)len;
+        if (threadIdx.x == 0) A.t_split[t] = S / (double)len;
     }
 }
 
