@@ -1,0 +1,64 @@
+"""The reference's OWN GPU path (oracle/_ref/ref_gpu = its unmodified host code + its photoNs_CUDA.cu compiled for
+sm_100a) timed beside this repository's paths on the same box and the same input: the bundled demo IC (32^3 particles,
+MAXLEAF 16, local list only -- the one configuration the reference kernel can run: SURVEY defects D2, D3, D7).
+Timing row only: the reference kernel skips task 0 and adds an uninitialised result slot (D1).
+usage: python tools/ref_gpu_compare.py            (on a GPU box; prints one JSON object)"""
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")]
+import p2p_b200  # noqa: E402
+from p2p_b200 import host  # noqa: E402
+
+BOX, NSIDE, MAXLEAF, THETA, MASS = 100000.0, 32, 16, 0.4, 211.75382579190332
+pos = np.load(os.path.join(ROOT, "tests", "golden", "demo_lcdm_pos_f32.npy")).astype(np.float64)
+out = {"input": "demo IC 32^3, MAXLEAF 16, theta 0.4, local list (381377 tasks, 83354950 pairs)"}
+with tempfile.TemporaryDirectory() as td:
+    pf, of = os.path.join(td, "pos.f64"), os.path.join(td, "acc.f64")
+    pos.tofile(pf)
+    for name in ("ref_gpu", "ref_dropin"):
+        exe = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.isfile(exe):
+            out[name] = "not built"
+            continue
+        r = subprocess.run([exe, pf, str(len(pos)), str(BOX), str(MAXLEAF), str(NSIDE), str(THETA), str(MASS), of],
+                           capture_output=True, text=True, timeout=300)
+        m = re.search(r"fmm_task first ([0-9.]+) s, second ([0-9.]+) s", r.stderr)
+        g = re.search(r"copyMemGPU ([0-9.]+) s, LaunchKernelP2PIndexing \(synchronous\) ([0-9.]+) s, readResultsGPU ([0-9.]+) s", r.stderr)
+        out[name] = {"rc": r.returncode, "fmm_task_first_s": float(m.group(1)), "fmm_task_warm_s": float(m.group(2))} if m else \
+            {"rc": r.returncode, "stderr": r.stderr[-400:]}
+        if m and g:
+            out[name].update(copyMemGPU_s=float(g.group(1)), launch_sync_s=float(g.group(2)), readResultsGPU_s=float(g.group(3)))
+# this repository, same input: host-list path (tree + walk on the host cores) and device-resident path
+rs, rcut, eps = host.derived_params(BOX, NSIDE, len(pos))
+ctx = p2p_b200.P2PContext(0)
+ctx.set_physics(MASS, eps, 0.0)            # plain kernel, as the reference compiles it (D4)
+ctx.set_box([0.0, 0.0, 0.0], BOX)
+best = {}
+for rep in range(4):
+    t0 = time.perf_counter()
+    T = host.LocalTree(pos, MAXLEAF, [0.0] * 3, [BOX] * 3, 0)
+    tt, ts = T.walk_task_p2p(THETA, rcut)
+    t1 = time.perf_counter()
+    ctx.step_host(T.pos, T.leaf_npart, T.leaf_ipart, tt, ts)
+    t2 = time.perf_counter()
+    ms_k, ms_csr = ctx.last_timings()
+    best["host_lists"] = {"tree_and_walk_s": t1 - t0, "h2d_pack_kernel_d2h_s": t2 - t1, "kernel_ms": ms_k, "csr_ms": ms_csr,
+                          "counts": ctx.counts()}
+    t0 = time.perf_counter()
+    ctx.step_device(pos, MAXLEAF, [0.0] * 3, [BOX] * 3, THETA, rcut, 0.0)      # local list only, like the reference run
+    t3 = time.perf_counter()
+    info = ctx.tree_info()
+    ms_k, ms_csr = ctx.last_timings()
+    best["device_resident"] = {"total_s": t3 - t0, "build_ms": info["ms_build"], "walk_ms": info["ms_walk"], "csr_ms": ms_csr,
+                               "kernel_ms": ms_k, "counts": ctx.counts()}
+out["this_repo"] = best
+print(json.dumps(out))
