@@ -100,6 +100,9 @@ int p2p_domain_route(int nproc, const double* split, double* records, int64_t st
  * 1_Indexing/src/domains.c:20-38,86-157); work[r] = task count of rank r; split[2P-1] updated in place */
 int p2p_domain_relax(int nproc, double box, double* split, const double* work);
 
+/* boxes (center_toptree, 1_Indexing/src/toptree.c:150-182) of the 2P-1 rank-tree nodes for given splits */
+int p2p_domain_boxes(int nproc, double box, const double* split, double* center, double* width, int* direct_of_node);
+
 int p2p_host_max_threads(void);
 
 #ifdef __cplusplus

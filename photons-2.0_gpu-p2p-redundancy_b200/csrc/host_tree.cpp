@@ -686,6 +686,31 @@ int p2p_domain_setup(int nproc, double box, double* split, double* center, doubl
     return 0;
 }
 
+// center_toptree (1_Indexing/src/toptree.c:150-182) for GIVEN splits (after p2p_domain_relax): boxes of all 2P-1 nodes
+int p2p_domain_boxes(int nproc, double box, const double* split, double* center, double* width, int* direct_of_node) {
+    if (nproc < 1 || !split || !center || !width) return -2;
+    const int P = nproc;
+    struct Frame { int n, dim; double l[3], r[3]; };
+    std::vector<Frame> st;
+    st.push_back(Frame{0, 0, {0, 0, 0}, {box, box, box}});
+    while (!st.empty()) {
+        Frame f = st.back();
+        st.pop_back();
+        for (int k = 0; k < 3; k++) {
+            width[3 * f.n + k] = f.r[k] - f.l[k];
+            center[3 * f.n + k] = 0.5 * (f.r[k] + f.l[k]);
+        }
+        if (direct_of_node) direct_of_node[f.n] = f.dim;
+        if (f.n >= P - 1) continue;
+        Frame a = f, b = f;
+        a.n = 2 * f.n + 1; a.dim = (f.dim + 1) % 3; a.r[f.dim] = split[f.n];
+        b.n = 2 * f.n + 2; b.dim = (f.dim + 1) % 3; b.l[f.dim] = split[f.n];
+        st.push_back(b);
+        st.push_back(a);
+    }
+    return 0;
+}
+
 // Work-weighted relaxation of the splits: measure_domain_runtime + determine_split_domtree
 // (1_Indexing/src/domains.c:20-38,86-157).  work[r] is rank r's task count; the fractions are
 // W_r P / (sum W + 1e-4) as 1_Indexing/src/photoNs.c:303 forms them.  Every split moves by

@@ -50,14 +50,17 @@ def _a2a_v(chunks, recv_rows, width, dtype, group):
     return out
 
 
-def decompose(pos, box, group=None):
+def decompose(pos, box, group=None, split=None):
     """Initial routing as the reference does it (1_Indexing/src/domains.c:298-377): rank r starts from
     the slab [N r/P, N (r+1)/P) of the input order, partitions it in place by the equal-volume rank
     kd-tree and ships the blocks; blocks are concatenated in source-rank order.
     Returns (local positions, original indices, toptree centre/width, direct_of_node, domain id)."""
     P, r = dist.get_world_size(group), dist.get_rank(group)
     n = pos.shape[0]
-    split, center, width, direct = host.domain_setup(P, box)
+    if split is None:
+        split, center, width, direct = host.domain_setup(P, box)
+    else:                                   # relaxed splits (host.domain_relax)
+        center, width, direct = host.domain_boxes(P, box, split)
     lo, hi = n * r // P, n * (r + 1) // P
     p = np.array(pos[lo:hi], np.float64, order="C", copy=True)
     idx = np.arange(lo, hi, dtype=np.int64)

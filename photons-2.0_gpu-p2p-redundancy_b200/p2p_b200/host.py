@@ -54,6 +54,7 @@ def load_host_library():
         L.p2p_host_free.argtypes = [C.c_void_p]
         L.p2p_domain_setup.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _ip]
         L.p2p_domain_relax.argtypes = [C.c_int, C.c_double, _dp, _dp]
+        L.p2p_domain_boxes.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _ip]
         L.p2p_domain_route.argtypes = [C.c_int, _dp, _dp, C.c_int64, _lp, C.c_int64, _ip]
         _lib = L
     return _lib
@@ -274,6 +275,18 @@ def domain_relax(nproc, box, split, work):
     if rc != 0:
         raise P2PError(rc, "p2p_domain_relax failed")
     return out
+
+
+def domain_boxes(nproc, box, split):
+    """(center, width, direct) of the rank-tree nodes for given splits (e.g. after domain_relax)."""
+    n = 2 * nproc - 1
+    center, width, direct = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n, np.int32)
+    sp = np.ascontiguousarray(split, np.float64)
+    rc = load_host_library().p2p_domain_boxes(int(nproc), float(box), sp.ctypes.data_as(_dp), center.ctypes.data_as(_dp),
+                                              width.ctypes.data_as(_dp), direct.ctypes.data_as(_ip))
+    if rc != 0:
+        raise P2PError(rc, "p2p_domain_boxes failed")
+    return center, width, direct
 
 
 def max_threads():
