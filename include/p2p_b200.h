@@ -204,6 +204,22 @@ int p2p_gather_leaves(p2p_ctx* ctx, const void* d_marks, const void* d_offset, v
  * (int32 start relative to d_part, int32 count; count 0 for leaves nobody references) */
 int p2p_set_ghosts_device(p2p_ctx* ctx, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf);
 
+/* ---- mid-field on the device: P2M / M2M / M2L / L2L / L2P --------------------------
+ * The other half of the short-range FMM force (1_Indexing/src/operator.c; fmm_prepare, task_compute_m2l and the tail
+ * of fmm_ext in 1_Indexing/src/fmm.c:745-790,913-945,1121-1128): third-order Cartesian expansions in fp64 with the
+ * erfc-split radial factors.  The M2L task list is the set of pairs the walk's acceptance criterion hands to the
+ * expansions (walk_task_m2l / walk_task_m2l_ext), emitted by p2p_tree_walk in the same pass as the P2P list. */
+/* on: the following walks also emit the M2L list.  literal_d6 (test knob): also walk the local tree against itself
+ * with the remote rules as the reference's zero-shift self exchange does (SURVEY defect D6: every local P2P and
+ * M2L task twice), to compare with the reference's literal output. */
+int p2p_midfield_enable(p2p_ctx* ctx, int on, int literal_d6);
+/* P2M -> M2M -> M2L -> L2L -> L2P for the device-built tree and the last walk (single rank: local tree + periodic
+ * images); p2p_download_acc_original then returns P2P + mid-field.  *nm2l: number of M2L tasks. */
+int p2p_midfield_compute(p2p_ctx* ctx, int64_t* nm2l);
+/* multipoles and local expansions, [leaf][20] / [node][20] in the reference's coefficient order
+ * (1_Indexing/inc/operator.h:24-67); NULL skips; *ms: device time of p2p_midfield_compute */
+int p2p_midfield_download(p2p_ctx* ctx, double* leaf_M, double* node_M, double* leaf_L, double* node_L, float* ms);
+
 /* test knob: runs up to this length use the plain in-order fold for the split mean, longer ones the exact parallel
  * evaluation of the same sequential sum (< 0 restores the default) */
 int p2p_tree_set_option(p2p_ctx* ctx, int seq_sum_plain_max);

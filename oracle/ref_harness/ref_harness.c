@@ -185,10 +185,33 @@ static int run_rank(int rank, int nproc, const double* pos, long ntot, double bo
     if (launch_no == 0) launch_no = 1;
     put_d("t_build_s", t_build); put_d("t_fmm_task_s", t_walk_local);
     put_i("idxP2P_local", (int64_t)idxP2P);
+    put_i("idxM2L_local", (int64_t)idxM2L);
+    {   /* multipoles after fmm_prepare (p2m + walk_m2m): the mid-field oracle of row N2 */
+        int nl = last_leaf - first_leaf, nn = last_node - first_node + 1;
+        double* m = (double*)malloc(sizeof(double) * NMULTI * (size_t)((nl > nn ? nl : nn) + 1));
+        for (int i = 0; i < nl; i++) memcpy(m + (size_t)NMULTI * i, leaf[first_leaf + i].M, sizeof(double) * NMULTI);
+        put("leaf_M", 1, m, (uint64_t)nl * NMULTI);
+        for (int i = 0; i < nn; i++) memcpy(m + (size_t)NMULTI * i, btree[first_node + i].M, sizeof(double) * NMULTI);
+        put("node_M", 1, m, (uint64_t)nn * NMULTI);
+        free(m);
+    }
     if (do_ext) {
         t0 = dtime();
         fmm_ext();
         put_d("t_fmm_ext_s", dtime() - t0);
+        put_i("idxM2L_total", (int64_t)idxM2L);
+        {   /* after walk_l2l + l2p: local expansions of the leaves and the mid-field accelerations (the P2P stubs above
+             * return zeros, so part[].acc holds M2L -> L2L -> L2P only), tree order */
+            int nl = last_leaf - first_leaf;
+            double* m = (double*)malloc(sizeof(double) * NMULTI * (size_t)(nl + 1));
+            for (int i = 0; i < nl; i++) memcpy(m + (size_t)NMULTI * i, leaf[first_leaf + i].L, sizeof(double) * NMULTI);
+            put("leaf_L", 1, m, (uint64_t)nl * NMULTI);
+            free(m);
+            double* a = (double*)malloc(sizeof(double) * 3 * (size_t)(NPART ? NPART : 1));
+            for (int i = 0; i < NPART; i++) for (int k = 0; k < 3; k++) a[3 * i + k] = part[i].acc[k];
+            put("acc_mid", 1, a, (uint64_t)NPART * 3);
+            free(a);
+        }
         put_i("numRemoteInteractions", numRemoteInteractions);
         put_i("n_remote_calls", launch_no - 1);
         /* Second decomposition with the reference's load-balance feedback (1_Indexing/src/photoNs.c:295-306:

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "device_tree.cuh"
+#include "midfield.cuh"
 #include "p2p_ctx.h"
 
 #define fail p2p_fail
@@ -31,6 +32,14 @@ struct p2p_dtree {
     DevBuf<int> choff, cmeta;
     DevBuf<double> capprox, capprox_end;
     DevBuf<long long> cinc;
+    // mid-field (M2L lists from the walk, multipoles, local expansions)
+    bool m2l_on = false, literal_d6 = false, mid_valid = false;
+    DevBuf<int> mt, ms, mq;
+    long long nm2l = 0;
+    DevBuf<double> Mall, Lall, acc_mid;
+    std::vector<int> lvl_begin, lvl_count;
+    float ms_mid = 0.f;
+    double walk_period = 0.0;
     int spec_min = 32768;        // nodes longer than this use the speculative chunked evaluation of the split mean
     int* d_scalar = nullptr;     // [0] next-level node count, [1] max leaf occupancy
     int* h_scalar = nullptr;     // pinned
@@ -58,6 +67,7 @@ void p2p_dtree_release(p2p_dtree* t) {
     t->t_start.release(); t->t_len.release(); t->t_parent.release(); t->t_np0.release(); t->t_child.release(); t->t_nleaf.release();
     t->t_nnode.release(); t->t_id.release(); t->t_leafbase.release(); t->child_cnt.release(); t->t_split.release(); t->t_lo.release();
     t->t_hi.release();
+    t->mt.release(); t->ms.release(); t->mq.release(); t->Mall.release(); t->Lall.release(); t->acc_mid.release();
     t->choff.release(); t->cmeta.release(); t->capprox.release(); t->capprox_end.release(); t->cinc.release();
     t->frontier[0].release(); t->frontier[1].release();
     if (t->d_scalar) cudaFree(t->d_scalar);
@@ -79,17 +89,18 @@ int get_tree(p2p_ctx* c, p2p_dtree** out) {
         c->dtree = t;
         CU(cudaMalloc(&t->d_scalar, 4 * sizeof(int)));
         CU(cudaMallocHost(&t->h_scalar, 4 * sizeof(int)));
-        CU(cudaMalloc(&t->d_wcount, 2 * sizeof(ull)));
-        CU(cudaMallocHost(&t->h_wcount, 2 * sizeof(ull)));
+        CU(cudaMalloc(&t->d_wcount, 4 * sizeof(ull)));
+        CU(cudaMallocHost(&t->h_wcount, 4 * sizeof(ull)));
         CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
         CU(cudaMalloc(&t->d_maxw, sizeof(unsigned long long)));
         CU(cudaEventCreate(&t->e0));
         CU(cudaEventCreate(&t->e1));
-        static const int shifts[27][3] = {{0, 0, 0},
+        static const int shifts[28][3] = {{0, 0, 0},
             {-1, -1, -1}, {-1, -1, 0}, {-1, -1, 1}, {-1, 0, -1}, {-1, 0, 0}, {-1, 0, 1}, {-1, 1, -1}, {-1, 1, 0}, {-1, 1, 1},
             {0, -1, -1}, {0, -1, 0}, {0, -1, 1}, {0, 0, -1}, {0, 0, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1},
-            {1, -1, -1}, {1, -1, 0}, {1, -1, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1}, {1, 1, -1}, {1, 1, 0}, {1, 1, 1}};
+            {1, -1, -1}, {1, -1, 0}, {1, -1, 1}, {1, 0, -1}, {1, 0, 0}, {1, 0, 1}, {1, 1, -1}, {1, 1, 0}, {1, 1, 1}, {0, 0, 0}};
         CU(cudaMemcpyToSymbol(p2p::dt::c_shift, shifts, sizeof shifts));
+        CU(cudaMemcpyToSymbol(p2p::mf::c_mshift, shifts, sizeof shifts));
     }
     *out = c->dtree;
     return 0;
@@ -288,7 +299,8 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     memcpy(&t->max_leaf_width, &wbits, sizeof wbits);
     CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
-    t->valid = true; t->built_here = true;
+    t->valid = true; t->built_here = true; t->mid_valid = false;
+    t->lvl_begin = lvl_begin; t->lvl_count = lvl_count;
     return 0;
 }
 
@@ -363,8 +375,13 @@ int p2p_tree_download(p2p_ctx* c, int64_t* perm, double* pos_sorted, int* leaf_n
 
 namespace {
 // breadth-first walk from the given items; appends the tasks to the context's list
-int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std::vector<ull>& init, size_t task_guess) {
+int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector<ull>& init, size_t task_guess) {
     cudaStream_t st = c->stream;
+    t->mid_valid = false; t->nm2l = 0; t->walk_period = P.period;
+    if (t->m2l_on) {
+        const size_t mcap = std::max<size_t>(task_guess, 1 << 16);
+        CU(t->mt.reserve(mcap, st)); CU(t->ms.reserve(mcap, st)); CU(t->mq.reserve(mcap, st));
+    }
     size_t fcap = std::max<size_t>(task_guess / 2, 1 << 16);
     size_t tcap = std::max<size_t>(task_guess, 1 << 16);
     CU(t->frontier[0].reserve(std::max(fcap, init.size()), st)); CU(t->frontier[1].reserve(fcap, st));
@@ -372,8 +389,8 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std:
     CU(c->ts.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
     CU(cudaEventRecord(t->e0, st));
     CU(cudaMemcpyAsync(t->frontier[0].p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(t->d_wcount, 0, 2 * sizeof(ull), st));
-    ull n_in = init.size(), ntask = 0, items = 0;
+    CU(cudaMemsetAsync(t->d_wcount, 0, 4 * sizeof(ull), st));
+    ull n_in = init.size(), ntask = 0, nm2l = 0, items = 0;
     int cur = 0, levels = 0;
     while (n_in) {
         if (++levels > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
@@ -381,13 +398,19 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std:
             const ull cap_out = t->frontier[cur ^ 1].cap;
             const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
             const unsigned grid = (unsigned)std::min<ull>((n_in + 255) / 256, (ull)c->num_sm * 16);
+            P.mt = t->m2l_on ? t->mt.p : nullptr; P.ms = t->ms.p; P.mq = t->mq.p;
+            P.cap_m2l = t->m2l_on ? std::min(t->mt.cap, std::min(t->ms.cap, t->mq.cap)) : 0;
             p2p::dt::walk_level_kernel<<<grid, 256, 0, st>>>(t->frontier[cur].p, n_in, t->frontier[cur ^ 1].p, cap_out, t->d_wcount,
                                                              c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, P);
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 2 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 3 * sizeof(ull), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            const ull n_out = t->h_wcount[0], nt = t->h_wcount[1];
-            if (n_out <= cap_out && nt <= cap_task) { items += n_in; n_in = n_out; ntask = nt; break; }
+            const ull n_out = t->h_wcount[0], nt = t->h_wcount[1], nm = t->h_wcount[2];
+            if (n_out <= cap_out && nt <= cap_task && nm <= P.cap_m2l) { items += n_in; n_in = n_out; ntask = nt; nm2l = nm; break; }
+            if (nm > P.cap_m2l) {
+                const size_t want = (size_t)(nm + nm / 2);
+                CU(t->mt.reserve(want, st, (size_t)nm2l)); CU(t->ms.reserve(want, st, (size_t)nm2l)); CU(t->mq.reserve(want, st, (size_t)nm2l));
+            }
             // a buffer was too small: grow it and repeat this level from the same input
             if (n_out > cap_out) CU(t->frontier[cur ^ 1].reserve((size_t)(n_out + n_out / 4), st));
             if (nt > cap_task) {
@@ -395,7 +418,7 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std:
                 CU(c->tt.reserve(want, st, (size_t)(c->ntask + ntask)));
                 CU(c->ts.reserve(want, st, (size_t)(c->ntask + ntask)));
             }
-            const ull reset[2] = {0, ntask};
+            const ull reset[3] = {0, ntask, nm2l};
             CU(cudaMemcpyAsync(t->d_wcount, reset, sizeof reset, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
         }
@@ -408,6 +431,7 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, const p2p::dt::WalkParams& P, const std:
     c->ntask += (long long)ntask;
     c->csr_valid = false;
     t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
+    t->nm2l = (long long)nm2l;
     return 0;
 }
 
@@ -446,7 +470,8 @@ int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const do
     const int root = nleaf;
     init.push_back(p2p::dt::item(root, root, 0, 0));
     if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, 0, s));
-    return walk_impl(c, t, P, init, (size_t)nleaf * (period > 0.0 ? 192 : 160));
+    if (t->literal_d6) init.push_back(p2p::dt::item(root, root, 0, 27));     // the reference's zero-shift self exchange (defect D6)
+    return walk_impl(c, t, P, init, (size_t)nleaf * (period > 0.0 ? 192 : 160) * (t->literal_d6 ? 2 : 1));
 }
 
 // ---- multi-rank: one tree per rank, every rank walks its tree against all of them --------------------------------
@@ -570,10 +595,80 @@ int p2p_download_acc_original(p2p_ctx* c, double* acc) {
     if (!acc) return fail(P2P_ERR_ARG, "null acc");
     const long long n = c->npart;
     CU(c->acc64.reserve((size_t)n * 3, c->stream));
-    p2p::dt::acc_unpermute_kernel<<<blocks(n, 256), 256, 0, c->stream>>>(c->acc.p, t->perm.p, n, c->acc64.p);
+    if (t->mid_valid)
+        p2p::mf::acc_unpermute_sum_kernel<<<blocks(n, 256), 256, 0, c->stream>>>(c->acc.p, t->acc_mid.p, t->perm.p, n, c->acc64.p);
+    else
+        p2p::dt::acc_unpermute_kernel<<<blocks(n, 256), 256, 0, c->stream>>>(c->acc.p, t->perm.p, n, c->acc64.p);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(acc, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
     return p2p_synchronize(c);
+}
+
+// ---- mid-field: M2L lists come from the same walk; P2M/M2M/M2L/L2L/L2P as kernels ---------------------
+// on != 0: the next walks also emit the M2L task list (pairs the acceptance criterion hands to the expansions).
+// literal_d6 != 0 (test knob): additionally walk the local tree against itself with the remote rules, as the reference's
+// zero-shift self exchange does (SURVEY defect D6) -- every local P2P and M2L task then appears twice, as in the reference.
+int p2p_midfield_enable(p2p_ctx* c, int on, int literal_d6) {
+    USE(c);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    t->m2l_on = on != 0; t->literal_d6 = literal_d6 != 0; t->mid_valid = false;
+    return 0;
+}
+
+// P2M -> M2M -> M2L (tasks of the last walk) -> L2L -> L2P on the device-built tree; the result (fp64, per particle) is
+// added by p2p_download_acc_original.  Single rank (sources are the local tree and its periodic images).
+int p2p_midfield_compute(p2p_ctx* c, int64_t* nm2l) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree (p2p_tree_build)");
+    if (!t->m2l_on) return fail(P2P_ERR_STATE, "enable the M2L lists (p2p_midfield_enable) before the walk");
+    cudaStream_t st = c->stream;
+    const int nl = t->nleaf, nn = t->nnode;
+    const size_t nu = (size_t)nl + nn;
+    CU(t->Mall.reserve(nu * p2p::mf::NM, st)); CU(t->Lall.reserve(nu * p2p::mf::NM, st)); CU(t->acc_mid.reserve((size_t)t->npart * 3, st));
+    CU(cudaEventRecord(t->e0, st));
+    if (nl) p2p::mf::p2m_kernel<<<blocks(nl, 128), 128, 0, st>>>(c->leaf.p, nl, t->box.p, t->x[0].p, t->x[1].p, t->x[2].p, c->mass, t->Mall.p);
+    for (int lvl = t->nlevel - 1; lvl >= 0; lvl--)
+        p2p::mf::m2m_level_kernel<<<blocks(t->lvl_count[lvl], 128), 128, 0, st>>>(t->t_id.p, t->lvl_begin[lvl], t->lvl_count[lvl], t->son.p, nl,
+                                                                                  t->box.p, t->Mall.p);
+    CU(cudaMemsetAsync(t->Lall.p, 0, nu * p2p::mf::NM * sizeof(double), st));
+    if (t->nm2l) {
+        p2p::mf::M2LParams P;
+        memset(&P, 0, sizeof P);
+        P.mt = t->mt.p; P.ms = t->ms.p; P.mq = t->mq.p; P.ntask = t->nm2l; P.box = t->box.p; P.sbox = t->box.p; P.sM = t->Mall.p;
+        P.period = t->walk_period; P.rs = c->rs; P.L = t->Lall.p;
+        p2p::mf::m2l_kernel<<<blocks(t->nm2l, 128), 128, 0, st>>>(P);
+    }
+    for (int lvl = 0; lvl < t->nlevel; lvl++)
+        p2p::mf::l2l_level_kernel<<<blocks(t->lvl_count[lvl], 128), 128, 0, st>>>(t->t_id.p, t->lvl_begin[lvl], t->lvl_count[lvl], t->son.p, nl,
+                                                                                  t->box.p, t->Lall.p);
+    CU(cudaMemsetAsync(t->acc_mid.p, 0, (size_t)t->npart * 24, st));
+    if (nl) p2p::mf::l2p_kernel<<<blocks((long long)nl * 32, 128), 128, 0, st>>>(c->leaf.p, nl, t->box.p, t->Lall.p, t->x[0].p, t->x[1].p, t->x[2].p,
+                                                                                 t->acc_mid.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(t->e1, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&t->ms_mid, t->e0, t->e1));
+    t->mid_valid = true;
+    if (nm2l) *nm2l = t->nm2l;
+    return 0;
+}
+
+// multipoles / local expansions of the device tree in the reference's layout ([leaf][20], [node][20]); NULL skips
+int p2p_midfield_download(p2p_ctx* c, double* leaf_M, double* node_M, double* leaf_L, double* node_L, float* ms) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->mid_valid) return fail(P2P_ERR_STATE, "no mid-field computed");
+    const size_t nl = (size_t)t->nleaf, nn = (size_t)t->nnode, W = p2p::mf::NM * sizeof(double);
+    if (leaf_M && nl) CU(cudaMemcpyAsync(leaf_M, t->Mall.p, nl * W, cudaMemcpyDeviceToHost, c->stream));
+    if (node_M) CU(cudaMemcpyAsync(node_M, t->Mall.p + nl * p2p::mf::NM, nn * W, cudaMemcpyDeviceToHost, c->stream));
+    if (leaf_L && nl) CU(cudaMemcpyAsync(leaf_L, t->Lall.p, nl * W, cudaMemcpyDeviceToHost, c->stream));
+    if (node_L) CU(cudaMemcpyAsync(node_L, t->Lall.p + nl * p2p::mf::NM, nn * W, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (ms) *ms = t->ms_mid;
+    return 0;
 }
 
 // The whole short-range P2P step of one rank in one call: positions (caller's order) in, accelerations (same order)

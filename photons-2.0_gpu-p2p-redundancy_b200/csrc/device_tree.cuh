@@ -836,9 +836,15 @@ struct WalkParams {
     long long sson_base[kMaxPeers];   // first node of peer p in sson
     int snleaf[kMaxPeers];
     int ts_base[kMaxPeers];           // task source id = ts_base[p] + leaf: 0 for me (local ids), ghost leaf ids otherwise
+    // M2L tasks (pairs the acceptance criterion hands to the multipole expansion), emitted when mt != nullptr:
+    // target = local unified id, source = unified id inside rank `peer`, mq = (peer << 5) | displacement index
+    int* mt;
+    int* ms;
+    int* mq;
+    ull cap_m2l;
 };
 
-__constant__ int c_shift[27][3];
+__constant__ int c_shift[28][3];   // [27] = zero displacement walked with the remote rules (the reference's zero-shift self exchange)
 
 // 1_Indexing/src/fmm.c:266-325
 __device__ __forceinline__ int acceptance(const double wi[3], const double wj[3], const double dist[3], double theta, double rcut) {
@@ -901,7 +907,7 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
     const ull n_round = (n_in + 31) & ~31ull;
     for (ull idx = (ull)blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
         int nchild = 0;
-        bool emit = false;
+        bool emit = false, m2l = false;
         int ci[4], cj[4];
         int im = 0, jm = 0, sh = 0, peer = 0, tsid = 0;
         if (idx < n_in) {
@@ -942,16 +948,17 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                         if (ileaf) open = 2;
                         else if (jleaf) open = 1;
                         else open = (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2]) ? 1 : 2;
-                    }
+                    } else if (flag == 1) m2l = true;                       // walk_task_m2l, fmm.c:598,633,668
                 } else if (flag != -1) {
                     bool pruned = false;
                     if (!jleaf) {
                         const double nc[3] = {bj[0], bj[1], bj[2]};
                         pruned = image_pruned(P, nc, wj, disp);
                     }
-                    if (ileaf) { if (flag != 1 && !pruned) open = 2; }
-                    else if (jleaf) { if (flag != 1) open = 1; }
+                    if (ileaf) { if (flag != 1 && !pruned) open = 2; else m2l = true; }   // remotes.c:506: accepted OR cut by the sender
+                    else if (jleaf) { if (flag != 1) open = 1; else m2l = true; }
                     else if (flag != 1) open = (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2] || pruned) ? 1 : 2;
+                    else m2l = true;
                 }
                 if (open == 1) {
                     ci[0] = P.son[2 * (im - P.nleaf)]; ci[1] = P.son[2 * (im - P.nleaf) + 1];
@@ -984,6 +991,15 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
             if (lane == 0) tb = atomicAdd(&counters[1], (ull)__popc(em));
             tb = __shfl_sync(full, tb, 0) + (ull)__popc(em & ((1u << lane) - 1));
             if (emit && tb < cap_task) { tt[tb] = im; ts[tb] = tsid; }
+        }
+        if (P.mt) {
+            const unsigned mm = __ballot_sync(full, m2l);
+            if (mm) {
+                ull mb = 0;
+                if (lane == 0) mb = atomicAdd(&counters[2], (ull)__popc(mm));
+                mb = __shfl_sync(full, mb, 0) + (ull)__popc(mm & ((1u << lane) - 1));
+                if (m2l && mb < P.cap_m2l) { P.mt[mb] = im; P.ms[mb] = jm; P.mq[mb] = (peer << 5) | sh; }
+            }
         }
     }
 }

@@ -76,6 +76,9 @@ def load_library():
     L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
     L.p2p_download_acc_original.argtypes = [C.c_void_p, _dp]
     L.p2p_tree_set_option.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_midfield_enable.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.p2p_midfield_compute.argtypes = [C.c_void_p, _lp]
+    L.p2p_midfield_download.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
     L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_tree_walk_peers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
                                       C.c_void_p, C.c_void_p]
@@ -339,6 +342,25 @@ class P2PContext:
         self.npart = pos.shape[0]
         self.nleaf = self.tree_info()["nleaf"]
         return acc
+
+    # ---- mid-field (M2L lists from the walk; P2M / M2M / M2L / L2L / L2P kernels)
+    def midfield_enable(self, on=True, literal_d6=False):
+        self._chk(self._L.p2p_midfield_enable(self._h, 1 if on else 0, 1 if literal_d6 else 0))
+
+    def midfield_compute(self):
+        n = C.c_int64()
+        self._chk(self._L.p2p_midfield_compute(self._h, C.byref(n)))
+        return n.value
+
+    def midfield_download(self):
+        info = self.tree_info()
+        nl, nn = info["nleaf"], info["nnode"]
+        out = dict(leaf_M=np.zeros((nl, 20)), node_M=np.zeros((nn, 20)), leaf_L=np.zeros((nl, 20)), node_L=np.zeros((nn, 20)))
+        ms = C.c_float()
+        self._chk(self._L.p2p_midfield_download(self._h, out["leaf_M"].ctypes.data_as(_dp), out["node_M"].ctypes.data_as(_dp),
+                                                out["leaf_L"].ctypes.data_as(_dp), out["node_L"].ctypes.data_as(_dp), C.byref(ms)))
+        out["ms"] = ms.value
+        return out
 
     # ---- multi-rank device path (device pointers, e.g. tensor.data_ptr())
     def tree_export(self, d_box, d_son, d_leaf):

@@ -1,5 +1,5 @@
 """Times the device-resident short-range step (tree build, dual-tree walk, packing, forces) on one GPU.
-usage: python tools/device_step.py [nside] [maxleaf] [reps] [--clustered]"""
+usage: python tools/device_step.py [nside] [maxleaf] [reps] [--clustered] [--midfield] [--theta=X]"""
 import os
 import sys
 import time
@@ -24,15 +24,19 @@ bdl, bdr = np.zeros(3), np.full(3, box)
 import torch  # noqa: E402  (pinned host buffers)
 ppos = torch.from_numpy(pos).pin_memory().numpy()
 acc = torch.empty((pos.shape[0], 3), dtype=torch.float64).pin_memory().numpy()
+theta = max([float(a.split("=")[1]) for a in sys.argv if a.startswith("--theta=")] + [0.0]) or 0.4
+mid = "--midfield" in sys.argv
+ctx.midfield_enable(mid)
 for r in range(reps):
     t0 = time.perf_counter()
     ctx.tree_build(ppos, maxleaf, bdl, bdr, 0)
     t1 = time.perf_counter()
     ctx.clear_tasks()
-    ctx.tree_walk(0.4, rcut, box, 0.5 * (bdr + bdl), bdr - bdl)
+    ctx.tree_walk(theta, rcut, box, 0.5 * (bdr + bdl), bdr - bdl)
     t2 = time.perf_counter()
     ctx.build_csr()
     ctx.compute()
+    nm2l = ctx.midfield_compute() if mid else 0
     ctx.download_acc_original(acc)
     t3 = time.perf_counter()
     info = ctx.tree_info()
@@ -41,4 +45,5 @@ for r in range(reps):
     print(f"rep {r}: total {1e3 * (t3 - t0):.1f} ms | build {1e3 * (t1 - t0):.1f} (device {info['ms_build']:.1f}) "
           f"walk {1e3 * (t2 - t1):.1f} (device {info['ms_walk']:.1f}, {info['walk_items']} items) "
           f"csr {ms_csr:.1f} force {ms_k:.1f} rest {1e3 * (t3 - t2) - ms_csr - ms_k:.1f} | "
+          + (f"midfield {ctx.midfield_download()['ms']:.2f} ms ({nm2l} M2L tasks) | " if mid else "") +
           f"{info['nleaf']} leaves {info['nlevel']} levels {nt} tasks {npairs} pairs dup {ctx.csr_duplicates()}", flush=True)
