@@ -398,7 +398,8 @@ def main():
                     "d2h_bytes_per_step": all_d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "csr_pack_ms": csr_ms},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None, "kernel": "p2p_rows_kernel<TT=16,NSRC=2,STAGE=384,trunc,packed(FFMA2),4 blocks/SM,split polynomial>", "kernel_ms": kernel_ms,
+                         "traffic": 1.35e9 if (not distributed and args.nside == 256 and args.maxleaf == 32 and not args.clustered) else None,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload (profiles/r1e_ncu_rows_kernel_256_final.txt); null for other workloads", "kernel": "p2p_rows_kernel<TT=16,NSRC=2,STAGE=384,trunc,packed(FFMA2),4 blocks/SM,split polynomial>", "kernel_ms": kernel_ms,
                          "flop_per_pair": FLOP_PER_PAIR,
                          "peak_source": f"{props.multi_processor_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peaks_kind}); "
                                         "the file holds no FP32 figure, SURVEY.md section 8d defines this peak",

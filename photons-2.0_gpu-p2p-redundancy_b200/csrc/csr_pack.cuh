@@ -156,11 +156,35 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
 // sum over tasks of n_t * n_s: the pair-interaction count of the metric; also records
 // every row's work and a histogram of the target occupancy n_t for the row schedule
 constexpr int kWorkBuckets = 64;
+constexpr int kMinBandRows = 16384;  // smallest band of the row schedule (bounds the size of the band histograms)
+
+// Band size of the row schedule, chosen on the device from the leaf occupancies: (number of distinct target
+// occupancies) x (resident warps), so that the warps resident at any time work on one or two occupancy values
+// (see below), but no larger, so that a band's particles stay in L2.  occ[0..63]: scratch, zeroed by the caller.
+__global__ void __launch_bounds__(256) occupancy_hist_kernel(const int2* __restrict__ leaf, int nrow, unsigned int* __restrict__ occ) {
+    __shared__ unsigned int h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < nrow) { const int nt = leaf[row].y; if (nt > 0) atomicAdd(h + min(nt, 63), 1u); }
+    __syncthreads();
+    if (threadIdx.x < 64 && h[threadIdx.x]) atomicAdd(occ + threadIdx.x, h[threadIdx.x]);
+}
+__global__ void band_rows_kernel(const unsigned int* __restrict__ occ, int nrow, int resident_warps, int fixed, int* __restrict__ band_rows) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int distinct = 0;
+        for (int b = 0; b < 64; b++) distinct += occ[b] != 0;
+        const int target = fixed > 0 ? max(fixed, kMinBandRows) : max(kMinBandRows, distinct * resident_warps);
+        const int nband = max(1, (nrow + target / 2) / target);          // equal bands: no short last band
+        *band_rows = max(kMinBandRows, (nrow + nband - 1) / nband);
+    }
+}
 __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col,
                                                          const int2* __restrict__ leaf, int nrow,
                                                          unsigned long long* __restrict__ npairs,
                                                          unsigned long long* __restrict__ row_work,
-                                                         unsigned int* __restrict__ hist) {
+                                                         unsigned int* __restrict__ hist, const int* __restrict__ band_rows_p) {
+    const int band_rows = *band_rows_p;
     unsigned long long s = 0;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -173,33 +197,38 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
         const unsigned long long w = nt * ns;
         if (lane == 0) {
             row_work[row] = w;
-            if (w) atomicAdd(hist + min((int)nt, kWorkBuckets - 1), 1u);
+            if (w) atomicAdd(hist + (row / band_rows) * kWorkBuckets + min((int)nt, kWorkBuckets - 1), 1u);
             s += w;
         }
     }
     if (lane == 0 && s) atomicAdd(npairs, s);
 }
 
-// Row schedule: only rows that have work, ordered by target occupancy n_t (fullest leaves first, row order
-// within one occupancy).  The force kernel instantiates its slice code per number of target pairs; with rows
+// Row schedule: only rows that have work; bands of consecutive rows (a spatially compact piece of the kd order whose
+// particles stay in L2; size from band_rows_kernel), and inside a band by target occupancy n_t (fullest leaves first).  The force kernel instantiates its slice code per number of target pairs; with rows
 // in arbitrary order the 16 resident warps of an SM run up to 8 different ~7 KB code bodies at once and the
 // instruction cache thrashes (ncu on the clustered box: stall_no_instruction 9.5 per issue, issue rate
 // halved).  Grouping rows by n_t makes the whole chip run the same one or two bodies at any time; the
 // fullest (most expensive) rows go first, so the tail of the persistent kernel consists of cheap rows.
-__global__ void work_bucket_offsets_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor,
+// Ordering the WHOLE list by n_t instead swept the particle array once per occupancy value: 8.5 GB of DRAM reads per
+// launch at 256^3 against 1 GB of compulsory traffic (ncu, profiles/r1e_ncu_rows_kernel_256_final.txt).
+__global__ void work_bucket_offsets_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor, int nband,
                                            unsigned int* __restrict__ n_active) {
+    // nband: upper bound (rows / kMinBandRows + 1); bands beyond the real count are empty
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned int run = 0;
-        for (int b = kWorkBuckets - 1; b >= 0; b--) { cursor[b] = run; run += hist[b]; }
+        for (int band = 0; band < nband; band++)
+            for (int b = kWorkBuckets - 1; b >= 0; b--) { cursor[band * kWorkBuckets + b] = run; run += hist[band * kWorkBuckets + b]; }
         *n_active = run;
     }
 }
 __global__ void work_order_scatter_kernel(const unsigned long long* __restrict__ row_work, const int2* __restrict__ nt_of,
-                                          int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order) {
+                                          int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order, const int* __restrict__ band_rows_p) {
+    const int band_rows = *band_rows_p;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row < nrow) {
         const unsigned long long w = row_work[row];
-        if (w) order[atomicAdd(cursor + min(nt_of[row].y, kWorkBuckets - 1), 1u)] = row;
+        if (w) order[atomicAdd(cursor + (row / band_rows) * kWorkBuckets + min(nt_of[row].y, kWorkBuckets - 1), 1u)] = row;
     }
 }
 

@@ -292,6 +292,7 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), st));
     c->acc_tasks = 0;
     c->max_target_leaf = maxleaf;
+    if ((r = p2p_update_occupancy(c))) return r;
     CU(cudaEventRecord(t->e1, st));
     unsigned long long wbits = 0;
     CU(cudaMemcpyAsync(&wbits, t->d_maxw, sizeof wbits, cudaMemcpyDeviceToHost, st));

@@ -33,6 +33,15 @@ int p2p_fail(int code, const char* fmt, ...) {
 }
 #define fail p2p_fail
 
+int p2p_update_occupancy(p2p_ctx* c) {
+    CU(cudaMemsetAsync(c->d_occ, 0, 64 * sizeof(unsigned int), c->stream));
+    if (c->nleaf) {
+        p2p::occupancy_hist_kernel<<<(c->nleaf + 255) / 256, 256, 0, c->stream>>>(c->leaf.p, c->nleaf, c->d_occ);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
 int p2p_use(p2p_ctx* c) {
     if (!c) return fail(P2P_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
@@ -180,6 +189,8 @@ int p2p_create(p2p_ctx** out, int device) {
     CU(cudaMallocHost(&c->h_flags, 8 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counter2, 4 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_bad, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_occ, 64 * sizeof(unsigned int)));
+    CU(cudaMemset(c->d_occ, 0, 64 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_bad, 0, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_npairs2, sizeof(unsigned long long)));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -211,6 +222,7 @@ int p2p_destroy(p2p_ctx* c) {
     c->tt2.release(); c->ts2.release(); c->col2.release(); c->row_ptr2.release(); c->cnt2.release(); c->cursor2.release(); c->tile2.release();
     if (c->d_counter2) cudaFree(c->d_counter2);
     if (c->d_bad) cudaFree(c->d_bad);
+    if (c->d_occ) cudaFree(c->d_occ);
     if (c->d_npairs2) cudaFree(c->d_npairs2);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < 2; k++) { if (c->ev_packed[k]) cudaEventDestroy(c->ev_packed[k]); if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]); }
@@ -294,7 +306,7 @@ int p2p_upload_leaves(p2p_ctx* c, const int* leaf_npart, const int* leaf_ipart, 
         p2p::leaves_pack_kernel<<<(nleaf + 255) / 256, 256, 0, c->stream>>>(ds, dc, nleaf, 0, c->leaf.p);
         CU(cudaGetLastError());
     }
-    return 0;
+    return p2p_update_occupancy(c);
 }
 
 static int append_ghost_leaves(p2p_ctx* c, const int* start, const int* count, int nleaf, long long nbody, int* first_id) {
@@ -406,6 +418,16 @@ struct ListSet {                       // one set of task / CSR buffers (the con
     unsigned int* d_counter;           // [0] row scheduler, [1] unsorted rows, [2] rows in the work-ordered schedule
     unsigned long long* d_npairs;
 };
+// rows per band of the row schedule (csr_pack.cuh): chosen on the device unless P2P_B200_BAND_ROWS fixes it (sweeps)
+int band_rows() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("P2P_B200_BAND_ROWS");
+        v = e ? atoi(e) : -1;
+        if (v < 256) v = -1;                       // -1: chosen on the device (band_rows_kernel)
+    }
+    return v;
+}
 ListSet list_set(p2p_ctx* c, int k) {
     if (k == 0)
         return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, &c->row_work, &c->order, &c->whist,
@@ -423,7 +445,7 @@ int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     CU(L.tile->reserve((size_t)((nrow + p2p::kScanTile - 1) / p2p::kScanTile) + 1, st));
     CU(L.row_work->reserve((size_t)nrow + 1, st));
     CU(L.order->reserve((size_t)nrow + 1, st));
-    CU(L.whist->reserve(2 * p2p::kWorkBuckets, st));
+    CU(L.whist->reserve(2 * (size_t)p2p::kWorkBuckets * (nrow / p2p::kMinBandRows + 1) + 128, st));
     return 0;
 }
 
@@ -435,7 +457,8 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
     CU(cudaMemsetAsync(L.cnt->p, 0, ((size_t)nrow + 1) * 4, st));
     CU(cudaMemsetAsync(L.d_counter, 0, 4 * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(L.whist->p, 0, 2 * p2p::kWorkBuckets * sizeof(unsigned int), st));
+    const int nband = nrow / p2p::kMinBandRows + 1;                    // upper bound; the band size itself is chosen on the device
+    CU(cudaMemsetAsync(L.whist->p, 0, (2 * (size_t)p2p::kWorkBuckets * nband + 128) * sizeof(unsigned int), st));
     CU(cudaMemsetAsync(L.d_npairs, 0, sizeof(unsigned long long), st));
     if (nrow == 0) {
         CU(cudaMemsetAsync(L.row_ptr->p, 0, sizeof(long long), st));
@@ -455,10 +478,12 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     if (n) {
         p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p);
         p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p, nrow, L.col->p, L.d_counter + 1);
-        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p);
-        p2p::work_bucket_offsets_kernel<<<1, 32, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets, L.d_counter + 2);
+        int* d_band = reinterpret_cast<int*>(L.whist->p + 2 * (size_t)p2p::kWorkBuckets * nband);
+        p2p::band_rows_kernel<<<1, 32, 0, st>>>(c->d_occ, nrow, c->num_sm * 16, band_rows(), d_band);
+        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p, d_band);
+        p2p::work_bucket_offsets_kernel<<<1, 32, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets * nband, nband, L.d_counter + 2);
         p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p, c->leaf.p, nrow,
-                                                                          L.whist->p + p2p::kWorkBuckets, L.order->p);
+                                                                          L.whist->p + p2p::kWorkBuckets * nband, L.order->p, d_band);
         CU(cudaGetLastError());
     }
     return 0;

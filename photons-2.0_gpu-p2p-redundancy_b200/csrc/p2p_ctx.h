@@ -93,9 +93,11 @@ struct p2p_ctx {
     int last_blocks_per_sm = 0;
     bool timed_compute = false, timed_csr = false;
     p2p_dtree* dtree = nullptr;
+    unsigned int* d_occ = nullptr;          // [64] histogram of the local leaves' occupancies (row schedule band size)
 };
 
 int p2p_use(p2p_ctx* c);
+int p2p_update_occupancy(p2p_ctx* c);     // after the local leaf table changed
 #define USE(c)                \
     do {                      \
         int r__ = p2p_use(c); \
