@@ -193,7 +193,11 @@ int p2p_create(p2p_ctx** out, int device) {
     CU(cudaMemset(c->d_occ, 0, 64 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_bad, 0, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_npairs2, sizeof(unsigned long long)));
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {   // the copy / packing stream outranks the force kernel's: its small kernels take the room left for them first
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
+    }
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
