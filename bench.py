@@ -411,9 +411,11 @@ def main():
             out["config"]["full_step"] = full_step
         if not args.no_cpu_baseline and not distributed:
             rate, npr, nrow, dt, threads = cpu_oracle_rate(L, mass, args.cpu_pairs, os.cpu_count() or 1)
+            rate1, npr1, _, dt1, _ = cpu_oracle_rate(L, mass, max(args.cpu_pairs / 40, 1e8), 1)
             out["cpu_baseline"] = {"value": rate, "unit": "pair/s", "cores": threads, "kind": "port",
                                    "sample": f"first {nrow} of {T.nleaf} target leaves (complete CSR rows) = {npr} pairs in {dt:.1f} s, "
-                                             "fp64 oracle (erfc/exp), OpenMP dynamic over target leaves"}
+                                             "fp64 oracle (erfc/exp), OpenMP dynamic over target leaves",
+                                   "single_thread": {"value": rate1, "unit": "pair/s", "sample": f"{npr1} pairs in {dt1:.1f} s"}}
         print_json(out)
     if distributed:
         dist.barrier()
