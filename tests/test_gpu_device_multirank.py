@@ -45,7 +45,7 @@ def _worker(rank, world, port, pos, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_device_multirank_matches_oracle(demo_pos, world):
     import flow
     port = _free_port()

@@ -235,3 +235,42 @@ def test_walk_argument_errors(ctx, demo_pos):
             c.tree_build(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, 3)   # bad direction
     finally:
         c.close()
+
+
+def test_degenerate_inputs_fail_loudly(ctx, demo_pos):
+    """more coincident particles than a leaf holds: the reference recurses until it overruns its arrays; here an error"""
+    box = 1000.0
+    pos = np.full((100, 3), 123.456)
+    ctx.set_physics(1.0, 0.01, 10.0)
+    ctx.set_box([0.0, 0.0, 0.0], box)
+    with pytest.raises(p2p_b200.P2PError):
+        ctx.tree_build(pos, 8, [0, 0, 0], [box] * 3, 0)
+    # a periodic box too small for minimal-image sources is refused by the one-call step
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, 8, len(demo_pos))          # r_s of an 8-cell box: r_cut > box / 2
+    ctx.set_physics(DEMO_MASS, eps, rs)
+    ctx.set_box([0.0, 0.0, 0.0], DEMO_BOX)
+    with pytest.raises(p2p_b200.P2PError):
+        ctx.step_device(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, THETA, rcut, DEMO_BOX)
+    # and the context is still usable afterwards
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    ctx.set_physics(DEMO_MASS, eps, rs)
+    acc = ctx.step_device(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, THETA, rcut, DEMO_BOX)
+    assert np.isfinite(acc).all() and ctx.counts() == (381377 + 205240, 83354950 + 36821870)
+
+
+def test_non_periodic_step_and_repeatability(ctx, demo_pos):
+    """period 0: local list only; two runs give bit-identical accelerations (sorted rows, no atomics on floats)"""
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    ctx.set_physics(DEMO_MASS, eps, rs)
+    ctx.set_box([0.0, 0.0, 0.0], DEMO_BOX)
+    a1 = ctx.step_device(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, THETA, rcut, 0.0).copy()
+    assert ctx.counts() == (381377, 83354950)
+    a2 = ctx.step_device(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, THETA, rcut, 0.0)
+    assert np.array_equal(a1, a2)
+    O = oracle.Tree(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, 0)
+    tt, ts = O.walk_p2p(THETA, rcut)
+    ref, _ = oracle.p2p(O.pos, O.leaf_npart, O.leaf_ipart, O.pos, O.leaf_npart, O.leaf_ipart, tt, ts, DEMO_MASS, eps, rs)
+    want = np.zeros_like(ref)
+    want[O.perm] = ref
+    na = np.linalg.norm(want, axis=1)
+    assert (np.linalg.norm(a1 - want, axis=1) / np.maximum(na, na.mean())).max() < TOL
