@@ -204,6 +204,23 @@ int p2p_gather_leaves(p2p_ctx* ctx, const void* d_marks, const void* d_offset, v
  * (int32 start relative to d_part, int32 count; count 0 for leaves nobody references) */
 int p2p_set_ghosts_device(p2p_ctx* ctx, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf);
 
+/* ---- particle routing on the device (domain_decomposition: prepare_body_inOrderOf_domain + exchange,
+ * 1_Indexing/src/domains.c:163-377): the slab a rank holds is partitioned by the rank kd-tree with the reference's
+ * in-place partition (same group order, same order inside a group), the groups travel as device buffers, and the
+ * tree is built from what arrived -- particles never return to the host between routing and forces. ------------- */
+/* host slab -> resident device arrays; particle i carries the global id first_index + i through the exchange */
+int p2p_route_load(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t n, int64_t first_index);
+/* split[2P-1] in heap order (p2p_domain_setup / p2p_domain_relax); P a power of two; sendcount[r] = group size for rank r */
+int p2p_route_partition(p2p_ctx* ctx, int nproc, const double* split, int* sendcount);
+/* copies of / into the resident arrays; DEVICE pointers owned by the caller: x, y, z doubles, idx int32 */
+int p2p_route_export(p2p_ctx* ctx, void* d_x, void* d_y, void* d_z, void* d_idx);
+int p2p_route_import(p2p_ctx* ctx, const void* d_x, const void* d_y, const void* d_z, const void* d_idx, int64_t n);
+/* build_localtree over the resident particles in their current order (what the reference's part[] holds after the
+ * exchange); afterwards as after p2p_tree_build, except that results are read with p2p_download_acc (tree order) and
+ * p2p_download_index (the global id of every tree position) */
+int p2p_tree_build_resident(p2p_ctx* ctx, int maxleaf, const double bdl[3], const double bdr[3], int direct_start);
+int p2p_download_index(p2p_ctx* ctx, int64_t* idx);
+
 /* ---- mid-field on the device: P2M / M2M / M2L / L2L / L2P --------------------------
  * The other half of the short-range FMM force (1_Indexing/src/operator.c; fmm_prepare, task_compute_m2l and the tail
  * of fmm_ext in 1_Indexing/src/fmm.c:745-790,913-945,1121-1128): third-order Cartesian expansions in fp64 with the

@@ -50,6 +50,8 @@ struct p2p_dtree {
     unsigned int* d_dup = nullptr;
     unsigned long long* d_maxw = nullptr;
     double max_leaf_width = 0.0;
+    long long resident = 0;      // particles currently in x[] / perm[]
+    bool perm_is_local = true;   // perm[] indexes the array given to p2p_tree_build (false: global ids after a routing)
     long long walk_tasks = 0, walk_items = 0;
     int walk_levels = 0;
     int plain_max = p2p::dt::kSeqPlainMax;
@@ -168,6 +170,35 @@ int p2p_tree_upload(p2p_ctx* c, int maxleaf, int nleaf, int nnode, int first_lea
 
 // build_localtree on the device.  pos: host rows of 3 doubles in the caller's order (stride in doubles).
 // On success the context holds the particles in tree order (fixed point), the leaves, and the tree for p2p_tree_walk.
+}  // extern "C"
+
+namespace {
+// buffers of the level-synchronous build / routing for npart particles and up to ncap temp nodes
+int reserve_build(p2p_ctx* c, p2p_dtree* t, long long npart, size_t ncap, p2p::dt::BuildArrays* A) {
+    cudaStream_t st = c->stream;
+    for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)npart, st, (size_t)std::min<long long>(t->resident, npart)));
+    CU(t->perm.reserve((size_t)npart, st, (size_t)std::min<long long>(t->resident, npart)));
+    CU(t->seg.reserve((size_t)npart, st)); CU(t->seg_next.reserve((size_t)npart, st));
+    CU(t->slot.reserve((size_t)npart, st)); CU(t->flag.reserve((size_t)npart, st)); CU(t->G.reserve((size_t)npart + 1, st));
+    const int ntile = (int)((npart + p2p::dt::kTile - 1) / p2p::dt::kTile);
+    CU(t->tile.reserve((size_t)ntile + 1, st));
+    CU(t->t_start.reserve(ncap, st)); CU(t->t_len.reserve(ncap, st)); CU(t->t_parent.reserve(ncap, st)); CU(t->t_np0.reserve(ncap, st));
+    CU(t->t_child.reserve(2 * ncap, st)); CU(t->t_nleaf.reserve(ncap, st)); CU(t->t_nnode.reserve(ncap, st)); CU(t->t_id.reserve(ncap, st));
+    CU(t->t_leafbase.reserve(ncap, st)); CU(t->child_cnt.reserve(ncap, st)); CU(t->t_split.reserve(ncap, st));
+    CU(t->t_lo.reserve(3 * ncap, st)); CU(t->t_hi.reserve(3 * ncap, st));
+    for (int k = 0; k < 3; k++) A->x[k] = t->x[k].p;
+    A->perm = t->perm.p; A->seg = t->seg.p; A->seg_next = t->seg_next.p; A->flag = t->flag.p; A->G = t->G.p; A->slot = t->slot.p;
+    A->t_start = t->t_start.p; A->t_len = t->t_len.p; A->t_parent = t->t_parent.p; A->t_np0 = t->t_np0.p; A->t_split = t->t_split.p;
+    A->t_child = t->t_child.p; A->t_nleaf = t->t_nleaf.p; A->t_nnode = t->t_nnode.p; A->t_id = t->t_id.p; A->t_leafbase = t->t_leafbase.p;
+    A->t_lo = t->t_lo.p; A->t_hi = t->t_hi.p;
+    return 0;
+}
+
+int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const double bdl[3], const double bdr[3], int direct_start);
+}  // namespace
+
+extern "C" {
+
 int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
                    const double bdr[3], int direct_start) {
     USE(c);
@@ -181,31 +212,36 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     if (r) return r;
     cudaStream_t st = c->stream;
     t->valid = false;
-    int cap = (int)(2.0 * (double)npart / (double)maxleaf);   // the reference's NLEAF = NNODE capacity (fmm.c:203-209)
-    if (cap > npart) cap = (int)npart + 1;
-    const size_t ncap = (size_t)std::max(cap, 1) + 2;
+    t->resident = 0;
     // ---- upload and split into coordinate arrays
     CU(c->stage.reserve((size_t)npart * 24, st));
     if (stride == 3) CU(cudaMemcpyAsync(c->stage.p, pos, (size_t)npart * 24, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)stride * 8, 24, (size_t)npart, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(t->e0, st));
     for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)npart, st));
-    CU(t->perm.reserve((size_t)npart, st)); CU(t->seg.reserve((size_t)npart, st)); CU(t->seg_next.reserve((size_t)npart, st));
-    CU(t->slot.reserve((size_t)npart, st)); CU(t->flag.reserve((size_t)npart, st)); CU(t->G.reserve((size_t)npart + 1, st));
-    const int ntile = (int)((npart + p2p::dt::kTile - 1) / p2p::dt::kTile);
-    CU(t->tile.reserve((size_t)ntile + 1, st));
-    CU(t->t_start.reserve(ncap, st)); CU(t->t_len.reserve(ncap, st)); CU(t->t_parent.reserve(ncap, st)); CU(t->t_np0.reserve(ncap, st));
-    CU(t->t_child.reserve(2 * ncap, st)); CU(t->t_nleaf.reserve(ncap, st)); CU(t->t_nnode.reserve(ncap, st)); CU(t->t_id.reserve(ncap, st));
-    CU(t->t_leafbase.reserve(ncap, st)); CU(t->child_cnt.reserve(ncap, st)); CU(t->t_split.reserve(ncap, st));
-    CU(t->t_lo.reserve(3 * ncap, st)); CU(t->t_hi.reserve(3 * ncap, st));
+    CU(t->perm.reserve((size_t)npart, st)); CU(t->seg.reserve((size_t)npart, st));
+    p2p::dt::soa_from_aos_kernel<<<blocks(npart, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), npart, t->x[0].p, t->x[1].p,
+                                                                     t->x[2].p, t->perm.p, t->seg.p);
+    CU(cudaGetLastError());
+    t->resident = npart;
+    t->perm_is_local = true;
+    return build_core(c, t, npart, maxleaf, bdl, bdr, direct_start);
+}
+
+}  // extern "C"
+
+namespace {
+// build_localtree over the particles resident in t->x / t->perm (current order = the order the reference would start from)
+int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const double bdl[3], const double bdr[3], int direct_start) {
+    cudaStream_t st = c->stream;
+    int r;
+    int cap = (int)(2.0 * (double)npart / (double)maxleaf);   // the reference's NLEAF = NNODE capacity (fmm.c:203-209)
+    if (cap > npart) cap = (int)npart + 1;
+    const size_t ncap = (size_t)std::max(cap, 1) + 2;
     p2p::dt::BuildArrays A;
-    for (int k = 0; k < 3; k++) A.x[k] = t->x[k].p;
-    A.perm = t->perm.p; A.seg = t->seg.p; A.seg_next = t->seg_next.p; A.flag = t->flag.p; A.G = t->G.p; A.slot = t->slot.p;
-    A.t_start = t->t_start.p; A.t_len = t->t_len.p; A.t_parent = t->t_parent.p; A.t_np0 = t->t_np0.p; A.t_split = t->t_split.p;
-    A.t_child = t->t_child.p; A.t_nleaf = t->t_nleaf.p; A.t_nnode = t->t_nnode.p; A.t_id = t->t_id.p; A.t_leafbase = t->t_leafbase.p;
-    A.t_lo = t->t_lo.p; A.t_hi = t->t_hi.p;
-    p2p::dt::soa_from_aos_kernel<<<blocks(npart, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), npart, A.x[0], A.x[1],
-                                                                     A.x[2], A.perm, A.seg);
+    if ((r = reserve_build(c, t, npart, ncap, &A))) return r;
+    const int ntile = (int)((npart + p2p::dt::kTile - 1) / p2p::dt::kTile);
+    CU(cudaMemsetAsync(A.seg, 0, (size_t)npart * sizeof(int), st));
     const int root[3] = {0, (int)npart, -1};
     CU(cudaMemcpyAsync(A.t_start, &root[0], 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(A.t_len, &root[1], 4, cudaMemcpyHostToDevice, st));
@@ -302,6 +338,136 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
     t->valid = true; t->built_here = true; t->mid_valid = false;
     t->lvl_begin = lvl_begin; t->lvl_count = lvl_count;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- particle routing on the device (domain_decomposition: prepare_body_inOrderOf_domain + exchange) -----------------
+// host slab -> resident arrays; perm[i] = first_index + i (the particle's global id, carried through the exchange)
+int p2p_route_load(p2p_ctx* c, const double* pos, int64_t stride, int64_t n, int64_t first_index) {
+    USE(c);
+    if (n < 0 || (n && !pos) || stride < 3 || first_index < 0 || first_index + n > 0x7fffffffLL) return fail(P2P_ERR_ARG, "bad slab");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    cudaStream_t st = c->stream;
+    t->valid = false; t->resident = 0;
+    if (n == 0) return 0;
+    CU(c->stage.reserve((size_t)n * 24, st));
+    if (stride == 3) CU(cudaMemcpyAsync(c->stage.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)n, st));
+    CU(t->perm.reserve((size_t)n, st)); CU(t->seg.reserve((size_t)n, st));
+    p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->x[0].p, t->x[1].p, t->x[2].p,
+                                                                 t->perm.p, t->seg.p);
+    p2p::dt::iota_offset_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n, (int)first_index);
+    CU(cudaGetLastError());
+    t->resident = n; t->perm_is_local = false;
+    return 0;
+}
+
+// Partition the resident particles by the rank kd-tree (split[2P-1] in heap order, as p2p_domain_setup / _relax give
+// them): afterwards they are grouped by destination rank, in rank order, each group in the order the reference's
+// in-place partition leaves it; sendcount[r] = size of the group for rank r.  P must be a power of two.
+int p2p_route_partition(p2p_ctx* c, int nproc, const double* split, int* sendcount) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t) return fail(P2P_ERR_STATE, "p2p_route_load first");
+    if (nproc < 1 || (nproc & (nproc - 1)) || !split || !sendcount) return fail(P2P_ERR_ARG, "the device routing needs a power-of-two rank count");
+    cudaStream_t st = c->stream;
+    const long long n = t->resident;
+    int levels = 0;
+    while ((1 << levels) < nproc) levels++;
+    if (n == 0) { for (int r = 0; r < nproc; r++) sendcount[r] = 0; return 0; }
+    p2p::dt::BuildArrays A;
+    int r = reserve_build(c, t, n, (size_t)2 * nproc + 2, &A);
+    if (r) return r;
+    DevBuf<double> dsplit;                      // tiny; released below
+    CU(dsplit.reserve((size_t)2 * nproc, st));
+    CU(cudaMemcpyAsync(dsplit.p, split, (size_t)(2 * nproc - 1) * 8, cudaMemcpyHostToDevice, st));
+    const int ntile = (int)((n + p2p::dt::kTile - 1) / p2p::dt::kTile);
+    CU(cudaMemsetAsync(A.seg, 0, (size_t)n * sizeof(int), st));
+    const int root[3] = {0, (int)n, -1};
+    CU(cudaMemcpyAsync(A.t_start, &root[0], 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A.t_len, &root[1], 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A.t_parent, &root[2], 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A.t_split, dsplit.p, 8, cudaMemcpyDeviceToDevice, st));
+    int begin = 0;
+    for (int lvl = 0; lvl < levels; lvl++) {
+        const int cnt = 1 << lvl, dir = lvl % 3;
+        p2p::dt::route_flag_kernel<<<blocks(n, 256), 256, 0, st>>>(A, n, dir);
+        p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, n, t->tile.p);
+        p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
+        p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, n, t->tile.p, A.G);
+        p2p::dt::route_split_kernel<<<blocks(cnt, 128), 128, 0, st>>>(A, begin, cnt, dir);
+        p2p::dt::route_children_kernel<<<blocks(cnt, 128), 128, 0, st>>>(A, begin, cnt, begin + cnt, dsplit.p, (2 << lvl) - 1, nproc - 1);
+        p2p::dt::slot_kernel<<<blocks(n, 256), 256, 0, st>>>(A, n);
+        p2p::dt::swap_kernel<<<blocks(n, 256), 256, 0, st>>>(A, n);
+        CU(cudaGetLastError());
+        std::swap(A.seg, A.seg_next);
+        begin += cnt;
+    }
+    // the last level's runs are the per-rank groups (left to right = rank order for a power of two)
+    CU(cudaMemcpyAsync(sendcount, A.t_len + begin, (size_t)nproc * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    dsplit.release();
+    return 0;
+}
+
+// copies of / into the resident particle arrays (device pointers owned by the caller: x, y, z doubles, idx int32)
+int p2p_route_export(p2p_ctx* c, void* d_x, void* d_y, void* d_z, void* d_idx) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t) return fail(P2P_ERR_STATE, "nothing resident");
+    const size_t n = (size_t)t->resident;
+    if (n == 0) return 0;
+    void* dst[3] = {d_x, d_y, d_z};
+    for (int k = 0; k < 3; k++) CU(cudaMemcpyAsync(dst[k], t->x[k].p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_idx, t->perm.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+int p2p_route_import(p2p_ctx* c, const void* d_x, const void* d_y, const void* d_z, const void* d_idx, int64_t n) {
+    USE(c);
+    if (n < 0 || n > 0x7fffffffLL || (n && (!d_x || !d_y || !d_z || !d_idx))) return fail(P2P_ERR_ARG, "bad arrays");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    t->valid = false; t->resident = 0;
+    const void* src[3] = {d_x, d_y, d_z};
+    for (int k = 0; k < 3; k++) {
+        CU(t->x[k].reserve((size_t)n + 1, c->stream));
+        if (n) CU(cudaMemcpyAsync(t->x[k].p, src[k], (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(t->perm.reserve((size_t)n + 1, c->stream));
+    if (n) CU(cudaMemcpyAsync(t->perm.p, d_idx, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    t->resident = n; t->perm_is_local = false;
+    return 0;
+}
+
+// build_localtree over the resident particles (after p2p_route_import); perm keeps the global ids
+int p2p_tree_build_resident(p2p_ctx* c, int maxleaf, const double bdl[3], const double bdr[3], int direct_start) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || t->resident < 1) return fail(P2P_ERR_STATE, "no resident particles (p2p_route_import)");
+    if (maxleaf < 1 || maxleaf > P2P_MAX_LEAF || !bdl || !bdr || direct_start < 0 || direct_start > 2) return fail(P2P_ERR_ARG, "bad arguments");
+    if (!c->box_set) return fail(P2P_ERR_STATE, "p2p_set_box must precede the tree build");
+    t->valid = false;
+    CU(cudaEventRecord(t->e0, c->stream));
+    return build_core(c, t, t->resident, maxleaf, bdl, bdr, direct_start);
+}
+
+// ids of the particles in tree order (global ids after a routing, positions in the caller's array otherwise)
+int p2p_download_index(p2p_ctx* c, int64_t* idx) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here || !idx) return fail(P2P_ERR_STATE, "no device-built tree");
+    std::vector<int> p((size_t)t->npart);
+    CU(cudaMemcpyAsync(p.data(), t->perm.p, (size_t)t->npart * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (long long i = 0; i < t->npart; i++) idx[i] = p[(size_t)i];
     return 0;
 }
 
@@ -593,6 +759,7 @@ int p2p_download_acc_original(p2p_ctx* c, double* acc) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "no device-built tree");
+    if (!t->perm_is_local) return fail(P2P_ERR_STATE, "particles were routed between ranks: use p2p_download_acc + p2p_download_index");
     if (!acc) return fail(P2P_ERR_ARG, "null acc");
     const long long n = c->npart;
     CU(c->acc64.reserve((size_t)n * 3, c->stream));

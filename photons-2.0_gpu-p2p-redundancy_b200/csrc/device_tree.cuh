@@ -689,6 +689,64 @@ __global__ void swap_kernel(BuildArrays A, long long npart) {
     A.perm[j] = pa;
 }
 
+// ---- particle routing by the rank kd-tree (prepare_body_inOrderOf_domain, 1_Indexing/src/domains.c:163-296) -----------
+// The same level-synchronous partition with GIVEN split values: the reference's bksort_body_inplace is, for runs of three
+// or more, the standard pairing (k-th big element from the left of [0, ns) <-> k-th small one from the right of [ns, len),
+// ns = number of elements <= split; model-checked in tests/test_device_tree_model.py); runs of one and two keep its
+// special cases (two elements are put in ascending order whatever the split).
+__global__ void route_flag_kernel(BuildArrays A, long long npart, int dir) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npart) return;
+    const int t = A.seg[i];
+    unsigned char f = 0;
+    if (t >= 0 && A.t_len[t] > 2) f = A.x[dir][i] > A.t_split[t];
+    A.flag[i] = f;
+}
+
+// per node: left count; runs of length <= 2 are also put in place here
+__global__ void route_split_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    const long long s = A.t_start[t];
+    const int len = A.t_len[t];
+    const double split = A.t_split[t];
+    double* X = A.x[dir];
+    int np0;
+    if (len == 0) np0 = 0;
+    else if (len == 1) np0 = X[s] > split ? 0 : 1;
+    else if (len == 2) {
+        if (X[s] > X[s + 1]) {
+            for (int d = 0; d < 3; d++) { const double a = A.x[d][s]; A.x[d][s] = A.x[d][s + 1]; A.x[d][s + 1] = a; }
+            const int p = A.perm[s]; A.perm[s] = A.perm[s + 1]; A.perm[s + 1] = p;
+        }
+        np0 = X[s] > split ? 0 : (X[s + 1] <= split ? 2 : 1);
+    } else np0 = len - (int)(A.G[s + len] - A.G[s]);
+    A.t_np0[t] = np0;
+}
+
+// both children of every node become nodes of the next level (possibly empty); their split values come from the rank tree
+__global__ void route_children_kernel(BuildArrays A, int lvl_begin, int lvl_count, int next_begin, const double* __restrict__ dsplit,
+                                      int next_heap_first, int nheap_inner) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= lvl_count) return;
+    const int t = lvl_begin + n;
+    const int start = A.t_start[t], len = A.t_len[t], np0 = A.t_np0[t];
+    for (int sde = 0; sde < 2; sde++) {
+        const int c = next_begin + 2 * n + sde, h = next_heap_first + 2 * n + sde;
+        A.t_start[c] = sde ? start + np0 : start;
+        A.t_len[c] = sde ? len - np0 : np0;
+        A.t_parent[c] = 2 * t + sde;
+        A.t_split[c] = h < nheap_inner ? dsplit[h] : 0.0;
+        A.t_child[2 * t + sde] = c;
+    }
+}
+
+__global__ void iota_offset_kernel(int* __restrict__ perm, long long n, int first) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = first + (int)i;
+}
+
 // bottom-up: subtree leaf / node counts
 __global__ void count_up_kernel(BuildArrays A, int lvl_begin, int lvl_count) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;

@@ -76,6 +76,12 @@ def load_library():
     L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
     L.p2p_download_acc_original.argtypes = [C.c_void_p, _dp]
     L.p2p_tree_set_option.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_route_load.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int64]
+    L.p2p_route_partition.argtypes = [C.c_void_p, C.c_int, _dp, _ip]
+    L.p2p_route_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.p2p_route_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.p2p_tree_build_resident.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+    L.p2p_download_index.argtypes = [C.c_void_p, _lp]
     L.p2p_midfield_enable.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.p2p_midfield_compute.argtypes = [C.c_void_p, _lp]
     L.p2p_midfield_download.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
@@ -342,6 +348,37 @@ class P2PContext:
         self.npart = pos.shape[0]
         self.nleaf = self.tree_info()["nleaf"]
         return acc
+
+    # ---- particle routing on the device (multi-rank)
+    def route_load(self, pos, first_index):
+        pos = _f64(pos)
+        self._chk(self._L.p2p_route_load(self._h, pos.ctypes.data_as(_dp), pos.shape[1] if pos.ndim == 2 else 3, pos.shape[0],
+                                         int(first_index)))
+
+    def route_partition(self, nproc, split):
+        sp = np.ascontiguousarray(split, np.float64)
+        send = np.zeros(nproc, np.int32)
+        self._chk(self._L.p2p_route_partition(self._h, int(nproc), sp.ctypes.data_as(_dp), send.ctypes.data_as(_ip)))
+        return send
+
+    def route_export(self, d_x, d_y, d_z, d_idx):
+        self._chk(self._L.p2p_route_export(self._h, d_x, d_y, d_z, d_idx))
+
+    def route_import(self, d_x, d_y, d_z, d_idx, n):
+        self._chk(self._L.p2p_route_import(self._h, d_x, d_y, d_z, d_idx, int(n)))
+        self._resident = int(n)
+
+    def tree_build_resident(self, maxleaf, bdl, bdr, direct_start=0):
+        bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)
+        self._chk(self._L.p2p_tree_build_resident(self._h, int(maxleaf), bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start)))
+        info = self.tree_info()
+        self.nleaf = info["nleaf"]
+        self.npart = self._resident
+
+    def download_index(self):
+        idx = np.zeros(self.npart, np.int64)
+        self._chk(self._L.p2p_download_index(self._h, idx.ctypes.data_as(_lp)))
+        return idx
 
     # ---- mid-field (M2L lists from the walk; P2M / M2M / M2L / L2L / L2P kernels)
     def midfield_enable(self, on=True, literal_d6=False):

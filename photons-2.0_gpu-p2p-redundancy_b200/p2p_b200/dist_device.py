@@ -49,17 +49,20 @@ def _all_to_all_v(send, in_split, out_split, group):
     return out.to(send.device)
 
 
+def _stream_of(ctx, dev):
+    if not ctx.stream_ptr:                      # torch ops, collectives and the library's kernels share one stream
+        ctx._torch_stream = torch.cuda.Stream(device=dev)
+        ctx.set_stream(ctx._torch_stream.cuda_stream)
+    return torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+
+
 def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl, bdr, direct_start, theta=0.4, periodic=True,
                     truncated=True, group=None, acc_out=None, timings=None):
     """One rank's part of the step.  local_pos: this rank's particles (host, float64, caller's order; pinned for full
     PCIe rate); bdl/bdr/direct_start: its domain box and first split direction (host.domain_setup).
     Returns (acc in the order of local_pos, ntask, npairs)."""
-    P, me = dist.get_world_size(group), dist.get_rank(group)
     dev = torch.device("cuda", ctx.device)
-    if not ctx.stream_ptr:                      # torch ops, collectives and the library's kernels share one stream
-        ctx._torch_stream = torch.cuda.Stream(device=dev)
-        ctx.set_stream(ctx._torch_stream.cuda_stream)
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    stream = _stream_of(ctx, dev)
     t0 = time.perf_counter()
     rs, rcut, eps = host.derived_params(box, nside, npart_total)
     ctx.set_physics(mass, eps, rs if truncated else 0.0)
@@ -67,6 +70,63 @@ def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl,
     bdl, bdr = np.asarray(bdl, np.float64), np.asarray(bdr, np.float64)
     with torch.cuda.stream(stream):
         ctx.tree_build(local_pos, maxleaf, bdl, bdr, direct_start)
+        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings)
+        acc = ctx.download_acc_original(acc_out)
+    if timings is not None:
+        timings["total_s"] = time.perf_counter() - t0
+    return acc, ntask, npairs
+
+
+def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside, mass, split, theta=0.4, periodic=True, truncated=True,
+                   group=None, timings=None):
+    """The same step starting one stage earlier: `slab_pos` is the slab of the global particle array this rank happens to
+    hold (global ids first_index ...), `split` the rank kd-tree (host.domain_setup / host.domain_relax).  The slab is
+    partitioned on the device exactly as the reference's prepare_body_inOrderOf_domain does, the groups are exchanged as
+    device buffers (all-to-all-v), and the tree is built from what arrived (1_Indexing/src/domains.c:163-377).
+    Returns (acc in TREE order, global ids of the tree positions, ntask, npairs)."""
+    P, me = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    stream = _stream_of(ctx, dev)
+    t0 = time.perf_counter()
+    rs, rcut, eps = host.derived_params(box, nside, npart_total)
+    ctx.set_physics(mass, eps, rs if truncated else 0.0)
+    ctx.set_box([0.0, 0.0, 0.0], box)
+    center, width, direct = host.domain_boxes(P, box, split)
+    dom = host.domain_of_rank(P, me)
+    bdl, bdr = center[dom] - 0.5 * width[dom], center[dom] + 0.5 * width[dom]
+    with torch.cuda.stream(stream):
+        n = slab_pos.shape[0]
+        ctx.route_load(slab_pos, first_index)
+        send = ctx.route_partition(P, split)
+        bufs = [torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(3)] + [torch.empty(max(n, 1), dtype=torch.int32, device=dev)]
+        ctx.route_export(*[b.data_ptr() for b in bufs])
+        s_t = torch.from_numpy(send.astype(np.int64))
+        r_t = torch.empty(P, dtype=torch.int64)
+        if _nccl(group):
+            rd = torch.empty(P, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(rd, s_t.to(dev), group=group)
+            r_t = rd.cpu()
+        else:
+            dist.all_to_all_single(r_t, s_t, group=group)
+        recv = [int(v) for v in r_t]
+        got = [_all_to_all_v(b[:n], [int(v) for v in send], recv, group) for b in bufs]
+        nloc = int(sum(recv))
+        ctx.route_import(*[g.data_ptr() for g in got], nloc)
+        t_route = time.perf_counter() - t0
+        ctx.tree_build_resident(maxleaf, bdl, bdr, int(direct[dom]))
+        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings)
+        acc = ctx.download_acc()
+        idx = ctx.download_index()
+    if timings is not None:
+        timings["route_s"] = t_route
+        timings["total_s"] = time.perf_counter() - t0
+    return acc, idx, ntask, npairs
+
+
+def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings):
+    """after the tree build: topology all-gather, walk against every rank's tree, halo fetch, packing, forces"""
+    P, me = dist.get_world_size(group), dist.get_rank(group)
+    if True:
         info = ctx.tree_info()
         nl, nn = info["nleaf"], info["nnode"]
         t1 = time.perf_counter()
@@ -129,16 +189,15 @@ def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl,
         ctx.set_ghosts_device(ghosts.data_ptr() if nbody else None, nbody, start.data_ptr() if G else None,
                               count.data_ptr() if G else None, G)
         t4 = time.perf_counter()
-        # ---- pack, forces, download
+        # ---- pack, forces
         ctx.build_csr()
         ctx.compute()
-        acc = ctx.download_acc_original(acc_out)
         ntask, npairs = ctx.counts()
     t5 = time.perf_counter()
     if timings is not None:
         ms_force, ms_csr = ctx.last_timings()
-        timings.update(total_s=t5 - t0, build_s=t1 - t0, topology_s=t2 - t1, walk_s=t3 - t2, halo_s=t4 - t3, force_s=t5 - t4,
+        timings.update(build_s=t1 - t0, topology_s=t2 - t1, walk_s=t3 - t2, halo_s=t4 - t3, force_s=t5 - t4,
                        build_ms=info["ms_build"], walk_ms=ctx.tree_info()["ms_walk"], csr_ms=ms_csr, force_ms=ms_force,
                        ghost_particles=nbody, ghost_leaves_referenced=int((count > 0).sum().item()) if G else 0,
                        topology_bytes=int(box_all.numel() * 8 + son_all.numel() * 4))
-    return acc, ntask, npairs
+    return ntask, npairs

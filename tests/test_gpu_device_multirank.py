@@ -80,3 +80,68 @@ def test_device_multirank_matches_oracle(demo_pos, world):
     e1 = (d / np.maximum(na, na.mean())).max()
     e2 = (d / np.maximum(np.linalg.norm(absr, axis=1), 1e-300)).max()
     assert e1 < 1e-5 and e2 < 1e-5, (e1, e2)
+
+
+def _route_worker(rank, world, port, pos, q):
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import p2p_b200
+    from p2p_b200 import dist as pdist
+    from p2p_b200 import dist_device, host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    n = pos.shape[0]
+    # the host routing (bit-exact with the reference's domain_decomposition) and the host tree built from it
+    lp, lidx, tcenter, twidth, direct, dom = pdist.decompose(pos, DEMO_BOX, None)
+    c, w = tcenter[dom], twidth[dom]
+    T = host.LocalTree(lp, 16, c - 0.5 * w, c + 0.5 * w, int(direct[dom]))
+    # the device routing from the same initial slab
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    split = host.domain_setup(world, DEMO_BOX)[0]
+    ctx = p2p_b200.P2PContext(0)
+    acc, idx, ntask, npairs = dist_device.route_and_step(ctx, pos[lo:hi].copy(), lo, n, DEMO_BOX, 16, DEMO_NSIDE, DEMO_MASS, split, THETA)
+    D = ctx.tree_download()
+    same_tree = bool(np.array_equal(D["pos"], T.pos) and np.array_equal(idx, lidx[T.perm]) and
+                     np.array_equal(D["leaf_ipart"], T.leaf_ipart) and np.array_equal(D["node_split"], T.node_split))
+    q.put((rank, idx, acc, ntask, npairs, same_tree))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_device_routing_then_step(demo_pos, world):
+    """slab -> device partition by the rank kd-tree -> exchange -> resident tree build -> lists, halo, forces: the
+    routed particle ORDER must be the reference's (the tree built from it is compared bit for bit with the host
+    path's, which is pinned against the reference's domain_decomposition), and the forces must match the oracle"""
+    import flow
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_route_worker, args=(r, world, port, demo_pos, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        item = q.get(timeout=600)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    acc = np.zeros((len(demo_pos), 3))
+    seen = 0
+    for r in range(world):
+        idx, a, ntask, npairs, same_tree = got[r]
+        assert same_tree
+        acc[idx] = a
+        seen += len(idx)
+    assert seen == len(demo_pos)
+    want, ntask_all, npairs_all = flow.reference_forces(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, DEMO_MASS, world, True)
+    assert sum(got[r][2] for r in range(world)) == ntask_all and sum(got[r][3] for r in range(world)) == npairs_all
+    d = np.linalg.norm(acc - want, axis=1)
+    na = np.linalg.norm(want, axis=1)
+    assert (d / np.maximum(na, na.mean())).max() < 1e-5

@@ -1,6 +1,8 @@
 """Multi-GPU device-resident short-range step (p2p_b200/dist_device.py) under torchrun, without the host-list legs of
 bench.py: generate, route, then time the step (max over ranks, wall clock between barriers).
 usage: torchrun --nproc-per-node N tools/dist_device_step.py [nside] [maxleaf] [reps] [--clustered] [--relax=K]
+--route: time the step from the slab of the global array each rank holds (device routing + exchange + resident build)
+instead of from already routed particles.
 --relax=K: K further steps, each after the reference's work-weighted split relaxation (p2p_domain_relax, fed with the
 per-rank task counts as 1_Indexing/src/photoNs.c:295-306 does) and a re-routing of the particles."""
 import json
@@ -57,11 +59,24 @@ for r in range(reps + relax):
     res.append((dt, tm, tot.tolist(), mx.tolist()))
     history.append({"step_s": dt, "imbalance_pairs": 1.0 - tot.tolist()[1] / (world * mx.tolist()[1]),
                     "imbalance_tasks": 1.0 - tot.tolist()[0] / (world * mx.tolist()[0])})
+routed = None
+if "--route" in sys.argv:
+    n = pos.shape[0]
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    slab = torch.from_numpy(np.ascontiguousarray(pos[lo:hi])).pin_memory()
+    for r in range(3):
+        tm2 = {}
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, nt2, np2 = dist_device.route_and_step(ctx, slab.numpy(), lo, npart_total, box, maxleaf, nside, 1.0, split, 0.4, timings=tm2)
+        dist.barrier(); torch.cuda.synchronize()
+        routed = (time.perf_counter() - t0, tm2)
 if rank == 0:
     dt, tm, tot, mx = res[-1]
     print(json.dumps({"n_gpus": world, "nside": nside, "maxleaf": maxleaf, "step_s": dt, "all_reps_s": [r[0] for r in res], "pairs": int(tot[1]),
                       "tasks": int(tot[0]), "pair_per_s_whole_step": tot[1] / dt, "imbalance": 1.0 - tot[1] / (world * mx[1]),
                       "rank0_breakdown": tm,
-                      "relaxation_history": history[reps - 1:] if relax else None}), flush=True)
+                      "relaxation_history": history[reps - 1:] if relax else None,
+                      "routed_step_s": routed[0] if routed else None, "routed_rank0_breakdown": routed[1] if routed else None}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
