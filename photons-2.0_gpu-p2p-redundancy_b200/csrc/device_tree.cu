@@ -464,10 +464,13 @@ int p2p_download_index(p2p_ctx* c, int64_t* idx) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->valid || !t->built_here || !idx) return fail(P2P_ERR_STATE, "no device-built tree");
-    std::vector<int> p((size_t)t->npart);
-    CU(cudaMemcpyAsync(p.data(), t->perm.p, (size_t)t->npart * 4, cudaMemcpyDeviceToHost, c->stream));
+    // widened on the device and copied straight into the caller's buffer (full PCIe rate when that is pinned)
+    CU(c->acc64.reserve((size_t)t->npart * 3, c->stream));
+    long long* tmp = reinterpret_cast<long long*>(c->acc64.p);
+    p2p::dt::widen_index_kernel<<<blocks(t->npart, 256), 256, 0, c->stream>>>(t->perm.p, t->npart, tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(idx, tmp, (size_t)t->npart * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    for (long long i = 0; i < t->npart; i++) idx[i] = p[(size_t)i];
     return 0;
 }
 

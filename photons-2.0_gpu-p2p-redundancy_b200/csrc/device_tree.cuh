@@ -742,6 +742,11 @@ __global__ void route_children_kernel(BuildArrays A, int lvl_begin, int lvl_coun
     }
 }
 
+__global__ void widen_index_kernel(const int* __restrict__ perm, long long n, long long* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = perm[i];
+}
+
 __global__ void iota_offset_kernel(int* __restrict__ perm, long long n, int first) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) perm[i] = first + (int)i;

@@ -375,8 +375,9 @@ class P2PContext:
         self.nleaf = info["nleaf"]
         self.npart = self._resident
 
-    def download_index(self):
-        idx = np.zeros(self.npart, np.int64)
+    def download_index(self, out=None):
+        idx = np.zeros(self.npart, np.int64) if out is None else out
+        assert idx.dtype == np.int64 and idx.flags.c_contiguous and idx.shape == (self.npart,)
         self._chk(self._L.p2p_download_index(self._h, idx.ctypes.data_as(_lp)))
         return idx
 

@@ -78,11 +78,12 @@ def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl,
 
 
 def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside, mass, split, theta=0.4, periodic=True, truncated=True,
-                   group=None, timings=None):
+                   group=None, timings=None, pinned_out=None):
     """The same step starting one stage earlier: `slab_pos` is the slab of the global particle array this rank happens to
     hold (global ids first_index ...), `split` the rank kd-tree (host.domain_setup / host.domain_relax).  The slab is
     partitioned on the device exactly as the reference's prepare_body_inOrderOf_domain does, the groups are exchanged as
     device buffers (all-to-all-v), and the tree is built from what arrived (1_Indexing/src/domains.c:163-377).
+    pinned_out: optional dict reused between steps for pinned result buffers (grown on demand).
     Returns (acc in TREE order, global ids of the tree positions, ntask, npairs)."""
     P, me = dist.get_world_size(group), dist.get_rank(group)
     dev = torch.device("cuda", ctx.device)
@@ -115,8 +116,16 @@ def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside,
         t_route = time.perf_counter() - t0
         ctx.tree_build_resident(maxleaf, bdl, bdr, int(direct[dom]))
         ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings)
-        acc = ctx.download_acc()
-        idx = ctx.download_index()
+        if pinned_out is not None:
+            if pinned_out.get("n", 0) < nloc:
+                pinned_out["acc"] = torch.empty((int(nloc * 1.1) + 16, 3), dtype=torch.float64).pin_memory()
+                pinned_out["idx"] = torch.empty(int(nloc * 1.1) + 16, dtype=torch.int64).pin_memory()
+                pinned_out["n"] = int(nloc * 1.1) + 16
+            acc = ctx.download_acc(pinned_out["acc"].numpy()[:nloc])
+            idx = ctx.download_index(pinned_out["idx"].numpy()[:nloc])
+        else:
+            acc = ctx.download_acc()
+            idx = ctx.download_index()
     if timings is not None:
         timings["route_s"] = t_route
         timings["total_s"] = time.perf_counter() - t0

@@ -64,11 +64,12 @@ if "--route" in sys.argv:
     n = pos.shape[0]
     lo, hi = n * rank // world, n * (rank + 1) // world
     slab = torch.from_numpy(np.ascontiguousarray(pos[lo:hi])).pin_memory()
+    pinned = {}
     for r in range(3):
         tm2 = {}
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        _, _, nt2, np2 = dist_device.route_and_step(ctx, slab.numpy(), lo, npart_total, box, maxleaf, nside, 1.0, split, 0.4, timings=tm2)
+        _, _, nt2, np2 = dist_device.route_and_step(ctx, slab.numpy(), lo, npart_total, box, maxleaf, nside, 1.0, split, 0.4, timings=tm2, pinned_out=pinned)
         dist.barrier(); torch.cuda.synchronize()
         routed = (time.perf_counter() - t0, tm2)
 if rank == 0:
