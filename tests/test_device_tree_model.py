@@ -185,3 +185,66 @@ def test_transducer_is_parallel_for_long_runs():
     got, rounds = model_seq_sum(x)
     assert dbits(got) == dbits(seq_sum(x))
     assert rounds < 100000 / 256 + 80
+
+
+def ref_route_partition(x, split):
+    """bksort_body_inplace as restated in oracle/p2p_oracle.c:split_at (1_Indexing/src/domains.c:163-270), runs >= 3"""
+    x = list(x)
+    idx = list(range(len(x)))
+    n = len(x)
+    top = 0
+    while top < n and x[top] <= split:
+        top += 1
+    but = n - 1
+    while but >= 0 and x[but] > split:
+        but -= 1
+    if top == n:
+        return idx, n
+    if but == -1:
+        return idx, 0
+    i = top
+    while i <= but:
+        if x[i] > split:
+            x[i], x[but] = x[but], x[i]
+            idx[i], idx[but] = idx[but], idx[i]
+            while x[but] > split:
+                but -= 1
+        i += 1
+    return idx, (but + 1 if i == but else i)
+
+
+def model_route_partition(x, split):
+    """closed form used by route_flag_kernel / route_split_kernel / slot_kernel / swap_kernel (csrc/device_tree.cuh)"""
+    x = np.asarray(x)
+    n = len(x)
+    big = x > split
+    G = np.concatenate([[0], np.cumsum(big)])
+    nbig = int(G[n])
+    np0 = n - nbig
+    slot = {}
+    for i in range(n):
+        if i >= np0 and not big[i]:
+            slot[(n - nbig) - (i - int(G[i])) - 1] = i
+    idx = list(range(n))
+    for i in range(np0):
+        if big[i]:
+            j = slot[int(G[i])]
+            idx[i], idx[j] = idx[j], idx[i]
+    return idx, np0
+
+
+def test_routing_partition_closed_form():
+    rng = np.random.default_rng(3)
+    for trial in range(6000):
+        n = int(rng.integers(3, 60))
+        kind = trial % 4
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = rng.integers(0, 4, n).astype(np.float64)
+        elif kind == 2:
+            x = np.full(n, 0.5)
+        else:
+            x = np.sort(rng.random(n))[::-1].copy()
+        split = float(rng.choice([0.5, rng.random(), -1.0, 2.0, 1.0, 0.0]))
+        assert ref_route_partition(x, split) == model_route_partition(x, split)

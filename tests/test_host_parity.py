@@ -112,3 +112,18 @@ def test_step_lists_equal_oracle_flow(demo_pos):
             b = rem["image"]["body"][rem["image"]["son"][s, 0]: rem["image"]["son"][s, 0] + rem["image"]["npart"][s]]
             assert np.array_equal(a, b)
         o += n
+
+
+def test_domain_boxes_of_given_splits():
+    """center_toptree for arbitrary splits: reproduces domain_setup's boxes for its own splits, and follows relaxed splits"""
+    from p2p_b200 import host
+    for P in (1, 2, 3, 4, 8):
+        split, center, width, direct = host.domain_setup(P, 100.0)
+        c2, w2, d2 = host.domain_boxes(P, 100.0, split)
+        assert np.array_equal(center, c2) and np.array_equal(width, w2) and np.array_equal(direct, d2)
+    split, center, width, direct = host.domain_setup(4, 100.0)
+    relaxed = host.domain_relax(4, 100.0, split, [4.0, 1.0, 1.0, 1.0])
+    c3, w3, _ = host.domain_boxes(4, 100.0, relaxed)
+    assert relaxed[0] != split[0] and c3[1][0] == 0.5 * relaxed[0] and w3[1][0] == relaxed[0]
+    # leaf boxes tile the volume
+    assert abs(sum(np.prod(w3[n]) for n in range(3, 7)) - 100.0 ** 3) < 1e-6
