@@ -179,7 +179,8 @@ int p2p_download_acc_original(p2p_ctx* ctx, double* acc);
 /* The whole short-range P2P step of one rank in one call (replaces fmm_prepare + fmm_task + fmm_ext for the P2P part,
  * 1_Indexing/src/photoNs.c:97-123): host positions in the caller's order in, host accelerations in the same order out;
  * tree build, walk (26 periodic images when period > 0), packing and forces on the device.  Fails with P2P_ERR_ARG
- * when r_cut + 2 x (largest leaf width) reaches period / 2 (minimal-image sources would be ambiguous). */
+ * when a listed leaf pair spans period / 2 or more along an axis (minimal-image sources would be ambiguous; the walk
+ * checks every pair it lists). */
 int p2p_step_device(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
                     const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc);
 /* ---- multi-rank device path: one tree per rank, every rank walks its own tree against all of them -----------
@@ -189,13 +190,14 @@ int p2p_step_device(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npa
  * and only the particles of the leaves the lists actually reference travel afterwards (one all-to-all-v).
  * All pointers below are DEVICE pointers owned by the caller (e.g. torch tensors used with torch.distributed). */
 /* box [(nleaf + nnode)][6] doubles {centre, width}, son [nnode][2] ints (leaf l -> l, node n -> nleaf + n),
- * leaf [nleaf] {first particle, count} */
-int p2p_tree_export(p2p_ctx* ctx, void* d_box, void* d_son, void* d_leaf);
+ * leaf [nleaf] {first particle, count}, bounds [nleaf][6] doubles = tight lo[3], hi[3] of each leaf's particles (for the
+ * minimal-image check of a periodic walk); NULL skips */
+int p2p_tree_export(p2p_ctx* ctx, void* d_box, void* d_son, void* d_leaf, void* d_bounds);
 /* peers' exports concatenated in rank order; sources of rank `me` are listed under local leaf ids, those of rank p
  * under nleaf_local + (leaves of the ranks before p, skipping me) + leaf */
 int p2p_tree_walk_peers(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
                         int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
-                        const void* d_son_all);
+                        const void* d_son_all, const void* d_bounds_all /* may be NULL: no minimal-image check */);
 /* marks[g] = 1 (uint8) for every ghost leaf g (0-based behind the local leaves) that the task list references */
 int p2p_ghost_marks(p2p_ctx* ctx, void* d_marks);
 /* out[offset[l] ...) = fixed-point particles (int4) of every LOCAL leaf l with marks[l] != 0; offset: int64 per leaf */
@@ -220,6 +222,20 @@ int p2p_route_import(p2p_ctx* ctx, const void* d_x, const void* d_y, const void*
  * p2p_download_index (the global id of every tree position) */
 int p2p_tree_build_resident(p2p_ctx* ctx, int maxleaf, const double bdl[3], const double bdr[3], int direct_start);
 int p2p_download_index(p2p_ctx* ctx, int64_t* idx);
+
+/* ---- device-resident stepping (the integrator part): positions, velocities and ids stay in
+ * HBM between steps -- no per-step upload of positions or download of accelerations.  The kick / drift arithmetic is the
+ * reference's (1_Indexing/src/photoNs.c:161-208: vel += acc dkh, pos += vel dd, wrap into [0, BOXSIZE) by its while
+ * loops); like the reference (fmm_construct after the drift) every step's tree is built from the particle order the
+ * previous step left.  The PM term (acc_pm) and the scale-factor integrals dk, dd belong to the caller. */
+int p2p_resident_load(p2p_ctx* ctx, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n);
+int p2p_resident_forces(p2p_ctx* ctx, int maxleaf, const double bdl[3], const double bdr[3], int direct_start, double theta, double rcut,
+                        double period);
+int p2p_resident_kick(p2p_ctx* ctx, double dkh);
+int p2p_resident_drift(p2p_ctx* ctx, double dd, double period);
+/* current positions / velocities (packed rows of 3 doubles) and ids (particle i of p2p_resident_load has id i), in the
+ * resident (tree) order; NULL skips */
+int p2p_resident_download(p2p_ctx* ctx, double* pos, double* vel, int64_t* id);
 
 /* ---- mid-field on the device: P2M / M2M / M2L / L2L / L2P --------------------------
  * The other half of the short-range FMM force (1_Indexing/src/operator.c; fmm_prepare, task_compute_m2l and the tail

@@ -35,6 +35,7 @@ struct p2p_dtree {
     // mid-field (M2L lists from the walk, multipoles, local expansions)
     bool m2l_on = false, literal_d6 = false, mid_valid = false;
     DevBuf<int> mt, ms, mq;
+    DevBuf<double> tb;                // tight particle bounds of the local leaves (minimal-image check of the walk)
     long long nm2l = 0;
     DevBuf<double> Mall, Lall, acc_mid;
     std::vector<int> lvl_begin, lvl_count;
@@ -50,6 +51,9 @@ struct p2p_dtree {
     unsigned int* d_dup = nullptr;
     unsigned long long* d_maxw = nullptr;
     double max_leaf_width = 0.0;
+    DevBuf<double> v[3], vtmp[3];     // device-resident stepping: velocities (tree order) and carry scratch
+    DevBuf<int> gid, gidtmp;          // ... and the particles' ids
+    bool stepping = false;
     long long resident = 0;      // particles currently in x[] / perm[]
     bool perm_is_local = true;   // perm[] indexes the array given to p2p_tree_build (false: global ids after a routing)
     long long walk_tasks = 0, walk_items = 0;
@@ -69,7 +73,10 @@ void p2p_dtree_release(p2p_dtree* t) {
     t->t_start.release(); t->t_len.release(); t->t_parent.release(); t->t_np0.release(); t->t_child.release(); t->t_nleaf.release();
     t->t_nnode.release(); t->t_id.release(); t->t_leafbase.release(); t->child_cnt.release(); t->t_split.release(); t->t_lo.release();
     t->t_hi.release();
+    t->tb.release();
     t->mt.release(); t->ms.release(); t->mq.release(); t->Mall.release(); t->Lall.release(); t->acc_mid.release();
+    for (int k = 0; k < 3; k++) { t->v[k].release(); t->vtmp[k].release(); }
+    t->gid.release(); t->gidtmp.release();
     t->choff.release(); t->cmeta.release(); t->capprox.release(); t->capprox_end.release(); t->cinc.release();
     t->frontier[0].release(); t->frontier[1].release();
     if (t->d_scalar) cudaFree(t->d_scalar);
@@ -459,6 +466,112 @@ int p2p_tree_build_resident(p2p_ctx* c, int maxleaf, const double bdl[3], const 
     return build_core(c, t, t->resident, maxleaf, bdl, bdr, direct_start);
 }
 
+// ---- device-resident stepping: positions, velocities and ids live in HBM between steps ---------------
+// pos / vel: host rows of 3 doubles (vel may be NULL = at rest); particle i gets id i
+int p2p_resident_load(p2p_ctx* c, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n) {
+    USE(c);
+    if (n < 1 || n > 0x7fffffffLL || !pos || pos_stride < 3 || (vel && vel_stride < 3)) return fail(P2P_ERR_ARG, "bad arrays");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    cudaStream_t st = c->stream;
+    t->valid = false; t->resident = 0; t->stepping = false;
+    CU(c->stage.reserve((size_t)n * 24, st));
+    for (int k = 0; k < 3; k++) { CU(t->x[k].reserve((size_t)n, st)); CU(t->v[k].reserve((size_t)n, st)); CU(t->vtmp[k].reserve((size_t)n, st)); }
+    CU(t->perm.reserve((size_t)n, st)); CU(t->seg.reserve((size_t)n, st)); CU(t->gid.reserve((size_t)n, st)); CU(t->gidtmp.reserve((size_t)n, st));
+    if (vel) {
+        CU(cudaMemcpy2DAsync(c->stage.p, 24, vel, (size_t)vel_stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, st));
+        p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->v[0].p, t->v[1].p,
+                                                                     t->v[2].p, t->perm.p, t->seg.p);
+    } else {
+        for (int k = 0; k < 3; k++) CU(cudaMemsetAsync(t->v[k].p, 0, (size_t)n * 8, st));
+    }
+    CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)pos_stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, st));
+    p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->x[0].p, t->x[1].p, t->x[2].p,
+                                                                 t->perm.p, t->seg.p);
+    p2p::dt::iota_kernel<<<blocks(n, 256), 256, 0, st>>>(t->gid.p, n);
+    CU(cudaGetLastError());
+    t->resident = n; t->perm_is_local = false; t->stepping = true;
+    return 0;
+}
+
+// short-range forces of the resident particles: tree build from their current order (the reference too rebuilds from the
+// order the previous step left, fmm_construct after the drift), velocities and ids carried along, walk, packing, forces
+int p2p_resident_forces(p2p_ctx* c, int maxleaf, const double bdl[3], const double bdr[3], int direct_start, double theta, double rcut,
+                        double period) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping || t->resident < 1) return fail(P2P_ERR_STATE, "p2p_resident_load first");
+    if (maxleaf < 1 || maxleaf > P2P_MAX_LEAF || !bdl || !bdr || direct_start < 0 || direct_start > 2) return fail(P2P_ERR_ARG, "bad arguments");
+    if (!c->box_set) return fail(P2P_ERR_STATE, "p2p_set_box must precede the tree build");
+    cudaStream_t st = c->stream;
+    const long long n = t->resident;
+    t->valid = false;
+    CU(cudaEventRecord(t->e0, st));
+    p2p::dt::iota_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n);
+    int r = build_core(c, t, n, maxleaf, bdl, bdr, direct_start);
+    if (r) return r;
+    p2p::dt::carry_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n, t->v[0].p, t->v[1].p, t->v[2].p, t->gid.p, t->vtmp[0].p, t->vtmp[1].p,
+                                                          t->vtmp[2].p, t->gidtmp.p);
+    CU(cudaGetLastError());
+    for (int k = 0; k < 3; k++) { std::swap(t->v[k].p, t->vtmp[k].p); std::swap(t->v[k].cap, t->vtmp[k].cap); }
+    std::swap(t->gid.p, t->gidtmp.p); std::swap(t->gid.cap, t->gidtmp.cap);
+    if ((r = p2p_clear_tasks(c))) return r;
+    double tc[3], tw[3];
+    for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }
+    if ((r = p2p_tree_walk(c, theta, rcut, period, tc, tw))) return r;
+    if ((r = p2p_build_csr(c))) return r;
+    return p2p_compute(c);
+}
+
+// vel += acc * dkh for the resident particles (acc of the last p2p_resident_forces)
+int p2p_resident_kick(p2p_ctx* c, double dkh) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping || !t->valid) return fail(P2P_ERR_STATE, "no forces computed for the resident particles");
+    p2p::dt::kick_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(c->acc.p, t->resident, dkh, t->v[0].p, t->v[1].p, t->v[2].p);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// pos += vel * dd, wrapped into [0, period) (period <= 0: no wrap); the tree is stale afterwards
+int p2p_resident_drift(p2p_ctx* c, double dd, double period) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping || t->resident < 1) return fail(P2P_ERR_STATE, "p2p_resident_load first");
+    p2p::dt::drift_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(t->resident, dd, period, t->v[0].p, t->v[1].p, t->v[2].p, t->x[0].p,
+                                                                           t->x[1].p, t->x[2].p);
+    CU(cudaGetLastError());
+    t->valid = false;
+    return 0;
+}
+
+// current positions / velocities (packed rows of 3 doubles) and ids, in the resident order; NULL skips
+int p2p_resident_download(p2p_ctx* c, double* pos, double* vel, int64_t* id) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping || t->resident < 1) return fail(P2P_ERR_STATE, "p2p_resident_load first");
+    const long long n = t->resident;
+    cudaStream_t st = c->stream;
+    CU(c->acc64.reserve((size_t)n * 3, st));
+    if (pos) {
+        p2p::dt::aos_from_soa_kernel<<<blocks(n, 256), 256, 0, st>>>(t->x[0].p, t->x[1].p, t->x[2].p, n, c->acc64.p);
+        CU(cudaMemcpyAsync(pos, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    }
+    if (vel) {
+        p2p::dt::aos_from_soa_kernel<<<blocks(n, 256), 256, 0, st>>>(t->v[0].p, t->v[1].p, t->v[2].p, n, c->acc64.p);
+        CU(cudaMemcpyAsync(vel, c->acc64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    }
+    if (id) {
+        long long* tmp = reinterpret_cast<long long*>(c->acc64.p);
+        p2p::dt::widen_index_kernel<<<blocks(n, 256), 256, 0, st>>>(t->gid.p, n, tmp);
+        CU(cudaMemcpyAsync(id, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ids of the particles in tree order (global ids after a routing, positions in the caller's array otherwise)
 int p2p_download_index(p2p_ctx* c, int64_t* idx) {
     USE(c);
@@ -560,7 +673,7 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
     CU(cudaEventRecord(t->e0, st));
     CU(cudaMemcpyAsync(t->frontier[0].p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(t->d_wcount, 0, 4 * sizeof(ull), st));
-    ull n_in = init.size(), ntask = 0, nm2l = 0, items = 0;
+    ull n_in = init.size(), ntask = 0, nm2l = 0, nviol = 0, items = 0;
     int cur = 0, levels = 0;
     while (n_in) {
         if (++levels > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
@@ -573,10 +686,10 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
             p2p::dt::walk_level_kernel<<<grid, 256, 0, st>>>(t->frontier[cur].p, n_in, t->frontier[cur ^ 1].p, cap_out, t->d_wcount,
                                                              c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, P);
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 3 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 4 * sizeof(ull), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             const ull n_out = t->h_wcount[0], nt = t->h_wcount[1], nm = t->h_wcount[2];
-            if (n_out <= cap_out && nt <= cap_task && nm <= P.cap_m2l) { items += n_in; n_in = n_out; ntask = nt; nm2l = nm; break; }
+            if (n_out <= cap_out && nt <= cap_task && nm <= P.cap_m2l) { items += n_in; n_in = n_out; ntask = nt; nm2l = nm; nviol = t->h_wcount[3]; break; }
             if (nm > P.cap_m2l) {
                 const size_t want = (size_t)(nm + nm / 2);
                 CU(t->mt.reserve(want, st, (size_t)nm2l)); CU(t->ms.reserve(want, st, (size_t)nm2l)); CU(t->mq.reserve(want, st, (size_t)nm2l));
@@ -588,7 +701,7 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
                 CU(c->tt.reserve(want, st, (size_t)(c->ntask + ntask)));
                 CU(c->ts.reserve(want, st, (size_t)(c->ntask + ntask)));
             }
-            const ull reset[3] = {0, ntask, nm2l};
+            const ull reset[4] = {0, ntask, nm2l, nviol};
             CU(cudaMemcpyAsync(t->d_wcount, reset, sizeof reset, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
         }
@@ -602,6 +715,20 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
     c->csr_valid = false;
     t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
     t->nm2l = (long long)nm2l;
+    if (nviol)
+        return fail(P2P_ERR_ARG, "%llu listed leaf pair(s) span half the period or more: the periodic box is too small for minimal-image "
+                    "sources (needs roughly box > 2 (r_cut + 2 leaf widths))", nviol);
+    return 0;
+}
+
+// tight bounds of the local leaves' particles (for the minimal-image check of a periodic walk)
+int leaf_bounds(p2p_ctx* c, p2p_dtree* t) {
+    CU(t->tb.reserve(6 * (size_t)std::max(c->nleaf, 1), c->stream));
+    if (c->nleaf) {
+        p2p::dt::leaf_bounds_kernel<<<blocks(c->nleaf, 128), 128, 0, c->stream>>>(c->leaf.p, c->nleaf, c->part.p, c->origin[0], c->origin[1],
+                                                                               c->origin[2], c->extent / 4294967296.0, t->tb.p);
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -636,6 +763,10 @@ int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const do
     P.box = t->box.p; P.son = t->son.p; P.nleaf = nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
     for (int k = 0; k < 3; k++) { P.tc[k] = tcenter ? tcenter[k] : 0.0; P.tw[k] = twidth ? twidth[k] : 0.0; }
     P.sbox = t->box.p; P.sson = t->son.p; P.me = 0; P.npeer = 1; P.snleaf[0] = nleaf;
+    if (period > 0.0) {
+        if ((r = leaf_bounds(c, t))) return r;
+        P.tb = t->tb.p; P.stb = t->tb.p;
+    }
     std::vector<ull> init;
     const int root = nleaf;
     init.push_back(p2p::dt::item(root, root, 0, 0));
@@ -647,7 +778,7 @@ int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const do
 // ---- multi-rank: one tree per rank, every rank walks its tree against all of them --------------------------------
 // copies of the device tree's walk arrays into caller-owned DEVICE memory (e.g. torch tensors that an all-gather
 // will send): box [(nleaf + nnode)][6] doubles, son [nnode][2] ints (unified ids), leaf [nleaf] {first particle, count}
-int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf) {
+int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf, void* d_bounds) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->valid) return fail(P2P_ERR_STATE, "no device tree");
@@ -655,6 +786,11 @@ int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf) {
     if (d_box) CU(cudaMemcpyAsync(d_box, t->box.p, nu * 48, cudaMemcpyDeviceToDevice, c->stream));
     if (d_son) CU(cudaMemcpyAsync(d_son, t->son.p, (size_t)t->nnode * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (d_leaf && t->nleaf) CU(cudaMemcpyAsync(d_leaf, c->leaf.p, (size_t)t->nleaf * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_bounds && t->nleaf) {
+        int r = leaf_bounds(c, t);
+        if (r) return r;
+        CU(cudaMemcpyAsync(d_bounds, t->tb.p, (size_t)t->nleaf * 48, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return 0;
 }
 
@@ -664,7 +800,8 @@ int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf) {
 // moving a single halo particle first.  Sources of rank `me` are listed under local leaf ids, those of rank p under
 // nleaf_local + (leaves of the ranks before p, skipping me) + leaf: the ghost leaf table p2p_set_ghosts_device expects.
 int p2p_tree_walk_peers(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
-                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all, const void* d_son_all) {
+                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all, const void* d_son_all,
+                        const void* d_bounds_all) {
     USE(c);
     int r = walk_checks(c, theta, rcut, period, tcenter, twidth);
     if (r) return r;
@@ -678,13 +815,18 @@ int p2p_tree_walk_peers(p2p_ctx* c, double theta, double rcut, double period, co
     P.box = t->box.p; P.son = t->son.p; P.nleaf = t->nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
     for (int k = 0; k < 3; k++) { P.tc[k] = tcenter[k]; P.tw[k] = twidth[k]; }
     P.sbox = reinterpret_cast<const double*>(d_box_all); P.sson = reinterpret_cast<const int*>(d_son_all); P.me = me; P.npeer = npeer;
-    long long ub = 0, nb = 0;
+    if (period > 0.0 && d_bounds_all) {
+        if ((r = leaf_bounds(c, t))) return r;
+        P.tb = t->tb.p; P.stb = reinterpret_cast<const double*>(d_bounds_all);
+    }
+    long long ub = 0, nb = 0, lb = 0;
     int ghost = t->nleaf;
     std::vector<ull> init;
     for (int p = 0; p < npeer; p++) {
         if (peer_nleaf[p] < 0 || peer_nnode[p] < 1) return fail(P2P_ERR_ARG, "peer %d has no tree", p);
         if ((long long)peer_nleaf[p] + peer_nnode[p] >= (1LL << 27)) return fail(P2P_ERR_ARG, "peer tree too large for the walk item encoding");
-        P.sbox_base[p] = ub; P.sson_base[p] = nb; P.snleaf[p] = peer_nleaf[p];
+        P.sbox_base[p] = ub; P.sson_base[p] = nb; P.snleaf[p] = peer_nleaf[p]; P.stb_base[p] = lb;
+        lb += peer_nleaf[p];
         P.ts_base[p] = p == me ? 0 : ghost;
         if (p != me) ghost += peer_nleaf[p];
         ub += (long long)peer_nleaf[p] + peer_nnode[p];
@@ -848,9 +990,6 @@ int p2p_step_device(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart
                     const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc) {
     int r;
     if ((r = p2p_tree_build(c, pos, stride, npart, maxleaf, bdl, bdr, direct_start))) return r;
-    if (period > 0.0 && !(rcut + 2.0 * c->dtree->max_leaf_width < 0.5 * period))
-        return fail(P2P_ERR_ARG, "r_cut (%g) + 2 x largest leaf width (%g) reaches half the period (%g): the box is too small for "
-                    "minimal-image sources", rcut, c->dtree->max_leaf_width, 0.5 * period);
     if ((r = p2p_clear_tasks(c))) return r;
     double tc[3], tw[3];
     for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }   // the local root cell (toptree.c:18-45)

@@ -742,6 +742,48 @@ __global__ void route_children_kernel(BuildArrays A, int lvl_begin, int lvl_coun
     }
 }
 
+// ---- device-resident stepping: particles stay in HBM between steps -------------------------------
+__global__ void iota_kernel(int* __restrict__ a, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int)i;
+}
+// velocities and ids follow the permutation the tree build applied to the positions
+__global__ void carry_kernel(const int* __restrict__ perm, long long n, const double* __restrict__ vx, const double* __restrict__ vy,
+                             const double* __restrict__ vz, const int* __restrict__ gid, double* __restrict__ ox, double* __restrict__ oy,
+                             double* __restrict__ oz, int* __restrict__ ogid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = perm[i];
+    ox[i] = vx[p]; oy[i] = vy[p]; oz[i] = vz[p]; ogid[i] = gid[p];
+}
+// vel += acc * dkh (1_Indexing/src/photoNs.c:176-180; dkh = 0.5 dk G)
+__global__ void kick_kernel(const float4* __restrict__ acc, long long n, double dkh, double* __restrict__ vx, double* __restrict__ vy,
+                            double* __restrict__ vz) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = acc[i];
+    vx[i] += (double)a.x * dkh; vy[i] += (double)a.y * dkh; vz[i] += (double)a.z * dkh;
+}
+// pos += vel * dd, then wrapped into [0, box) exactly as the reference's while loops do (photoNs.c:182-208)
+__global__ void drift_kernel(long long n, double dd, double box, const double* __restrict__ vx, const double* __restrict__ vy,
+                             const double* __restrict__ vz, double* __restrict__ x, double* __restrict__ y, double* __restrict__ z) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3] = {x[i] + vx[i] * dd, y[i] + vy[i] * dd, z[i] + vz[i] * dd};
+    if (box > 0.0)
+        for (int k = 0; k < 3; k++) {
+            if (!(p[k] == p[k]) || fabs(p[k]) > 1e6 * box) continue;      // NaN / runaway: leave it, do not spin
+            while (p[k] < 0.0) p[k] += box;
+            while (p[k] >= box) p[k] -= box;
+        }
+    x[i] = p[0]; y[i] = p[1]; z[i] = p[2];
+}
+__global__ void aos_from_soa_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, long long n,
+                                    double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[3 * i] = x[i]; out[3 * i + 1] = y[i]; out[3 * i + 2] = z[i]; }
+}
+
 __global__ void widen_index_kernel(const int* __restrict__ perm, long long n, long long* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = perm[i];
@@ -899,6 +941,9 @@ struct WalkParams {
     long long sson_base[kMaxPeers];   // first node of peer p in sson
     int snleaf[kMaxPeers];
     int ts_base[kMaxPeers];           // task source id = ts_base[p] + leaf: 0 for me (local ids), ghost leaf ids otherwise
+    const double* tb;    // tight bounds of the particles of every LOCAL leaf, [leaf][6] = lo[3], hi[3]; nullptr: no check
+    const double* stb;   // the same for the source trees' leaves (concatenated per rank)
+    long long stb_base[kMaxPeers];
     // M2L tasks (pairs the acceptance criterion hands to the multipole expansion), emitted when mt != nullptr:
     // target = local unified id, source = unified id inside rank `peer`, mq = (peer << 5) | displacement index
     int* mt;
@@ -993,6 +1038,21 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 }
             } else if (ileaf && jleaf) {
                 emit = true;
+                if (P.period > 0.0 && P.tb) {
+                    // the source will be read through minimal-image coordinates: every particle separation this leaf pair
+                    // contains must stay below half the period, or another image would be picked.  tb: tight bounds of the
+                    // leaves' particles {lo[3], hi[3]} (lo > hi for an empty leaf)
+                    const double* bi = P.tb + 6 * (size_t)im;
+                    const double* bj = P.stb + 6 * (size_t)(P.stb_base[peer] + jm);
+                    bool bad = false;
+                    if (bi[0] <= bi[3] && bj[0] <= bj[3])
+                        for (int k = 0; k < 3; k++) {
+                            const double disp = (double)c_shift[sh][k] * P.period;
+                            const double d = fmax(bi[3 + k] - (bj[k] + disp), (bj[3 + k] + disp) - bi[k]);
+                            bad |= !(d < 0.5 * P.period);
+                        }
+                    if (bad) atomicAdd(&counters[3], 1ull);
+                }
             } else {
                 const double* bi = P.box + 6 * (size_t)im;
                 const double* bj = P.sbox + 6 * (size_t)(P.sbox_base[peer] + jm);
@@ -1064,6 +1124,26 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 if (m2l && mb < P.cap_m2l) { P.mt[mb] = im; P.ms[mb] = jm; P.mq[mb] = (peer << 5) | sh; }
             }
         }
+    }
+}
+
+// tight bounds of every local leaf's particles, from the fixed-point coordinates the force kernel reads
+__global__ void leaf_bounds_kernel(const int2* __restrict__ leaf, int nleaf, const int4* __restrict__ part, double ox, double oy, double oz,
+                                   double step, double* __restrict__ tb) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaf) return;
+    const int2 L = leaf[l];
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0, 0, 0};
+    for (int p = L.x; p < L.x + L.y; p++) {
+        const int4 q = part[p];
+        const unsigned v[3] = {(unsigned)q.x, (unsigned)q.y, (unsigned)q.z};
+        for (int k = 0; k < 3; k++) { lo[k] = min(lo[k], v[k]); hi[k] = max(hi[k], v[k]); }
+    }
+    double* o = tb + 6 * (size_t)l;
+    const double org[3] = {ox, oy, oz};
+    for (int k = 0; k < 3; k++) {
+        o[k] = L.y > 0 ? org[k] + (double)lo[k] * step : 1.0;
+        o[3 + k] = L.y > 0 ? org[k] + (double)hi[k] * step : 0.0;
     }
 }
 

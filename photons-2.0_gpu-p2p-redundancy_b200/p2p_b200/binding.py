@@ -82,12 +82,17 @@ def load_library():
     L.p2p_route_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.p2p_tree_build_resident.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
     L.p2p_download_index.argtypes = [C.c_void_p, _lp]
+    L.p2p_resident_load.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, C.c_int64]
+    L.p2p_resident_forces.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.p2p_resident_kick.argtypes = [C.c_void_p, C.c_double]
+    L.p2p_resident_drift.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.p2p_resident_download.argtypes = [C.c_void_p, _dp, _dp, _lp]
     L.p2p_midfield_enable.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.p2p_midfield_compute.argtypes = [C.c_void_p, _lp]
     L.p2p_midfield_download.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
-    L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_tree_walk_peers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
-                                      C.c_void_p, C.c_void_p]
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_ghost_marks.argtypes = [C.c_void_p, C.c_void_p]
     L.p2p_gather_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_set_ghosts_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
@@ -381,6 +386,32 @@ class P2PContext:
         self._chk(self._L.p2p_download_index(self._h, idx.ctypes.data_as(_lp)))
         return idx
 
+    # ---- device-resident stepping
+    def resident_load(self, pos, vel=None):
+        pos = _f64(pos)
+        v = _f64(vel) if vel is not None else None
+        self._chk(self._L.p2p_resident_load(self._h, pos.ctypes.data_as(_dp), pos.shape[1], v.ctypes.data_as(_dp) if v is not None else None,
+                                            v.shape[1] if v is not None else 3, pos.shape[0]))
+        self.npart = pos.shape[0]
+
+    def resident_forces(self, maxleaf, bdl, bdr, theta, rcut, period, direct_start=0):
+        bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)
+        self._chk(self._L.p2p_resident_forces(self._h, int(maxleaf), bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start),
+                                              float(theta), float(rcut), float(period)))
+        self.nleaf = self.tree_info()["nleaf"]
+
+    def resident_kick(self, dkh):
+        self._chk(self._L.p2p_resident_kick(self._h, float(dkh)))
+
+    def resident_drift(self, dd, period):
+        self._chk(self._L.p2p_resident_drift(self._h, float(dd), float(period)))
+
+    def resident_download(self):
+        n = self.npart
+        pos, vel, idx = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n, np.int64)
+        self._chk(self._L.p2p_resident_download(self._h, pos.ctypes.data_as(_dp), vel.ctypes.data_as(_dp), idx.ctypes.data_as(_lp)))
+        return pos, vel, idx
+
     # ---- mid-field (M2L lists from the walk; P2M / M2M / M2L / L2L / L2P kernels)
     def midfield_enable(self, on=True, literal_d6=False):
         self._chk(self._L.p2p_midfield_enable(self._h, 1 if on else 0, 1 if literal_d6 else 0))
@@ -401,15 +432,15 @@ class P2PContext:
         return out
 
     # ---- multi-rank device path (device pointers, e.g. tensor.data_ptr())
-    def tree_export(self, d_box, d_son, d_leaf):
-        self._chk(self._L.p2p_tree_export(self._h, d_box, d_son, d_leaf))
+    def tree_export(self, d_box, d_son, d_leaf, d_bounds=None):
+        self._chk(self._L.p2p_tree_export(self._h, d_box, d_son, d_leaf, d_bounds))
 
-    def tree_walk_peers(self, theta, rcut, period, tcenter, twidth, me, peer_nleaf, peer_nnode, d_box_all, d_son_all):
+    def tree_walk_peers(self, theta, rcut, period, tcenter, twidth, me, peer_nleaf, peer_nnode, d_box_all, d_son_all, d_bounds_all=None):
         tc, tw = np.ascontiguousarray(tcenter, np.float64), np.ascontiguousarray(twidth, np.float64)
         nl, nn = _i32(peer_nleaf), _i32(peer_nnode)
         self._chk(self._L.p2p_tree_walk_peers(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp),
                                               tw.ctypes.data_as(_dp), len(nl), int(me), nl.ctypes.data_as(_ip),
-                                              nn.ctypes.data_as(_ip), d_box_all, d_son_all))
+                                              nn.ctypes.data_as(_ip), d_box_all, d_son_all, d_bounds_all))
 
     def ghost_marks(self, d_marks):
         self._chk(self._L.p2p_ghost_marks(self._h, d_marks))

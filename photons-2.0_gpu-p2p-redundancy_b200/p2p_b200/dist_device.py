@@ -150,22 +150,21 @@ def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group
             dist.all_gather(sizes, mine, group=group)
         nls = [int(s[0]) for s in sizes]
         nns = [int(s[1]) for s in sizes]
-        wmax = max(float(np.int64(int(s[2])).view(np.float64)) for s in sizes)
-        if periodic and not rcut + 2.0 * wmax < 0.5 * box:
-            raise ValueError(f"r_cut ({rcut:g}) + 2 x largest leaf width ({wmax:g}) reaches box/2: box too small for minimal-image sources")
         box_t = torch.empty((nl + nn) * 6, dtype=torch.float64, device=dev)
         son_t = torch.empty(nn * 2, dtype=torch.int32, device=dev)
         leaf_t = torch.empty(nl * 2, dtype=torch.int32, device=dev)
-        ctx.tree_export(box_t.data_ptr(), son_t.data_ptr(), leaf_t.data_ptr())
+        tb_t = torch.empty(nl * 6, dtype=torch.float64, device=dev)
+        ctx.tree_export(box_t.data_ptr(), son_t.data_ptr(), leaf_t.data_ptr(), tb_t.data_ptr())
         boxes = _all_gather_v(box_t, [(a + b) * 6 for a, b in zip(nls, nns)], group)
         sons = _all_gather_v(son_t, [2 * b for b in nns], group)
         leaves = _all_gather_v(leaf_t, [2 * a for a in nls], group)
         box_all, son_all = torch.cat(boxes), torch.cat(sons)
+        tb_all = torch.cat(_all_gather_v(tb_t, [6 * a for a in nls], group))
         t2 = time.perf_counter()
         # ---- lists: my tree against every rank's tree, all displacements
         ctx.clear_tasks()
         ctx.tree_walk_peers(theta, rcut, box if periodic else 0.0, 0.5 * (bdr + bdl), bdr - bdl, me, nls, nns, box_all.data_ptr(),
-                            son_all.data_ptr())
+                            son_all.data_ptr(), tb_all.data_ptr())
         t3 = time.perf_counter()
         # ---- which remote leaves do I need; which of mine do the others need
         others = [p for p in range(P) if p != me]

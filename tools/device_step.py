@@ -1,5 +1,6 @@
 """Times the device-resident short-range step (tree build, dual-tree walk, packing, forces) on one GPU.
-usage: python tools/device_step.py [nside] [maxleaf] [reps] [--clustered] [--midfield] [--theta=X]"""
+usage: python tools/device_step.py [nside] [maxleaf] [reps] [--clustered] [--midfield] [--theta=X] [--resident]
+--resident: also time device-resident steps (forces + kick + drift with the particles staying in HBM)."""
 import os
 import sys
 import time
@@ -47,3 +48,20 @@ for r in range(reps):
           f"csr {ms_csr:.1f} force {ms_k:.1f} rest {1e3 * (t3 - t2) - ms_csr - ms_k:.1f} | "
           + (f"midfield {ctx.midfield_download()['ms']:.2f} ms ({nm2l} M2L tasks) | " if mid else "") +
           f"{info['nleaf']} leaves {info['nlevel']} levels {nt} tasks {npairs} pairs dup {ctx.csr_duplicates()}", flush=True)
+
+if "--resident" in sys.argv:
+    ctx.midfield_enable(False)
+    ctx.resident_load(ppos)
+    cell = box / nside
+    for r in range(reps + 1):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        ctx.resident_forces(maxleaf, bdl, bdr, theta, rcut, box)
+        ctx.resident_kick(1e-3 * cell)          # small steps: the box stays quasi-uniform
+        ctx.resident_drift(1e-3, box)
+        ctx.synchronize()
+        t1 = time.perf_counter()
+        info = ctx.tree_info()
+        ms_k, ms_csr = ctx.last_timings()
+        print(f"resident step {r}: {1e3 * (t1 - t0):.1f} ms | build {info['ms_build']:.1f} walk {info['ms_walk']:.1f} csr {ms_csr:.1f} force {ms_k:.1f} | "
+              f"{ctx.counts()[1]} pairs", flush=True)
