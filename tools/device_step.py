@@ -57,11 +57,11 @@ if "--resident" in sys.argv:
         ctx.synchronize()
         t0 = time.perf_counter()
         ctx.resident_forces(maxleaf, bdl, bdr, theta, rcut, box)
+        info = ctx.tree_info()                  # (host-side numbers only)
         ctx.resident_kick(1e-3 * cell)          # small steps: the box stays quasi-uniform
         ctx.resident_drift(1e-3, box)
         ctx.synchronize()
         t1 = time.perf_counter()
-        info = ctx.tree_info()
         ms_k, ms_csr = ctx.last_timings()
         print(f"resident step {r}: {1e3 * (t1 - t0):.1f} ms | build {info['ms_build']:.1f} walk {info['ms_walk']:.1f} csr {ms_csr:.1f} force {ms_k:.1f} | "
-              f"{ctx.counts()[1]} pairs", flush=True)
+              f"{ctx.accumulated_counts()[1]} pairs", flush=True)
