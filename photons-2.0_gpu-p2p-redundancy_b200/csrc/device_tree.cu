@@ -677,7 +677,8 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
     int cur = 0, levels = 0;
     while (n_in) {
         if (++levels > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
-        for (;;) {
+        for (int attempt = 0;; attempt++) {
+            if (attempt > 4) return fail(P2P_ERR_CUDA, "dual-tree walk: a level still overflows its buffers after %d attempts", attempt);
             const ull cap_out = t->frontier[cur ^ 1].cap;
             const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
             const unsigned grid = (unsigned)std::min<ull>((n_in + 255) / 256, (ull)c->num_sm * 16);

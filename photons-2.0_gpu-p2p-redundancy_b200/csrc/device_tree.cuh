@@ -1009,10 +1009,12 @@ __host__ __device__ __forceinline__ ull item(int im, int jm, int peer, int sh) {
 __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
                                                          ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
                                                          ull cap_task, WalkParams P) {
+    __shared__ int s_cnt[3][8];
+    __shared__ ull s_base[3];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const ull stride = (ull)gridDim.x * blockDim.x;
-    const ull n_round = (n_in + 31) & ~31ull;
+    const ull n_round = (n_in + 255) & ~255ull;           // whole blocks iterate together (block-wide slot claims)
     for (ull idx = (ull)blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
         int nchild = 0;
         bool emit = false, m2l = false;
@@ -1057,12 +1059,18 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 const double* bi = P.box + 6 * (size_t)im;
                 const double* bj = P.sbox + 6 * (size_t)(P.sbox_base[peer] + jm);
                 double wi[3], wj[3], cjd[3], dist[3], disp[3];
+                // read-only path (L1 / texture cache): siblings in the frontier share one of the two boxes
+                const double2 i0 = __ldg(reinterpret_cast<const double2*>(bi)), i1 = __ldg(reinterpret_cast<const double2*>(bi) + 1),
+                              i2 = __ldg(reinterpret_cast<const double2*>(bi) + 2);
+                const double2 j0 = __ldg(reinterpret_cast<const double2*>(bj)), j1 = __ldg(reinterpret_cast<const double2*>(bj) + 1),
+                              j2 = __ldg(reinterpret_cast<const double2*>(bj) + 2);
+                const double ci_[3] = {i0.x, i0.y, i1.x}, cj_[3] = {j0.x, j0.y, j1.x};
+                wi[0] = i1.y; wi[1] = i2.x; wi[2] = i2.y;
+                wj[0] = j1.y; wj[1] = j2.x; wj[2] = j2.y;
                 for (int k = 0; k < 3; k++) {
                     disp[k] = (double)c_shift[sh][k] * P.period;
-                    wi[k] = bi[3 + k];
-                    wj[k] = bj[3 + k];
-                    cjd[k] = sh ? bj[k] + disp[k] : bj[k];
-                    dist[k] = bi[k] - cjd[k];
+                    cjd[k] = sh ? cj_[k] + disp[k] : cj_[k];
+                    dist[k] = ci_[k] - cjd[k];
                 }
                 const int flag = acceptance(wi, wj, dist, P.theta, P.rcut);
                 int open = 0;     // 1: target side, 2: source side
@@ -1075,8 +1083,7 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 } else if (flag != -1) {
                     bool pruned = false;
                     if (!jleaf) {
-                        const double nc[3] = {bj[0], bj[1], bj[2]};
-                        pruned = image_pruned(P, nc, wj, disp);
+                        pruned = image_pruned(P, cj_, wj, disp);
                     }
                     if (ileaf) { if (flag != 1 && !pruned) open = 2; else m2l = true; }   // remotes.c:506: accepted OR cut by the sender
                     else if (jleaf) { if (flag != 1) open = 1; else m2l = true; }
@@ -1084,46 +1091,50 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                     else m2l = true;
                 }
                 if (open == 1) {
-                    ci[0] = P.son[2 * (im - P.nleaf)]; ci[1] = P.son[2 * (im - P.nleaf) + 1];
+                    const int2 sn = __ldg(reinterpret_cast<const int2*>(P.son) + (im - P.nleaf));
+                    ci[0] = sn.x; ci[1] = sn.y;
                     cj[0] = cj[1] = jm;
                     nchild = 2;
                 } else if (open == 2) {
-                    cj[0] = sson[2 * (jm - snl)]; cj[1] = sson[2 * (jm - snl) + 1];
+                    const int2 sn = __ldg(reinterpret_cast<const int2*>(sson) + (jm - snl));
+                    cj[0] = sn.x; cj[1] = sn.y;
                     ci[0] = ci[1] = im;
                     nchild = 2;
                 }
             }
         }
-        // claim output slots per warp
+        // claim output slots: per warp totals, ONE atomic per block and counter (all walkers of the chip add to the same three
+        // words; per-warp atomics made the walk atomic-throughput bound), then per-warp and per-lane offsets
         int incl = nchild;
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(full, incl, o);
             if (lane >= o) incl += y;
         }
         const int total = __shfl_sync(full, incl, 31);
-        ull base = 0;
-        if (total) {
-            if (lane == 0) base = atomicAdd(&counters[0], (ull)total);
-            base = __shfl_sync(full, base, 0) + (ull)(incl - nchild);
+        const unsigned em = __ballot_sync(full, emit);
+        const unsigned mm = P.mt ? __ballot_sync(full, m2l) : 0u;      // counted only when the M2L list is wanted
+        if (lane == 0) { s_cnt[0][wid] = total; s_cnt[1][wid] = __popc(em); s_cnt[2][wid] = __popc(mm); }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            int run = 0;
+            for (int w = 0; w < 8; w++) { const int v = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = run; run += v; }
+            s_base[threadIdx.x] = run ? atomicAdd(&counters[threadIdx.x], (ull)run) : 0ull;
+        }
+        __syncthreads();
+        if (nchild) {
+            const ull base = s_base[0] + (ull)s_cnt[0][wid] + (ull)(incl - nchild);
             if (base + nchild <= cap_out)
                 for (int k = 0; k < nchild; k++) out[base + k] = item(ci[k], cj[k], peer, sh);
         }
-        const unsigned em = __ballot_sync(full, emit);
-        if (em) {
-            ull tb = 0;
-            if (lane == 0) tb = atomicAdd(&counters[1], (ull)__popc(em));
-            tb = __shfl_sync(full, tb, 0) + (ull)__popc(em & ((1u << lane) - 1));
-            if (emit && tb < cap_task) { tt[tb] = im; ts[tb] = tsid; }
+        if (emit) {
+            const ull tb = s_base[1] + (ull)s_cnt[1][wid] + (ull)__popc(em & ((1u << lane) - 1));
+            if (tb < cap_task) { tt[tb] = im; ts[tb] = tsid; }
         }
-        if (P.mt) {
-            const unsigned mm = __ballot_sync(full, m2l);
-            if (mm) {
-                ull mb = 0;
-                if (lane == 0) mb = atomicAdd(&counters[2], (ull)__popc(mm));
-                mb = __shfl_sync(full, mb, 0) + (ull)__popc(mm & ((1u << lane) - 1));
-                if (m2l && mb < P.cap_m2l) { P.mt[mb] = im; P.ms[mb] = jm; P.mq[mb] = (peer << 5) | sh; }
-            }
+        if (m2l && P.mt) {
+            const ull mb = s_base[2] + (ull)s_cnt[2][wid] + (ull)__popc(mm & ((1u << lane) - 1));
+            if (mb < P.cap_m2l) { P.mt[mb] = im; P.ms[mb] = jm; P.mq[mb] = (peer << 5) | sh; }
         }
+        __syncthreads();
     }
 }
 
