@@ -137,13 +137,11 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
         __syncwarp();
         for (int k = 2; k <= m; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = lane; i < m; i += 32) {
-                    int p = i ^ j;
-                    if (p > i) {
-                        int x = a[i], y = a[p];
-                        bool up = (i & k) == 0;
-                        if ((x > y) == up) { a[i] = y; a[p] = x; }
-                    }
+                for (int t = lane; t < (m >> 1); t += 32) {         // one compare-exchange per lane and step: no idle partner lanes
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                    const int x = a[i], y = a[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[p] = x; }
                 }
                 __syncwarp();
             }
