@@ -49,7 +49,7 @@ struct p2p_dtree {
     ull* d_wcount = nullptr;     // [0] next frontier, [1] tasks
     ull* h_wcount = nullptr;     // pinned
     unsigned int* d_dup = nullptr;
-    unsigned long long* d_maxw = nullptr;
+    int* d_maxw = nullptr;
     double max_leaf_width = 0.0;
     DevBuf<double> v[3], vtmp[3];     // device-resident stepping: velocities (tree order) and carry scratch
     DevBuf<int> gid, gidtmp;          // ... and the particles' ids
@@ -101,7 +101,7 @@ int get_tree(p2p_ctx* c, p2p_dtree** out) {
         CU(cudaMalloc(&t->d_wcount, 4 * sizeof(ull)));
         CU(cudaMallocHost(&t->h_wcount, 4 * sizeof(ull)));
         CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
-        CU(cudaMalloc(&t->d_maxw, sizeof(unsigned long long)));
+        CU(cudaMalloc(&t->d_maxw, sizeof(int)));
         CU(cudaEventCreate(&t->e0));
         CU(cudaEventCreate(&t->e1));
         static const int shifts[28][3] = {{0, 0, 0},
@@ -316,7 +316,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     p2p::dt::TreeOut O;
     O.nleaf = nleaf; O.box = t->box.p; O.son = t->son.p; O.node_npart = t->node_npart.p; O.node_split = t->node_split.p;
     O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p; O.max_width = t->d_maxw;
-    CU(cudaMemsetAsync(t->d_maxw, 0, sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(t->d_maxw, 0, sizeof(int), st));
     for (int lvl = 0; lvl < t->nlevel; lvl++)
         p2p::dt::assign_down_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, O, lvl_begin[lvl], lvl_count[lvl], (direct_start + lvl) % 3,
                                                                                bdl[0], bdl[1], bdl[2], bdr[0], bdr[1], bdr[2]);
@@ -337,10 +337,10 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     c->max_target_leaf = maxleaf;
     if ((r = p2p_update_occupancy(c))) return r;
     CU(cudaEventRecord(t->e1, st));
-    unsigned long long wbits = 0;
-    CU(cudaMemcpyAsync(&wbits, t->d_maxw, sizeof wbits, cudaMemcpyDeviceToHost, st));
+    float wmaxf = 0.f;
+    CU(cudaMemcpyAsync(&wmaxf, t->d_maxw, sizeof wmaxf, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    memcpy(&t->max_leaf_width, &wbits, sizeof wbits);
+    t->max_leaf_width = wmaxf;
     CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
     t->valid = true; t->built_here = true; t->mid_valid = false;

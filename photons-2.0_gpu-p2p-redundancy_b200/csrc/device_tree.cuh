@@ -108,6 +108,13 @@ __global__ void flag_scan_apply_kernel(const unsigned char* __restrict__ flag, l
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) G[n] = tile[gridDim.x];
 }
 
+// max over the lanes that are active here, ONE atomic per warp (per-thread atomics on one word serialise chip-wide)
+__device__ __forceinline__ void warp_atomic_max(int* addr, int v) {
+    const unsigned m = __activemask();
+    v = __reduce_max_sync(m, v);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && v > 0) atomicMax(addr, v);
+}
+
 // ------------------------------------------------------------------------------------------------ build
 struct BuildArrays {
     // particles in the current order (SoA) and their original indices
@@ -643,8 +650,7 @@ __global__ void children_kernel(BuildArrays A, int lvl_begin, int lvl_count, int
     } else c1 = -1 - np1;
     A.t_child[2 * t] = c0;
     A.t_child[2 * t + 1] = c1;
-    const int mx = max(np0 > maxleaf ? np0 : 0, np1 > maxleaf ? np1 : 0);
-    if (mx) atomicMax(longest, mx);
+    warp_atomic_max(longest, max(np0 > maxleaf ? np0 : 0, np1 > maxleaf ? np1 : 0));
 }
 
 // positions of the right-zone small elements by rank from the right, and the owner of every position at the next level
@@ -818,7 +824,7 @@ struct TreeOut {
     double* node_split;
     int* leaf_npart;
     int* leaf_ipart;
-    unsigned long long* max_width;   // bits of the largest leaf width (non-negative doubles order like integers)
+    int* max_width;                  // float bits of the largest leaf width (non-negative floats order like integers); informational
 };
 
 // top-down: final ids, kd cells, output arrays
@@ -860,6 +866,7 @@ __global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int 
     O.node_split[id] = split;
     if (A.t_len[t] == 0) { O.son[2 * id] = O.son[2 * id + 1] = -1; return; }
     int lb = leafbase, nid = id + 1, ip = A.t_start[t];
+    double wmax = 0.0;
     for (int s = 0; s < 2; s++) {
         const int c = A.t_child[2 * t + s];
         if (c >= 0) {
@@ -876,12 +883,12 @@ __global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int 
             for (int k = 0; k < 3; k++) { b[k] = ncen[k]; b[3 + k] = nwid[k]; }
             if (s == 0) { b[3 + dir] = split - lo[dir]; b[dir] = 0.5 * (lo[dir] + split); }
             else        { b[3 + dir] = hi[dir] - split; b[dir] = 0.5 * (hi[dir] + split); }
-            const double wm = fmax(b[3], fmax(b[4], b[5]));
-            if (wm > 0.0) atomicMax(O.max_width, (unsigned long long)__double_as_longlong(wm));
+            wmax = fmax(wmax, fmax(b[3], fmax(b[4], b[5])));
             lb += 1;
             ip += cnt;
         }
     }
+    warp_atomic_max(O.max_width, __float_as_int((float)wmax));
 }
 
 __global__ void soa_from_aos_kernel(const double* __restrict__ pos, long long n, double* __restrict__ x, double* __restrict__ y,
@@ -912,7 +919,7 @@ __global__ void leaf_pack_kernel(const int* __restrict__ npart, const int* __res
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = make_int2(ipart[i], npart[i]);
-    atomicMax(maxocc, npart[i]);
+    warp_atomic_max(maxocc, npart[i]);
 }
 
 __global__ void acc_unpermute_kernel(const float4* __restrict__ acc, const int* __restrict__ perm, long long n, double* __restrict__ out) {
