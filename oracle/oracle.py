@@ -38,6 +38,7 @@ def lib():
         _lib.oracle_p2p_tasks.restype = C.c_int64
         _lib.oracle_p2p_absterms.restype = C.c_int64
         _lib.oracle_fingerprint.restype = C.c_uint64
+        _lib.oracle_midfield.restype = C.c_int
     return _lib
 
 
@@ -145,6 +146,22 @@ class Tree:
             if n <= cap:
                 return tt[:n] - self.first_leaf, ts[:n].copy()
             cap = int(n)
+
+
+def midfield(T, theta, rcut, rs, mass, box=0.0, literal_d6=False):
+    """Mid-field of a single rank's tree (oracle.Tree): P2M / M2M / M2L / L2L / L2P as the reference runs them
+    (1_Indexing/src/operator.c).  Returns dict(leaf_M, node_M, leaf_L, acc [tree order], nm2l_local, nm2l_total)."""
+    nl, nn = T.nleaf, T.nnode
+    leaf_M, node_M, leaf_L = np.zeros((nl, 20)), np.zeros((nn, 20)), np.zeros((nl, 20))
+    acc = np.zeros((T.npart, 3))
+    a, b = C.c_int64(), C.c_int64()
+    rc = lib().oracle_midfield(T.npart, T.nleaf_cap, nl, nn, T.maxleaf, _d(T.pos), _i(T.leaf_npart), _i(T.leaf_ipart), _d(T.leaf_center),
+                               _d(T.leaf_width), _i(T.node_npart), _i(T.node_son), _d(T.node_center), _d(T.node_width),
+                               C.c_double(theta), C.c_double(rcut), C.c_double(rs), C.c_double(mass), C.c_double(box),
+                               1 if literal_d6 else 0, _d(leaf_M), _d(node_M), _d(leaf_L), _d(acc), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise RuntimeError("oracle_midfield failed")
+    return dict(leaf_M=leaf_M, node_M=node_M, leaf_L=leaf_L, acc=acc, nm2l_local=a.value, nm2l_total=b.value)
 
 
 def p2p(tpos, t_npart, t_ipart, spos, s_count, s_start, tt, ts, mass, eps, rs, acc=None, nthreads=0, absterms=False):

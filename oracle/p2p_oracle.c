@@ -308,12 +308,14 @@ typedef struct {
     int cap_node, cap_body, numnode, numbody, overflow;
     int *r_npart, *r_son;
     double *r_center, *r_width, *r_body;
+    int* r_src;                      /* optional: local id (reference numbering) of every image node */
 } Prune;
 
 /* I/src/remotes.c:337-446 */
 static void prune_rec(Prune* p, int isend, int ilocal) {
     if (p->overflow) return;
     if (isend >= p->cap_node) { p->overflow = 1; return; }
+    if (p->r_src) p->r_src[isend] = ilocal;
     if (ilocal < p->first_node && ilocal >= p->first_leaf) {
         int li = ilocal - p->first_leaf;
         p->r_npart[isend] = p->leaf_npart[li];
@@ -642,4 +644,251 @@ void oracle_domain_partition(int nproc, const double* split, double* pos, int64_
     Bodies b = {pos, payload};
     for (int r = 0; r < nproc; r++) sendcount[r] = 0;
     route_rec(&b, nproc, mostleft_of(nproc), split, 0, 0, npart, 0, sendcount);
+}
+
+
+/* ------------------------------------------------------------------ mid-field ----
+ * P2M / M2M / M2L / L2L / L2P restated from 1_Indexing/src/operator.c (QUADRUPOLE + OCTUPOLE: 20 coefficients in the
+ * order of 1_Indexing/inc/operator.h:24-67), driven as fmm_prepare / fmm_task / fmm_ext drive them
+ * (1_Indexing/src/fmm.c:745-790, 562-705, 913-945, 1026-1145; 1_Indexing/src/remotes.c:477-640).
+ * A coefficient with multi-index (a,b,c) carries 1/(a! b! c!); the expansions are written over that table. */
+enum { NMUL = 20 };
+static const int MIDX[NMUL][3] = {{0,0,0},{1,0,0},{0,1,0},{0,0,1},{2,0,0},{1,1,0},{1,0,1},{0,2,0},{0,1,1},{0,0,2},
+                                  {3,0,0},{2,1,0},{2,0,1},{1,2,0},{1,1,1},{1,0,2},{0,3,0},{0,2,1},{0,1,2},{0,0,3}};
+static int mpos(int a, int b, int c) {
+    for (int n = 0; n < NMUL; n++) if (MIDX[n][0] == a && MIDX[n][1] == b && MIDX[n][2] == c) return n;
+    return -1;
+}
+static double mfact(int n) { return n <= 1 ? 1.0 : (n == 2 ? 2.0 : 6.0); }
+static void mpowers(double x, double y, double z, double pw[NMUL]) {
+    for (int n = 0; n < NMUL; n++) {
+        double v = 1.0;
+        for (int k = 0; k < MIDX[n][0]; k++) v *= x;
+        for (int k = 0; k < MIDX[n][1]; k++) v *= y;
+        for (int k = 0; k < MIDX[n][2]; k++) v *= z;
+        pw[n] = v / (mfact(MIDX[n][0]) * mfact(MIDX[n][1]) * mfact(MIDX[n][2]));
+    }
+}
+/* operator.c:13-93 */
+static void o_p2m(const double* pos, int ipart, int npart, const double c[3], double mass, double M[NMUL]) {
+    for (int n = 0; n < NMUL; n++) M[n] = 0.0;
+    for (int p = ipart; p < ipart + npart; p++) {
+        double pw[NMUL];
+        mpowers(pos[3 * (size_t)p] - c[0], pos[3 * (size_t)p + 1] - c[1], pos[3 * (size_t)p + 2] - c[2], pw);
+        for (int n = 0; n < NMUL; n++) M[n] += ((MIDX[n][0] + MIDX[n][1] + MIDX[n][2]) & 1) ? -mass * pw[n] : mass * pw[n];
+    }
+}
+/* operator.c:96-160: tM += M shifted by d = new centre - old centre */
+static void o_m2m(const double d[3], const double M[NMUL], double tM[NMUL]) {
+    double pw[NMUL];
+    mpowers(d[0], d[1], d[2], pw);
+    for (int n = 0; n < NMUL; n++) {
+        double s = 0.0;
+        for (int k = 0; k < NMUL; k++)
+            if (MIDX[k][0] <= MIDX[n][0] && MIDX[k][1] <= MIDX[n][1] && MIDX[k][2] <= MIDX[n][2])
+                s += M[k] * pw[mpos(MIDX[n][0] - MIDX[k][0], MIDX[n][1] - MIDX[k][1], MIDX[n][2] - MIDX[k][2])];
+        tM[n] += s;
+    }
+}
+/* operator.c:255-392 with the LONGSHORT factors :296-305 (rs <= 0: plain 1/r) */
+static void o_m2l(const double x[3], const double M[NMUL], double rs, double toL[NMUL]) {
+    const double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2], dr = sqrt(r2);
+    const double ir = 1.0 / dr, ir2 = ir * ir, ir3 = ir2 * ir, ir4 = ir3 * ir, ir5 = ir4 * ir, ir6 = ir5 * ir, ir7 = ir6 * ir;
+    double f[4];
+    if (rs > 0.0) {
+        const double irs = 1.0 / rs, irs2 = irs * irs, irs3 = irs2 * irs, irs5 = irs3 * irs2;
+        const double u = 0.5 * dr / rs, fe = exp(-u * u) * (1.0 / sqrt(M_PI)), fc = erfc(u);
+        f[0] = ir * fc;
+        f[1] = -ir3 * (fc + dr * fe * irs);
+        f[2] = 3.0 * ir5 * fc + (3.0 * irs * ir4 + 0.5 * ir2 * irs3) * fe;
+        f[3] = -3.0 * 5.0 * ir7 * fc - (15.0 * ir6 * irs + 2.5 * ir4 * irs3 + 0.25 * ir2 * irs5) * fe;
+    } else { f[0] = ir; f[1] = -ir3; f[2] = 3.0 * ir5; f[3] = -15.0 * ir7; }
+    double D[NMUL];
+    D[0] = f[0];
+    for (int n = 1; n < NMUL; n++) {
+        int ax[3] = {0, 0, 0}, m = 0;
+        for (int d = 0; d < 3; d++) for (int k = 0; k < MIDX[n][d]; k++) ax[m++] = d;
+        if (m == 1) D[n] = f[1] * x[ax[0]];
+        else if (m == 2) D[n] = f[2] * x[ax[0]] * x[ax[1]] + (ax[0] == ax[1] ? f[1] : 0.0);
+        else {
+            double t = 0.0;
+            if (ax[1] == ax[2]) t += x[ax[0]];
+            if (ax[0] == ax[2]) t += x[ax[1]];
+            if (ax[0] == ax[1]) t += x[ax[2]];
+            D[n] = f[3] * x[ax[0]] * x[ax[1]] * x[ax[2]] + f[2] * t;
+        }
+    }
+    for (int n = 0; n < NMUL; n++) {
+        double a = 0.0;
+        for (int k = 0; k < NMUL; k++) {
+            const int o = MIDX[n][0] + MIDX[n][1] + MIDX[n][2] + MIDX[k][0] + MIDX[k][1] + MIDX[k][2];
+            if (o <= 3) a += M[k] * D[mpos(MIDX[n][0] + MIDX[k][0], MIDX[n][1] + MIDX[k][1], MIDX[n][2] + MIDX[k][2])];
+        }
+        toL[n] += a;
+    }
+}
+/* operator.c:395-494: toL += L shifted by d = new centre - old centre */
+static void o_l2l(const double d[3], const double L[NMUL], double toL[NMUL]) {
+    double pw[NMUL];
+    mpowers(d[0], d[1], d[2], pw);
+    for (int n = 0; n < NMUL; n++) {
+        double s = 0.0;
+        for (int k = 0; k < NMUL; k++)
+            if (MIDX[k][0] >= MIDX[n][0] && MIDX[k][1] >= MIDX[n][1] && MIDX[k][2] >= MIDX[n][2])
+                s += L[k] * pw[mpos(MIDX[k][0] - MIDX[n][0], MIDX[k][1] - MIDX[n][1], MIDX[k][2] - MIDX[n][2])];
+        toL[n] += s;
+    }
+}
+
+typedef struct {
+    Walk w;                       /* tree arrays, theta, rcut (reference numbering) */
+    double rs;
+    double *lM, *nM, *lL, *nL;    /* [leaf][20], [node][20] */
+    int64_t nm2l;
+    /* received image */
+    const int* r_src;
+} Mid;
+static double* mid_M(Mid* m, int id) { return id < m->w.first_node ? m->lM + NMUL * (size_t)(id - m->w.first_leaf) : m->nM + NMUL * (size_t)(id - m->w.first_node); }
+static double* mid_L(Mid* m, int id) { return id < m->w.first_node ? m->lL + NMUL * (size_t)(id - m->w.first_leaf) : m->nL + NMUL * (size_t)(id - m->w.first_node); }
+
+/* operator.c:165-194 */
+static void mid_m2m_rec(Mid* m, int inode) {
+    const double* cn = box_c(&m->w, inode);
+    for (int n = 0; n < 2; n++) {
+        const int idx = son_of(&m->w, inode, n);
+        if (idx < 0) continue;
+        if (idx >= m->w.first_node) mid_m2m_rec(m, idx);
+        const double* cs = box_c(&m->w, idx);
+        const double d[3] = {cn[0] - cs[0], cn[1] - cs[1], cn[2] - cs[2]};
+        o_m2m(d, mid_M(m, idx), mid_M(m, inode));
+    }
+}
+/* fmm.c:562-705 + task_compute_m2l :913-945 (tasks are applied in the order they are found) */
+static void mid_walk_local(Mid* m, int im, int jm) {
+    Walk* w = &m->w;
+    if (im == -1 || jm == -1) return;
+    if (im == jm) {
+        if (im >= w->first_node)
+            for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) mid_walk_local(m, son_of(w, im, a), son_of(w, jm, b));
+        return;
+    }
+    const int ileaf = im < w->first_node, jleaf = jm < w->first_node;
+    if (ileaf && jleaf) return;
+    const double *ci = box_c(w, im), *cj = box_c(w, jm), *wi = box_w(w, im), *wj = box_w(w, jm);
+    const double dist[3] = {ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2]};
+    const int flag = oracle_acceptance(wi, wj, dist, w->theta, w->rcut);
+    if (flag == 1) { o_m2l(dist, mid_M(m, jm), m->rs, mid_L(m, im)); m->nm2l++; return; }
+    if (flag != 0) return;
+    if (ileaf) { mid_walk_local(m, im, son_of(w, jm, 0)); mid_walk_local(m, im, son_of(w, jm, 1)); return; }
+    if (jleaf) { mid_walk_local(m, son_of(w, im, 0), jm); mid_walk_local(m, son_of(w, im, 1), jm); return; }
+    if (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2]) { mid_walk_local(m, son_of(w, im, 0), jm); mid_walk_local(m, son_of(w, im, 1), jm); }
+    else { mid_walk_local(m, im, son_of(w, jm, 0)); mid_walk_local(m, im, son_of(w, jm, 1)); }
+}
+/* remotes.c:477-640 + task_compute_m2l_ext: the image node's multipole is that of the local node it was copied from */
+static void mid_walk_ext(Mid* m, int im, int jm) {
+    Walk* w = &m->w;
+    const int ileaf = im < w->first_node, jleaf = w->r_npart[jm] <= w->maxleaf;
+    if (ileaf && jleaf) return;
+    const double* ci = box_c(w, im);
+    const double* cj = w->r_center + 3 * (size_t)jm;
+    const double dist[3] = {ci[0] - cj[0], ci[1] - cj[1], ci[2] - cj[2]};
+    const double *wi = box_w(w, im), *wj = w->r_width + 3 * (size_t)jm;
+    const int flag = oracle_acceptance(wi, wj, dist, w->theta, w->rcut);
+    const int s0 = w->r_son[2 * (size_t)jm], s1 = w->r_son[2 * (size_t)jm + 1];
+    if (flag == -1) return;
+    if (ileaf) {
+        if (flag == 1 || s0 < 0 || s1 < 0) { o_m2l(dist, mid_M(m, m->r_src[jm]), m->rs, mid_L(m, im)); m->nm2l++; return; }
+        mid_walk_ext(m, im, s0); mid_walk_ext(m, im, s1);
+        return;
+    }
+    if (flag == 1) { o_m2l(dist, mid_M(m, m->r_src[jm]), m->rs, mid_L(m, im)); m->nm2l++; return; }
+    if (jleaf) { mid_walk_ext(m, son_of(w, im, 0), jm); mid_walk_ext(m, son_of(w, im, 1), jm); return; }
+    if (wi[0] + wi[1] + wi[2] > wj[0] + wj[1] + wj[2] || s0 < 0 || s1 < 0) { mid_walk_ext(m, son_of(w, im, 0), jm); mid_walk_ext(m, son_of(w, im, 1), jm); }
+    else { mid_walk_ext(m, im, s0); mid_walk_ext(m, im, s1); }
+}
+/* operator.c:498-530 */
+static void mid_l2l_rec(Mid* m, int inode) {
+    if (inode < m->w.first_node) return;
+    const double* cn = box_c(&m->w, inode);
+    for (int n = 0; n < 2; n++) {
+        const int idx = son_of(&m->w, inode, n);
+        if (idx < m->w.first_leaf) return;
+        const double* cs = box_c(&m->w, idx);
+        const double d[3] = {cs[0] - cn[0], cs[1] - cn[1], cs[2] - cn[2]};
+        o_l2l(d, mid_L(m, inode), mid_L(m, idx));
+        if (idx >= m->w.first_node) mid_l2l_rec(m, idx);
+    }
+}
+
+/* Single rank: local tree + (box > 0) the 26 periodic images pruned against the root box; literal_d6 != 0 also replays
+ * the reference's zero-shift self exchange (SURVEY defect D6).  Outputs: leaf_M[nleaf][20], node_M[nnode][20],
+ * leaf_L[nleaf][20] (after L2L), acc[npart][3] (L2P, accumulated), *nm2l_local / *nm2l_total. */
+int oracle_midfield(int npart, int nleaf_cap, int nleaf, int nnode, int maxleaf, const double* pos, const int* leaf_npart,
+                    const int* leaf_ipart, const double* leaf_center, const double* leaf_width, const int* node_npart,
+                    const int* node_son, const double* node_center, const double* node_width, double theta, double rcut,
+                    double rs, double mass, double box, int literal_d6, double* leaf_M, double* node_M, double* leaf_L,
+                    double* acc, int64_t* nm2l_local, int64_t* nm2l_total) {
+    Mid m;
+    memset(&m, 0, sizeof m);
+    Walk* w = &m.w;
+    w->first_leaf = npart; w->last_leaf = npart + nleaf; w->first_node = npart + nleaf_cap;
+    w->lc = leaf_center; w->lw = leaf_width; w->nc = node_center; w->nw = node_width; w->son = node_son;
+    w->theta = theta; w->rcut = rcut; w->maxleaf = maxleaf;
+    m.rs = rs; m.lM = leaf_M; m.nM = node_M; m.lL = leaf_L;
+    m.nL = (double*)calloc((size_t)NMUL * (size_t)(nnode > 0 ? nnode : 1), sizeof(double));
+    if (!m.nL) return -1;
+    memset(leaf_L, 0, sizeof(double) * NMUL * (size_t)nleaf);
+    memset(node_M, 0, sizeof(double) * NMUL * (size_t)nnode);
+    for (int l = 0; l < nleaf; l++) o_p2m(pos, leaf_ipart[l], leaf_npart[l], leaf_center + 3 * (size_t)l, mass, leaf_M + NMUL * (size_t)l);
+    mid_m2m_rec(&m, w->first_node);
+    mid_walk_local(&m, w->first_node, w->first_node);
+    if (nm2l_local) *nm2l_local = m.nm2l;
+    if (box > 0.0) {
+        const int cap_node = nleaf + nnode + 2, cap_body = npart + 1;
+        int* r_npart = (int*)malloc(sizeof(int) * (size_t)cap_node);
+        int* r_son = (int*)malloc(sizeof(int) * 2 * (size_t)cap_node);
+        int* r_src = (int*)malloc(sizeof(int) * (size_t)cap_node);
+        double* r_center = (double*)malloc(sizeof(double) * 3 * (size_t)cap_node);
+        double* r_width = (double*)malloc(sizeof(double) * 3 * (size_t)cap_node);
+        double* r_body = (double*)malloc(sizeof(double) * 3 * (size_t)cap_body);
+        if (!r_npart || !r_son || !r_src || !r_center || !r_width || !r_body) return -1;
+        for (int si = literal_d6 ? 0 : 1; si < 27; si++) {
+            /* order of 1_Indexing/src/fmm.c:1064-1106: zero displacement, then mi, mj, mk in {-1,0,1} */
+            int sh[3] = {0, 0, 0};
+            if (si > 0) { int q = si - 1; if (q >= 13) q++; sh[0] = q / 9 - 1; sh[1] = (q / 3) % 3 - 1; sh[2] = q % 3 - 1; }
+            const double disp[3] = {sh[0] * box, sh[1] * box, sh[2] * box};
+            Prune p;
+            memset(&p, 0, sizeof p);
+            p.first_leaf = npart; p.first_node = npart + nleaf_cap;
+            p.pos = pos; p.leaf_npart = leaf_npart; p.leaf_ipart = leaf_ipart; p.node_npart = node_npart; p.node_son = node_son;
+            p.lc = leaf_center; p.lw = leaf_width; p.nc = node_center; p.nw = node_width;
+            p.tc = node_center; p.tw = node_width;           /* the local root box (toptree.c:18-45) */
+            p.disp = disp; p.theta = theta; p.rcut = rcut; p.cap_node = cap_node; p.cap_body = cap_body;
+            p.r_npart = r_npart; p.r_son = r_son; p.r_center = r_center; p.r_width = r_width; p.r_body = r_body; p.r_src = r_src;
+            prune_rec(&p, 0, p.first_node);
+            if (p.overflow) return -1;
+            w->r_npart = r_npart; w->r_son = r_son; w->r_center = r_center; w->r_width = r_width; m.r_src = r_src;
+            if (p.numnode > 0) mid_walk_ext(&m, w->first_node, 0);
+        }
+        free(r_npart); free(r_son); free(r_src); free(r_center); free(r_width); free(r_body);
+    }
+    if (nm2l_total) *nm2l_total = m.nm2l;
+    mid_l2l_rec(&m, w->first_node);
+    /* operator.c:197-251 */
+    for (int l = 0; l < nleaf; l++) {
+        const double* F = leaf_L + NMUL * (size_t)l;
+        for (int p = leaf_ipart[l]; p < leaf_ipart[l] + leaf_npart[l]; p++) {
+            double pw[NMUL];
+            mpowers(pos[3 * (size_t)p] - leaf_center[3 * (size_t)l], pos[3 * (size_t)p + 1] - leaf_center[3 * (size_t)l + 1],
+                    pos[3 * (size_t)p + 2] - leaf_center[3 * (size_t)l + 2], pw);
+            for (int n = 0; n < NMUL; n++) {
+                if (MIDX[n][0] + MIDX[n][1] + MIDX[n][2] > 2) continue;
+                acc[3 * (size_t)p] += F[mpos(MIDX[n][0] + 1, MIDX[n][1], MIDX[n][2])] * pw[n];
+                acc[3 * (size_t)p + 1] += F[mpos(MIDX[n][0], MIDX[n][1] + 1, MIDX[n][2])] * pw[n];
+                acc[3 * (size_t)p + 2] += F[mpos(MIDX[n][0], MIDX[n][1], MIDX[n][2] + 1)] * pw[n];
+            }
+        }
+    }
+    free(m.nL);
+    return 0;
 }

@@ -94,6 +94,16 @@ void oracle_domain_partition(int nproc, const double* split, double* pos, int64_
                              int* sendorder);
 /* work-weighted relaxation of the rank-tree splits, I/src/domains.c:20-38,86-157 */
 void oracle_domain_relax(int nproc, double box, double* split, const double* frac);
+/* Mid-field: P2M / M2M / M2L / L2L / L2P restated from 1_Indexing/src/operator.c:13-530 and driven as
+ * fmm_prepare / fmm_task / fmm_ext drive them (1_Indexing/src/fmm.c:745-790,562-705,913-945,1026-1145;
+ * 1_Indexing/src/remotes.c:477-640).  Single rank; box > 0 adds the 26 periodic images; literal_d6 replays the
+ * reference's zero-shift self exchange (defect D6).  Pinned against the reference's own operators in
+ * tests/test_oracle_vs_ref.py.  acc[npart][3] is ACCUMULATED into. */
+int oracle_midfield(int npart, int nleaf_cap, int nleaf, int nnode, int maxleaf, const double* pos, const int* leaf_npart,
+                    const int* leaf_ipart, const double* leaf_center, const double* leaf_width, const int* node_npart,
+                    const int* node_son, const double* node_center, const double* node_width, double theta, double rcut,
+                    double rs, double mass, double box, int literal_d6, double* leaf_M, double* node_M, double* leaf_L,
+                    double* acc, int64_t* nm2l_local, int64_t* nm2l_total);
 int oracle_max_threads(void);
 #ifdef __cplusplus
 }

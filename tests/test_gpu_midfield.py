@@ -69,3 +69,22 @@ def test_midfield_matches_the_reference_operators(demo_pos, maxleaf, theta):
     assert np.abs(want).max() > 0
     err = np.linalg.norm(acc - want, axis=1).max() / np.linalg.norm(want, axis=1).mean()
     assert err < 1e-10, err
+
+
+@pytest.mark.parametrize("literal_d6", [False, True])
+def test_midfield_matches_the_oracle_restatement(demo_pos, literal_d6):
+    """the same comparison against oracle/p2p_oracle.c:oracle_midfield (itself pinned to the reference's operators in
+    tests/test_oracle_vs_ref.py), which needs no prebuilt reference binary; literal_d6 False is the intended semantics"""
+    pos = demo_pos[::4].copy()
+    maxleaf, theta = 3, 1.1
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(pos))
+    T = oracle.Tree(pos, maxleaf, [0, 0, 0], [DEMO_BOX] * 3, 0)
+    m = oracle.midfield(T, theta, rcut, rs, 1.0, DEMO_BOX, literal_d6=literal_d6)
+    nm2l, acc, mid, _ = _device_mid(pos, maxleaf, theta, literal_d6)
+    assert nm2l == m["nm2l_total"] > 1000
+    for k in ("leaf_M", "node_M", "leaf_L"):
+        scale = np.abs(m[k]).max(axis=0) + 1e-300
+        assert (np.abs(mid[k] - m[k]) / scale).max() < 1e-11, k
+    want = np.zeros_like(acc)
+    want[T.perm] = m["acc"]
+    assert np.linalg.norm(acc - want, axis=1).max() < 1e-10 * np.linalg.norm(want, axis=1).mean()

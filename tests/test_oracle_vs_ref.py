@@ -92,3 +92,30 @@ def test_work_weighted_split_relaxation(demo_pos, nproc):
             blocks[d][r] = idx[off[d]:off[d + 1]]
     for d in range(nproc):
         assert np.array_equal(np.concatenate(blocks[d]), rr[d]["part_orig_index_step2"])
+
+
+@pytest.mark.parametrize("maxleaf,theta", [(2, 1.0), (4, 1.2), (16, 0.4)])
+def test_midfield_restatement_against_the_reference_operators(demo_pos, maxleaf, theta):
+    """oracle_midfield (P2M / M2M / M2L / L2L / L2P) against the reference's own CPU operators: ref_lists runs the
+    unmodified fmm_prepare / fmm_task / fmm_ext while the P2P stubs return zeros, so part[].acc is the mid-field alone.
+    Same operations in the same order -> agreement to rounding.  With the reference's own parameters (last case)
+    the M2L list is empty and the mid-field vanishes identically."""
+    import oracle
+    pos = demo_pos[::4].copy()
+    box, nside = 100000.0, 32
+    r = refrun.run(pos, box, maxleaf, nside, theta, True, 1)[0]
+    rs, rcut, eps = oracle.derived_params(box, nside, len(pos))
+    T = oracle.Tree(pos, maxleaf, [0, 0, 0], [box] * 3, 0)
+    m = oracle.midfield(T, theta, rcut, rs, 1.0, box, literal_d6=True)           # the harness runs with MASSPART = 1
+    assert m["nm2l_local"] == int(r["idxM2L_local"][0])
+    if maxleaf == 16:
+        assert m["nm2l_total"] == 0 and not m["acc"].any() and not r["acc_mid"].any()
+        return
+    assert m["nm2l_local"] > 1000
+    nl = T.nleaf
+    for got, want in ((m["leaf_M"], r["leaf_M"].reshape(-1, 20)[:nl]), (m["node_M"], r["node_M"].reshape(-1, 20)),
+                      (m["leaf_L"], r["leaf_L"].reshape(-1, 20)[:nl])):
+        scale = np.abs(want).max(axis=0) + 1e-300
+        assert (np.abs(got - want) / scale).max() < 1e-13
+    want = r["acc_mid"].reshape(-1, 3)
+    assert np.abs(m["acc"] - want).max() < 1e-12 * np.linalg.norm(want, axis=1).mean()
