@@ -249,6 +249,12 @@ int p2p_midfield_enable(p2p_ctx* ctx, int on, int literal_d6);
 /* P2M -> M2M -> M2L -> L2L -> L2P for the device-built tree and the last walk (single rank: local tree + periodic
  * images); p2p_download_acc_original then returns P2P + mid-field.  *nm2l: number of M2L tasks. */
 int p2p_midfield_compute(p2p_ctx* ctx, int64_t* nm2l);
+/* multi-rank: the local multipoles (P2M + M2M) copied to d_M [(nleaf + nnode)][20] doubles (DEVICE memory, e.g. for an
+ * all-gather next to p2p_tree_export), then M2L -> L2L -> L2P with the boxes and multipoles of ALL ranks (concatenated
+ * in rank order like the arrays of p2p_tree_walk_peers, whose M2L list is used) */
+int p2p_midfield_multipoles(p2p_ctx* ctx, void* d_M);
+int p2p_midfield_compute_peers(p2p_ctx* ctx, int npeer, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
+                               const void* d_M_all, int64_t* nm2l);
 /* multipoles and local expansions, [leaf][20] / [node][20] in the reference's coefficient order
  * (1_Indexing/inc/operator.h:24-67); NULL skips; *ms: device time of p2p_midfield_compute */
 int p2p_midfield_download(p2p_ctx* ctx, double* leaf_M, double* node_M, double* leaf_L, double* node_L, float* ms);

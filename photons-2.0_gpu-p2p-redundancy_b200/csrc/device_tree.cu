@@ -833,6 +833,7 @@ int p2p_tree_walk_peers(p2p_ctx* c, double theta, double rcut, double period, co
         ub += (long long)peer_nleaf[p] + peer_nnode[p];
         nb += peer_nnode[p];
         for (int s = 0; s < (period > 0.0 ? 27 : 1); s++) init.push_back(p2p::dt::item(t->nleaf, peer_nleaf[p], p, s));
+        if (p == me && t->literal_d6) init.push_back(p2p::dt::item(t->nleaf, peer_nleaf[p], p, 27));   // zero-shift self exchange (defect D6)
     }
     c->nghostleaf = ghost - t->nleaf;          // the ghost leaf table must follow (p2p_set_ghosts_device) before p2p_build_csr
     c->nghost = 0;
@@ -931,27 +932,34 @@ int p2p_midfield_enable(p2p_ctx* c, int on, int literal_d6) {
     return 0;
 }
 
-// P2M -> M2M -> M2L (tasks of the last walk) -> L2L -> L2P on the device-built tree; the result (fp64, per particle) is
-// added by p2p_download_acc_original.  Single rank (sources are the local tree and its periodic images).
-int p2p_midfield_compute(p2p_ctx* c, int64_t* nm2l) {
-    USE(c);
-    p2p_dtree* t = c->dtree;
-    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree (p2p_tree_build)");
-    if (!t->m2l_on) return fail(P2P_ERR_STATE, "enable the M2L lists (p2p_midfield_enable) before the walk");
+}  // extern "C"
+
+namespace {
+// P2M + M2M of the local tree
+int mid_upward(p2p_ctx* c, p2p_dtree* t) {
     cudaStream_t st = c->stream;
-    const int nl = t->nleaf, nn = t->nnode;
-    const size_t nu = (size_t)nl + nn;
-    CU(t->Mall.reserve(nu * p2p::mf::NM, st)); CU(t->Lall.reserve(nu * p2p::mf::NM, st)); CU(t->acc_mid.reserve((size_t)t->npart * 3, st));
-    CU(cudaEventRecord(t->e0, st));
+    const int nl = t->nleaf;
+    const size_t nu = (size_t)nl + t->nnode;
+    CU(t->Mall.reserve(nu * p2p::mf::NM, st));
     if (nl) p2p::mf::p2m_kernel<<<blocks(nl, 128), 128, 0, st>>>(c->leaf.p, nl, t->box.p, t->x[0].p, t->x[1].p, t->x[2].p, c->mass, t->Mall.p);
     for (int lvl = t->nlevel - 1; lvl >= 0; lvl--)
         p2p::mf::m2m_level_kernel<<<blocks(t->lvl_count[lvl], 128), 128, 0, st>>>(t->t_id.p, t->lvl_begin[lvl], t->lvl_count[lvl], t->son.p, nl,
                                                                                   t->box.p, t->Mall.p);
+    CU(cudaGetLastError());
+    return 0;
+}
+// M2L of the last walk's list with the given source trees, then L2L and L2P
+int mid_m2l_down(p2p_ctx* c, p2p_dtree* t, const double* sbox, const double* sM, const long long* sbase, int npeer) {
+    cudaStream_t st = c->stream;
+    const int nl = t->nleaf;
+    const size_t nu = (size_t)nl + t->nnode;
+    CU(t->Lall.reserve(nu * p2p::mf::NM, st)); CU(t->acc_mid.reserve((size_t)t->npart * 3, st));
     CU(cudaMemsetAsync(t->Lall.p, 0, nu * p2p::mf::NM * sizeof(double), st));
     if (t->nm2l) {
         p2p::mf::M2LParams P;
         memset(&P, 0, sizeof P);
-        P.mt = t->mt.p; P.ms = t->ms.p; P.mq = t->mq.p; P.ntask = t->nm2l; P.box = t->box.p; P.sbox = t->box.p; P.sM = t->Mall.p;
+        P.mt = t->mt.p; P.ms = t->ms.p; P.mq = t->mq.p; P.ntask = t->nm2l; P.box = t->box.p; P.sbox = sbox; P.sM = sM;
+        for (int p = 0; p < npeer; p++) P.sbase[p] = sbase[p];
         P.period = t->walk_period; P.rs = c->rs; P.L = t->Lall.p;
         p2p::mf::m2l_kernel<<<blocks(t->nm2l, 128), 128, 0, st>>>(P);
     }
@@ -962,6 +970,58 @@ int p2p_midfield_compute(p2p_ctx* c, int64_t* nm2l) {
     if (nl) p2p::mf::l2p_kernel<<<blocks((long long)nl * 32, 128), 128, 0, st>>>(c->leaf.p, nl, t->box.p, t->Lall.p, t->x[0].p, t->x[1].p, t->x[2].p,
                                                                                  t->acc_mid.p);
     CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// P2M -> M2M -> M2L (tasks of the last walk) -> L2L -> L2P on the device-built tree; the result (fp64, per particle) is
+// added by p2p_download_acc_original.  Single rank (sources are the local tree and its periodic images).
+int p2p_midfield_compute(p2p_ctx* c, int64_t* nm2l) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree (p2p_tree_build)");
+    if (!t->m2l_on) return fail(P2P_ERR_STATE, "enable the M2L lists (p2p_midfield_enable) before the walk");
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(t->e0, st));
+    int r = mid_upward(c, t);
+    if (r) return r;
+    const long long zero = 0;
+    if ((r = mid_m2l_down(c, t, t->box.p, t->Mall.p, &zero, 1))) return r;
+    CU(cudaEventRecord(t->e1, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&t->ms_mid, t->e0, t->e1));
+    t->mid_valid = true;
+    if (nm2l) *nm2l = t->nm2l;
+    return 0;
+}
+
+// multi-rank: the local multipoles (P2M + M2M), copied to d_M [(nleaf + nnode)][20] (device) for an all-gather ...
+int p2p_midfield_multipoles(p2p_ctx* c, void* d_M) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree");
+    int r = mid_upward(c, t);
+    if (r) return r;
+    if (d_M) CU(cudaMemcpyAsync(d_M, t->Mall.p, ((size_t)t->nleaf + t->nnode) * p2p::mf::NM * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+// ... and M2L -> L2L -> L2P with the multipoles and boxes of ALL ranks (concatenated in rank order like the arrays of
+// p2p_tree_walk_peers, whose M2L list is used)
+int p2p_midfield_compute_peers(p2p_ctx* c, int npeer, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
+                               const void* d_M_all, int64_t* nm2l) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree");
+    if (!t->m2l_on) return fail(P2P_ERR_STATE, "enable the M2L lists (p2p_midfield_enable) before the walk");
+    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || !peer_nleaf || !peer_nnode || !d_box_all || !d_M_all) return fail(P2P_ERR_ARG, "bad peer arrays");
+    long long sbase[p2p::dt::kMaxPeers], ub = 0;
+    for (int p = 0; p < npeer; p++) { sbase[p] = ub; ub += (long long)peer_nleaf[p] + peer_nnode[p]; }
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(t->e0, st));
+    int r = mid_m2l_down(c, t, reinterpret_cast<const double*>(d_box_all), reinterpret_cast<const double*>(d_M_all), sbase, npeer);
+    if (r) return r;
     CU(cudaEventRecord(t->e1, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&t->ms_mid, t->e0, t->e1));

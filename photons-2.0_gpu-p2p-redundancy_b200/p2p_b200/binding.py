@@ -89,6 +89,8 @@ def load_library():
     L.p2p_resident_download.argtypes = [C.c_void_p, _dp, _dp, _lp]
     L.p2p_midfield_enable.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.p2p_midfield_compute.argtypes = [C.c_void_p, _lp]
+    L.p2p_midfield_multipoles.argtypes = [C.c_void_p, C.c_void_p]
+    L.p2p_midfield_compute_peers.argtypes = [C.c_void_p, C.c_int, _ip, _ip, C.c_void_p, C.c_void_p, _lp]
     L.p2p_midfield_download.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
     L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_tree_walk_peers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
@@ -419,6 +421,16 @@ class P2PContext:
     def midfield_compute(self):
         n = C.c_int64()
         self._chk(self._L.p2p_midfield_compute(self._h, C.byref(n)))
+        return n.value
+
+    def midfield_multipoles(self, d_M):
+        self._chk(self._L.p2p_midfield_multipoles(self._h, d_M))
+
+    def midfield_compute_peers(self, peer_nleaf, peer_nnode, d_box_all, d_M_all):
+        nl, nn = _i32(peer_nleaf), _i32(peer_nnode)
+        n = C.c_int64()
+        self._chk(self._L.p2p_midfield_compute_peers(self._h, len(nl), nl.ctypes.data_as(_ip), nn.ctypes.data_as(_ip), d_box_all, d_M_all,
+                                                     C.byref(n)))
         return n.value
 
     def midfield_download(self):

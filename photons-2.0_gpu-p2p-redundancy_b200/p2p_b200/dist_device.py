@@ -57,9 +57,11 @@ def _stream_of(ctx, dev):
 
 
 def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl, bdr, direct_start, theta=0.4, periodic=True,
-                    truncated=True, group=None, acc_out=None, timings=None):
+                    truncated=True, group=None, acc_out=None, timings=None, midfield=False, literal_d6=False, p2p=True):
     """One rank's part of the step.  local_pos: this rank's particles (host, float64, caller's order; pinned for full
     PCIe rate); bdl/bdr/direct_start: its domain box and first split direction (host.domain_setup).
+    midfield: also the multipole part (P2M/M2M on every rank, all-gather of the multipoles, M2L/L2L/L2P); literal_d6 and
+    p2p=False are test knobs (replay the reference's zero-shift self exchange; skip the P2P forces).
     Returns (acc in the order of local_pos, ntask, npairs)."""
     dev = torch.device("cuda", ctx.device)
     stream = _stream_of(ctx, dev)
@@ -69,8 +71,9 @@ def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl,
     ctx.set_box([0.0, 0.0, 0.0], box)
     bdl, bdr = np.asarray(bdl, np.float64), np.asarray(bdr, np.float64)
     with torch.cuda.stream(stream):
+        ctx.midfield_enable(midfield, literal_d6)
         ctx.tree_build(local_pos, maxleaf, bdl, bdr, direct_start)
-        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings)
+        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings, midfield, p2p)
         acc = ctx.download_acc_original(acc_out)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
@@ -132,7 +135,7 @@ def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside,
     return acc, idx, ntask, npairs
 
 
-def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings):
+def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings, midfield=False, p2p=True):
     """after the tree build: topology all-gather, walk against every rank's tree, halo fetch, packing, forces"""
     P, me = dist.get_world_size(group), dist.get_rank(group)
     if True:
@@ -160,6 +163,10 @@ def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group
         leaves = _all_gather_v(leaf_t, [2 * a for a in nls], group)
         box_all, son_all = torch.cat(boxes), torch.cat(sons)
         tb_all = torch.cat(_all_gather_v(tb_t, [6 * a for a in nls], group))
+        if midfield:
+            M_t = torch.empty((nl + nn) * 20, dtype=torch.float64, device=dev)
+            ctx.midfield_multipoles(M_t.data_ptr())
+            M_all = torch.cat(_all_gather_v(M_t, [(a + b) * 20 for a, b in zip(nls, nns)], group))
         t2 = time.perf_counter()
         # ---- lists: my tree against every rank's tree, all displacements
         ctx.clear_tasks()
@@ -199,8 +206,11 @@ def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group
         t4 = time.perf_counter()
         # ---- pack, forces
         ctx.build_csr()
-        ctx.compute()
+        if p2p:
+            ctx.compute()
         ntask, npairs = ctx.counts()
+        if midfield:
+            ctx.midfield_compute_peers(nls, nns, box_all.data_ptr(), M_all.data_ptr())
     t5 = time.perf_counter()
     if timings is not None:
         ms_force, ms_csr = ctx.last_timings()

@@ -145,3 +145,56 @@ def test_device_routing_then_step(demo_pos, world):
     d = np.linalg.norm(acc - want, axis=1)
     na = np.linalg.norm(want, axis=1)
     assert (d / np.maximum(na, na.mean())).max() < 1e-5
+
+
+def _mid_worker(rank, world, port, pos, maxleaf, theta, q):
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import p2p_b200
+    from p2p_b200 import dist as pdist
+    from p2p_b200 import dist_device
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    lp, lidx, tcenter, twidth, direct, dom = pdist.decompose(pos, DEMO_BOX, None)
+    c, w = tcenter[dom], twidth[dom]
+    ctx = p2p_b200.P2PContext(0)
+    acc, ntask, npairs = dist_device.run_device_step(ctx, lp, pos.shape[0], DEMO_BOX, maxleaf, DEMO_NSIDE, 1.0, c - 0.5 * w, c + 0.5 * w,
+                                                     int(direct[dom]), theta, periodic=True, truncated=True, midfield=True,
+                                                     literal_d6=True, p2p=False)
+    q.put((rank, lidx, acc))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_device_multirank_midfield_matches_the_reference(demo_pos):
+    """two ranks: multipoles all-gathered, M2L against the other rank's tree and all images; against the reference's
+    own operators run as two ranks (P2P stubbed to zero, zero-shift self exchange replayed)"""
+    import refrun
+    if not os.path.isfile(refrun.REF_BIN):
+        pytest.skip("oracle/_ref/ref_lists not built")
+    world, maxleaf, theta = 2, 2, 1.0
+    pos = demo_pos[::4].copy()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mid_worker, args=(r, world, port, pos, maxleaf, theta, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((item[0], item[1:]) for item in (q.get(timeout=600) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = refrun.run(pos, DEMO_BOX, maxleaf, DEMO_NSIDE, theta, True, world)
+    acc = np.zeros((len(pos), 3))
+    want = np.zeros((len(pos), 3))
+    for r in range(world):
+        lidx, a = got[r]
+        acc[lidx] = a
+        want[ref[r]["part_orig_index"]] = ref[r]["acc_mid"].reshape(-1, 3)
+    assert np.abs(want).max() > 0
+    assert np.linalg.norm(acc - want, axis=1).max() < 1e-10 * np.linalg.norm(want, axis=1).mean()
