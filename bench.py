@@ -396,7 +396,7 @@ def main():
                            else {"generate": t_gen, "lists_total": t_lists}),
             "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pair/s", "h2d_bytes_per_step": all_h2d,
                     "d2h_bytes_per_step": all_d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "csr_pack_ms": csr_ms},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,       # per timed step: p2p_rows_kernel + add_counter_kernel (the pair count), on this rank
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": 1.35e9 if (not distributed and args.nside == 256 and args.maxleaf == 32 and not args.clustered) else None,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload (profiles/r1e_ncu_rows_kernel_256_final.txt); null for other workloads", "kernel": "p2p_rows_kernel<TT=16,NSRC=2,STAGE=384,trunc,packed(FFMA2),4 blocks/SM,split polynomial>", "kernel_ms": kernel_ms,
