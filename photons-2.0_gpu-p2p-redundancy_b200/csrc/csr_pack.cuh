@@ -210,15 +210,43 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
 // fullest (most expensive) rows go first, so the tail of the persistent kernel consists of cheap rows.
 // Ordering the WHOLE list by n_t instead swept the particle array once per occupancy value: 8.5 GB of DRAM reads per
 // launch at 256^3 against 1 GB of compulsory traffic (ncu, profiles/r1e_ncu_rows_kernel_256_final.txt).
-__global__ void work_bucket_offsets_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor, int nband,
-                                           unsigned int* __restrict__ n_active) {
-    // nband: upper bound (rows / kMinBandRows + 1); bands beyond the real count are empty
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned int run = 0;
-        for (int band = 0; band < nband; band++)
-            for (int b = kWorkBuckets - 1; b >= 0; b--) { cursor[band * kWorkBuckets + b] = run; run += hist[band * kWorkBuckets + b]; }
-        *n_active = run;
+__global__ void __launch_bounds__(1024) work_bucket_offsets_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor,
+                                                                  int nband, unsigned int* __restrict__ n_active) {
+    // nband: upper bound (rows / kMinBandRows + 1); bands beyond the real count are empty.  Exclusive scan of the histogram
+    // in schedule order (band major, fullest occupancy first) by one block.
+    __shared__ unsigned int ws[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int n = nband * kWorkBuckets;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int slot = i < n ? (i / kWorkBuckets) * kWorkBuckets + (kWorkBuckets - 1 - i % kWorkBuckets) : 0;
+        const unsigned int v = i < n ? hist[slot] : 0;
+        unsigned int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const unsigned int w = ws[threadIdx.x];
+            unsigned int z = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, z, o);
+                if (threadIdx.x >= o) z += y;
+            }
+            ws[threadIdx.x] = z - w;
+        }
+        __syncthreads();
+        const unsigned int excl = carry + ws[threadIdx.x >> 5] + x - v;
+        if (i < n) cursor[slot] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *n_active = carry;
 }
 __global__ void work_order_scatter_kernel(const unsigned long long* __restrict__ row_work, const int2* __restrict__ nt_of,
                                           int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order, const int* __restrict__ band_rows_p) {

@@ -485,7 +485,7 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
         int* d_band = reinterpret_cast<int*>(L.whist->p + 2 * (size_t)p2p::kWorkBuckets * nband);
         p2p::band_rows_kernel<<<1, 32, 0, st>>>(c->d_occ, nrow, c->num_sm * 16, band_rows(), d_band);
         p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p, d_band);
-        p2p::work_bucket_offsets_kernel<<<1, 32, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets * nband, nband, L.d_counter + 2);
+        p2p::work_bucket_offsets_kernel<<<1, 1024, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets * nband, nband, L.d_counter + 2);
         p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p, c->leaf.p, nrow,
                                                                           L.whist->p + p2p::kWorkBuckets * nband, L.order->p, d_band);
         CU(cudaGetLastError());
