@@ -1,7 +1,7 @@
 """Quick GPU sanity run (development aid): demo IC, oracle lists, CUDA forces vs fp64 oracle."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200"))
 import oracle, p2p_b200
 pos = np.load(os.path.join(ROOT, "tests/golden/demo_lcdm_pos_f32.npy")).astype(np.float64)

@@ -2,7 +2,7 @@
 sm_100a) timed beside this repository's paths on the same box and the same input: the bundled demo IC (32^3 particles,
 MAXLEAF 16, local list only -- the one configuration the reference kernel can run: SURVEY defects D2, D3, D7).
 Timing row only: the reference kernel skips task 0 and adds an uninitialised result slot (D1).
-usage: python tools/ref_gpu_compare.py            (on a GPU box; prints one JSON object)"""
+usage: python tests/tools/ref_gpu_compare.py            (on a GPU box; prints one JSON object)"""
 import json
 import os
 import re
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")]
 import p2p_b200  # noqa: E402
 from p2p_b200 import host  # noqa: E402
