@@ -4,17 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  the CPU arm (fp64 oracle port, all host threads)
 
-Workload: synthetic LambdaCDM-like box (grid + Gaussian displacement, seed 20250101), 256^3
-particles by default (BASELINE configs[1]), MAXLEAF 32, theta 0.4, erfc-truncated kernel, the 26
-periodic images included.  N = 1: the whole box on one GPU.  N > 1: the SAME box split by the
-reference's rank kd-tree (strong scaling), halos exchanged once per step setup over NCCL; every rank
-computes the forces of the particles it owns, no data-path collective.
+Workload: synthetic LambdaCDM-like box (grid + Gaussian displacement, seed 20250101), 256^3 particles by default
+(BASELINE configs[1]), MAXLEAF 32, theta 0.4, erfc-truncated kernel, the 26 periodic images included.  N = 1: the whole
+box on one GPU.  N > 1: the SAME box split by the reference's rank kd-tree (strong scaling); every rank generates only the
+slab of the global particle array it starts from, the slabs are routed on the devices, and every rank computes the forces
+of the particles it owns.
 
-A step = one pass of the hot path over the whole list: `value` times the force kernel with all inputs
-resident in HBM; `e2e` times the reference-facing C-ABI sequence with HOST (pinned) buffers: H2D of
-positions / leaves / tasks / ghosts, device CSR packing, force kernel, D2H of accelerations.
-The lists (tree build, dual-tree walk, halo images) are produced on the host by libp2p_host.so
-BEFORE the timed region; their wall times are reported in config.host_setup_s.
+A step = one short-range step of the hot path, EVERYTHING per-step inside the timed region at every N:
+  value : particles resident in HBM (in the order the previous step left them) -> tree build, dual-tree walk (own tree +
+          26 images), [N > 1: topology all-gather, walk against the other ranks' trees, leaf-granular halo exchange over
+          NCCL], list packing, force kernels.  Device time (CUDA events), max over ranks.
+  e2e   : the same step through the reference-facing call with HOST buffers: pinned host positions in (H2D), pinned host
+          accelerations out (D2H), wall clock between barriers, max over ranks.
+  roofline : the force kernel alone (library events around its launches), 38 flop per pair against the FP32 FMA peak.
 """
 import argparse
 import json
@@ -77,13 +79,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def make_workload(nside, clustered=False):
+def generate(args, lo, hi):
     from p2p_b200 import synth
-    if clustered:
-        pos, box = synth.clustered(nside)
-    else:
-        pos, box = synth.zeldovich_like(nside)
-    return pos, box, synth.DEMO_MASS
+    gen = synth.clustered_slab if args.clustered else synth.zeldovich_slab
+    return gen(args.nside, lo, hi)
+
+
+def workload_config(args, box):
+    return {"workload": f"{args.nside}^3 particles {'clustered (Zeldovich + NFW-like clumps)' if args.clustered else 'Zeldovich-like (grid + sigma 0.2 spacing)'}"
+                        f", box {box:g} h^-1 kpc, MAXLEAF {args.maxleaf}, theta {THETA}, NSIDE {args.nside}, erfc-truncated kernel, "
+                        f"local list + 26 periodic images", "nside": args.nside, "maxleaf": args.maxleaf, "seed": 20250101,
+            "l2_policy": "inputs larger than L2 (particles + CSR columns >> 126 MB); no flush between steps"}
+
+
+def host_lists(args, pos, box, nthreads):
+    from p2p_b200 import step
+    return step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=nthreads)
 
 
 def sample_rows_for_cpu(L, target_pairs):
@@ -102,7 +113,8 @@ def sample_rows_for_cpu(L, target_pairs):
 
 
 def cpu_oracle_rate(L, mass, target_pairs, nthreads):
-    """fp64 oracle (the CPU port of the reference's pair arithmetic) on a bounded sample of rows."""
+    """fp64 oracle (the CPU port of the reference's pair arithmetic) on a bounded sample of rows.
+    Returns (pair/s, pairs, rows, seconds, threads, accelerations [tree order; only the sampled rows are filled])."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     T = L.tree
@@ -116,7 +128,7 @@ def cpu_oracle_rate(L, mass, target_pairs, nthreads):
         _, n2 = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, L.ghost_pos, L.ghost_count, L.ghost_start, gtt, gts, mass,
                            L.params["eps"], L.params["rs"], acc=acc, nthreads=nthreads)
     dt = time.perf_counter() - t0
-    return (n1 + n2) / dt, n1 + n2, nrow, dt, oracle.max_threads() if nthreads <= 0 else nthreads
+    return (n1 + n2) / dt, n1 + n2, nrow, dt, oracle.max_threads() if nthreads <= 0 else nthreads, acc
 
 
 def run_reference_arm(args):
@@ -125,16 +137,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from p2p_b200 import step
-    pos, box, mass = make_workload(args.nside, args.clustered)
-    L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=os.cpu_count() or 1)
-    rates, tot_pairs, tot_dt = [], 0, 0.0
+    from p2p_b200 import synth
+    pos, box = generate(args, 0, args.nside ** 3)
+    mass = synth.DEMO_MASS
+    L = host_lists(args, pos, box, os.cpu_count() or 1)
+    tot_pairs, tot_dt = 0, 0.0
     # one step = a bounded sample (default 5e9 pairs ~ 9 s on 16 cores) so that W + K steps end within minutes
     per_step_pairs = min(args.cpu_pairs, 5e9)
     for i in range(args.warmup + args.steps):
-        rate, npairs, nrow, dt, threads = cpu_oracle_rate(L, mass, per_step_pairs, os.cpu_count() or 1)
+        rate, npairs, nrow, dt, threads, _ = cpu_oracle_rate(L, mass, per_step_pairs, os.cpu_count() or 1)
         if i >= args.warmup:
-            rates.append(rate); tot_pairs += npairs; tot_dt += dt
+            tot_pairs += npairs; tot_dt += dt
     value = tot_pairs / tot_dt
     out = {
         "impl": "reference", "metric": "P2P pair-interactions/s", "value": value, "unit": "pair/s", "n_gpus": args.gpus,
@@ -149,11 +162,33 @@ def run_reference_arm(args):
     print_json(out)
 
 
-def workload_config(args, box):
-    return {"workload": f"{args.nside}^3 particles {'clustered (Zeldovich + NFW-like clumps)' if args.clustered else 'Zeldovich-like (grid + sigma 0.2 spacing)'}"
-                        f", box {box:g} h^-1 kpc, MAXLEAF {args.maxleaf}, theta {THETA}, NSIDE {args.nside}, erfc-truncated kernel, "
-                        f"local list + 26 periodic images", "nside": args.nside, "maxleaf": args.maxleaf, "seed": 20250101,
-            "l2_policy": "inputs larger than L2 (particles + CSR columns >> 126 MB); no flush between steps"}
+def count_kernels(fn):
+    """kernels of this process launched by one call of fn (CUPTI through torch.profiler); NCCL's own kernels are listed apart"""
+    import torch
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if str(e.device_type).endswith("CUDA") and not e.name.startswith(("Memcpy", "Memset"))]
+        ours = [n for n in names if "nccl" not in n.lower()]
+        return len(ours), len(names) - len(ours)
+    except Exception as e:  # pragma: no cover
+        print(f"[bench] kernel count unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+        return None, None
+
+
+def roofline_traffic(args, world):
+    """DRAM bytes of one launch of the force kernel at this workload, from the committed ncu capture (profiles/)"""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.isfile(path):
+        return None, "no ncu capture committed for this workload"
+    with open(path) as f:
+        tab = json.load(f)
+    key = f"{args.nside}{'c' if args.clustered else ''}_ml{args.maxleaf}_n{world}"
+    if key in tab:
+        return tab[key]["dram_bytes"], tab[key]["source"]
+    return None, f"no ncu capture for {key} in profiles/roofline_traffic.json"
 
 
 def main():
@@ -173,9 +208,10 @@ def main():
     ap.add_argument("--maxleaf", type=int, default=32)
     ap.add_argument("--clustered", action="store_true")
     ap.add_argument("--cpu-pairs", type=float, default=1.5e10, help="pairs in the CPU baseline sample")
-    ap.add_argument("--chunks", type=int, default=16, help="target chunks of the list (groups of the pipelined host step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-full-step", action="store_true", help="skip the walk/compute pipeline measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (sizes whose positions do not fit pinned host memory)")
+    ap.add_argument("--no-overlap", action="store_true", help="remote phase on the compute stream (A/B of the halo overlap)")
+    ap.add_argument("--relax", type=int, default=0, help="work-weighted split relaxations before the timed region (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -185,8 +221,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from p2p_b200 import step
-    from p2p_b200 import dist as pdist
+    import p2p_b200
+    from p2p_b200 import dist_device, host, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,232 +230,206 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the P2P library has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    # ---------------------------------------------------------------- host setup (untimed)
-    t0 = time.perf_counter()
-    pos, box, mass = make_workload(args.nside, args.clustered)
-    t_gen = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    # torchrun exports OMP_NUM_THREADS=1; the host producers take an explicit thread count instead
-    nthreads = max(1, (os.cpu_count() or 1) // world)
-    if distributed:
-        L = pdist.build_lists(pos, box, args.maxleaf, args.nside, THETA, nthreads=nthreads)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 or "RANK" in os.environ:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)      # NCCL's kernels outrank the force kernel
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     else:
-        L = step.build_lists(pos, box, args.maxleaf, args.nside, THETA, periodic=True, nthreads=nthreads, nchunks=args.chunks)
-    t_lists = time.perf_counter() - t0
-    T = L.tree
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29512")
+        dist.init_process_group("gloo", rank=0, world_size=1)                   # one rank: no collective is ever issued
+    nvtx = torch.cuda.nvtx
 
-    st = step.ShortRangeStep(local_rank)
-    ctx = st.ctx
-    # a dedicated torch stream (the legacy default stream has handle 0, which the C-ABI reads as "own stream"):
-    # the kernels are launched on it and the torch events below are recorded on it
-    stream = torch.cuda.Stream()
+    # ---------------------------------------------------------------- setup (untimed): slab, routing, resident particles
+    npart = args.nside ** 3
+    box = synth.box_for(args.nside)
+    mass = synth.DEMO_MASS
+    rs, rcut, eps = host.derived_params(box, args.nside, npart)
+    t0 = time.perf_counter()
+    lo, hi = npart * rank // world, npart * (rank + 1) // world
+    slab, _ = generate(args, lo, hi)
+    t_gen = time.perf_counter() - t0
+    split = host.domain_setup(world, box)[0]
+    ctx = p2p_b200.P2PContext(local_rank)
+    ctx.set_physics(mass, eps, rs)
+    ctx.set_box([0.0, 0.0, 0.0], box)
+    S = dist_device._streams_of(ctx)
+    stream = S.main
     torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
+    overlap = not args.no_overlap
 
-    # pinned host buffers for the e2e leg
-    def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t, t.numpy()
-    keep = []
-    hp = {}
-    for name, arr in (("pos", T.pos), ("leaf_npart", T.leaf_npart), ("leaf_ipart", T.leaf_ipart), ("tt", L.tt), ("ts", L.ts),
-                      ("gpos", L.ghost_pos.reshape(-1, 3)), ("gstart", L.ghost_start), ("gcount", L.ghost_count), ("gtt", L.gtt),
-                      ("gts", L.gts)):
-        t, v = pin(arr)
-        keep.append(t)
-        hp[name] = v
-    acc_t = torch.empty((T.npart, 3), dtype=torch.float64).pin_memory()
-    acc_host = acc_t.numpy()
-    h2d = sum(hp[k].nbytes for k in hp)
-    d2h = acc_host.nbytes
-
-    ctt, cts, coff = step.chunked_task_arrays(L)
-    t1_, ctt = pin(ctt)
-    t2_, cts = pin(cts)
-    keep += [t1_, t2_]
-    h2d = sum(hp[k].nbytes for k in ("pos", "leaf_npart", "leaf_ipart", "gpos", "gstart", "gcount")) + ctt.nbytes + cts.nbytes
-
-    def resident_setup():
-        """everything on the device, ONE CSR over the whole list: the state the kernel-only leg times"""
-        ctx.set_physics(mass, L.params["eps"], L.params["rs"])
-        ctx.set_box([0.0, 0.0, 0.0], box)
-        ctx.upload_particles(hp["pos"])
-        ctx.upload_leaves(hp["leaf_npart"], hp["leaf_ipart"])
-        ctx.clear_tasks()
-        ctx.append_tasks(hp["tt"], hp["ts"])
-        if len(hp["gtt"]):
-            first = ctx.append_ghosts(hp["gpos"], hp["gstart"], hp["gcount"])
-            ctx.append_tasks(hp["gtt"], hp["gts"], source_offset=first)
-        ctx.build_csr()
-
-    def e2e_step():
-        """the reference-facing call: host (pinned) buffers in, host accelerations out; H2D + packing of list
-        group g+1 overlap the kernel of group g (p2p_step_host_chunked)"""
-        ctx.set_physics(mass, L.params["eps"], L.params["rs"])
-        ctx.set_box([0.0, 0.0, 0.0], box)
-        ctx.step_host_chunked(hp["pos"], hp["leaf_npart"], hp["leaf_ipart"], ctt, cts, coff, hp["gpos"], hp["gstart"],
-                              hp["gcount"], acc=acc_host)
+    def domain():
+        center, width, direct = host.domain_boxes(world, box, split)
+        dom = host.domain_of_rank(world, rank)
+        return center[dom] - 0.5 * width[dom], center[dom] + 0.5 * width[dom], int(direct[dom])
 
     def barrier():
-        if distributed:
+        if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # resident state for the kernel-only leg
-    resident_setup()
-    ntask, npairs = ctx.counts()
+    t0 = time.perf_counter()
+    ctx.route_load(slab, lo)
+    if world > 1:
+        del slab
+    nloc = dist_device.migrate(ctx, world, split, None, dev)
+    bdl, bdr, direct = domain()
+    tm = {}
 
-    # ---------------------------------------------------------------- value: kernel with resident inputs
-    for _ in range(max(args.warmup, 3)):
-        ctx.zero_acc(); ctx.compute()
+    def resident_step(timings=None):
+        """the timed unit of `value`: particles resident in HBM -> accelerations resident in HBM"""
+        nvtx.range_push("resident_step")
+        ctx.tree_build_resident(args.maxleaf, bdl, bdr, direct)
+        out = dist_device.lists_halo_forces(ctx, rcut, box, bdl, bdr, THETA, True, None, timings, False, True, overlap)
+        nvtx.range_pop()
+        return out
+
+    ntask, npairs = resident_step()
+    history = []
+    for _ in range(args.relax if world > 1 else 0):
+        # the reference's feedback (1_Indexing/src/photoNs.c:295-306): splits move towards equal work, particles migrate
+        w_all = dist_device._gather_host_ints([ntask], None, dev)[:, 0].astype(np.float64)
+        split = host.domain_relax(world, box, split, w_all)
+        nloc = dist_device.migrate(ctx, world, split, None, dev)
+        bdl, bdr, direct = domain()
+        ntask, npairs = resident_step()
+        history.append(float(1.0 - w_all.sum() / (world * w_all.max())))
+    t_setup = time.perf_counter() - t0
+
+    # ---------------------------------------------------------------- value: device-resident step, per-step communication inside
+    for _ in range(max(args.warmup, 3) - 1):
+        resident_step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record(stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kernel_ms = []
     for i in range(args.steps):
-        ctx.zero_acc(); ctx.compute()
-        ev[i + 1].record(stream)
+        tm = {}
+        ntask, npairs = resident_step(tm)
+        kernel_ms.append(tm["force_ms"])
+    e1.record(stream)
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    # launch duration of the force kernel alone (library events around the launch, same stream)
-    kernel_ms = ctx.last_timings()[0]
+    value_ms = e0.elapsed_time(e1) / args.steps
+    force_ms = float(np.mean(kernel_ms))
+    breakdown = {k: tm[k] for k in ("build_ms", "walk_ms", "csr_ms", "force_ms", "comm_ms", "remote_walk_ms", "force_local_ms", "force_remote_ms")}
+    ghost_particles, chunks = tm["ghost_particles"], tm["chunks"]
 
-    # ---------------------------------------------------------------- e2e: host buffers through the C-ABI
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    resident_setup()
-    ctx.synchronize()
-    _, csr_ms = ctx.last_timings()
+    # ---------------------------------------------------------------- e2e: host buffers through the public call
+    e2e_ms, e2e_tm, h2d, d2h = None, {}, 0, 0
+    if not args.no_e2e:
+        if world > 1:
+            bufs = [torch.empty(nloc, dtype=torch.float64, device=dev) for _ in range(3)] + [torch.empty(nloc, dtype=torch.int32, device=dev)]
+            ctx.route_export(*[b.data_ptr() for b in bufs])
+            hpos_t = torch.stack(bufs[:3], dim=1).cpu().pin_memory()         # this rank's particles, as a host code would hold them
+            del bufs
+        else:
+            hpos_t = torch.from_numpy(slab).pin_memory()                     # the box in the order it was generated
+            del slab
+        hpos, acc_t = hpos_t.numpy(), torch.empty((nloc, 3), dtype=torch.float64).pin_memory()
+        h2d, d2h = hpos.nbytes, acc_t.numpy().nbytes
+
+        def e2e_step(timings=None):
+            nvtx.range_push("e2e_step")
+            out = dist_device.run_device_step(ctx, hpos, npart, box, args.maxleaf, args.nside, mass, bdl, bdr, direct, THETA, periodic=True,
+                                              truncated=True, acc_out=acc_t.numpy(), timings=timings, overlap=overlap)
+            nvtx.range_pop()
+            return out
+
+        for _ in range(min(max(args.warmup, 1), 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_tm = {}
+            _, nt2, np2 = e2e_step(e2e_tm)
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        # (N = 1: the e2e tree is built from the generation order, the resident one from the previous step's order; the split
+        # means are sums in those orders, so a leaf pair at the very edge of the cut may differ)
+        assert abs(np2 - npairs) <= 1e-6 * npairs, ((nt2, np2), (ntask, npairs))
     sampler.stop_flag = True
     sampler.join(timeout=2)
-
-    # ---------------------------------------------------------------- full step with the walk/compute pipeline
-    full_step = None
-    if not distributed and not args.no_full_step:
-        ctx2 = step.ShortRangeStep(local_rank).ctx
-        ctx2.set_stream(stream.cuda_stream)
-        acc2 = torch.empty((T.npart, 3), dtype=torch.float64).pin_memory().numpy()
-        res = {}
-        for mode in (False, True, False, True):        # sequential / pipelined, twice: the second pair is reported
-            barrier()
-            t0 = time.perf_counter()
-            _, _, tp, n_t, n_p = step.run_full_step(ctx2, pos, box, args.maxleaf, args.nside, mass, THETA, nchunks=32,
-                                                    periodic=True, nthreads=nthreads, pipelined=mode, acc_out=acc2)
-            barrier()
-            res[mode] = (time.perf_counter() - t0, tp)
-            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
-        # the same step with the list producers on the device (tree build + dual-tree walk kernels)
-        ppos = torch.from_numpy(pos).pin_memory().numpy()
-        dev = None
-        for _ in range(4):
-            barrier()
-            t0 = time.perf_counter()
-            _, td, n_t, n_p = step.run_device_step(ctx2, ppos, box, args.maxleaf, args.nside, mass, THETA, periodic=True, acc_out=acc2)
-            barrier()
-            dev = (time.perf_counter() - t0, td)
-            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
-        del ppos
-        full_step = {"what": "positions in, accelerations out: tree build + dual-tree walk + 26 periodic-image walks + CSR + P2P, one rank",
-                     "device_resident_s": dev[0], "device_resident_breakdown": dev[1],
-                     "host_pipelined_s": res[True][0], "host_pipelined_breakdown": res[True][1],
-                     "host_sequential_s": res[False][0], "host_sequential_breakdown": res[False][1], "host_threads": nthreads,
-                     "note": "device_resident: list producers as CUDA kernels (p2p_step_device); host_*: list producers on the host "
-                             "cores (libp2p_host.so), pipelined = host walks chunk c+1 while the device computes chunk c"}
-        ctx2.close()
-    elif not args.no_full_step:
-        # multi-rank: every rank builds its tree and walks it against the trees of all ranks on its GPU; halo particles
-        # travel leaf-granular over NCCL (p2p_b200/dist_device.py)
-        from p2p_b200 import dist_device
-        lp, _, tcenter, twidth, direct, dom = pdist.decompose(pos, box)
-        c_, w_ = tcenter[dom], twidth[dom]
-        lp_t, lp_pin = pin(lp)
-        ctx2 = step.ShortRangeStep(local_rank).ctx
-        ctx2.set_stream(stream.cuda_stream)
-        acc2 = torch.empty((lp.shape[0], 3), dtype=torch.float64).pin_memory().numpy()
-        dev = None
-        for _ in range(4):
-            tm = {}
-            barrier()
-            t0 = time.perf_counter()
-            _, n_t, n_p = dist_device.run_device_step(ctx2, lp_pin, pos.shape[0], box, args.maxleaf, args.nside, mass, c_ - 0.5 * w_,
-                                                      c_ + 0.5 * w_, int(direct[dom]), THETA, periodic=True, truncated=True,
-                                                      acc_out=acc2, timings=tm)
-            barrier()
-            dev = (time.perf_counter() - t0, tm)
-            assert (n_t, n_p) == (ntask, npairs), ((n_t, n_p), (ntask, npairs))
-        full_step = {"what": "per-rank positions in, accelerations out: tree build + topology all-gather + walk against every rank's tree "
-                             "(27 displacements) + leaf-granular halo fetch (NCCL all-to-all-v) + CSR + P2P; wall time between barriers",
-                     "device_resident_s": dev[0], "rank0_breakdown": dev[1]}
-        ctx2.close()
-    del pos
+    launches, nccl_launches = count_kernels(resident_step)
 
     # ---------------------------------------------------------------- reduce over ranks
-    if distributed:
-        t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        t = torch.tensor([value_ms, e2e_ms or 0.0, force_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kernel_ms_max = t.tolist()
-        s = torch.tensor([npairs, ntask, h2d, d2h, T.npart], dtype=torch.float64, device="cuda")
+        value_ms, e2e_max, force_ms_max = t.tolist()
+        e2e_ms = e2e_max if e2e_ms is not None else None
+        s = torch.tensor([npairs, ntask, h2d, d2h, nloc, ghost_particles], dtype=torch.float64, device=dev)
         mx = s.clone()
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        all_pairs, all_tasks, all_h2d, all_d2h, all_part = [int(x) for x in s.tolist()]
+        all_pairs, all_tasks, all_h2d, all_d2h, all_part, all_ghost = [int(x) for x in s.tolist()]
         imbalance = 1.0 - all_pairs / (world * mx[0].item())       # the reference's definition, 1_Indexing/src/photoNs.c:309
     else:
-        all_pairs, all_tasks, all_h2d, all_d2h, all_part, imbalance, kernel_ms_max = npairs, ntask, h2d, d2h, T.npart, 0.0, kernel_ms
+        all_pairs, all_tasks, all_h2d, all_d2h, all_part, all_ghost, imbalance = npairs, ntask, h2d, d2h, nloc, 0, 0.0
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
         props = torch.cuda.get_device_properties(local_rank)
         fp32_peak = props.multi_processor_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12     # TFLOP/s
-        value = all_pairs * args.steps / (total_ms * 1e-3)
-        # roofline of the dominant kernel: this rank's pairs over its own launch duration
-        achieved = npairs * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
-        algo_bytes = T.npart * 16 + T.npart * 16 + ntask * 4 + (len(L.ghost_pos)) * 16
+        # roofline of the dominant kernel: this rank's pairs over the duration of its force-kernel launches
+        achieved = npairs * FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12
+        algo_bytes = nloc * 32 + ntask * 4 + ghost_particles * 16
+        traffic, traffic_source = roofline_traffic(args, world)
         out = {
-            "metric": "P2P pair-interactions/s", "value": value, "unit": "pair/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": "P2P pair-interactions/s", "value": all_pairs / (value_ms * 1e-3), "unit": "pair/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": value_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, box), parallelism=f"domains{args.gpus}", particles=all_part, tasks=all_tasks,
-                           pairs_per_step=all_pairs, imbalance=imbalance,
-                           host_setup_s={"generate": t_gen, "lists_total": t_lists, **L.timings} if not distributed
-                           else {"generate": t_gen, "lists_total": t_lists}),
-            "e2e": {"value": all_pairs * args.steps / e2e_s, "unit": "pair/s", "h2d_bytes_per_step": all_h2d,
-                    "d2h_bytes_per_step": all_d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "csr_pack_ms": csr_ms},
-            "gpu_launches": 2 * args.steps,       # per timed step: p2p_rows_kernel + add_counter_kernel (the pair count), on this rank
+                           pairs_per_step=all_pairs, imbalance=imbalance, ghost_particles=all_ghost, chunks=chunks,
+                           halo_overlap=bool(overlap and world > 1), relaxations=len(history),
+                           step="resident particles -> tree build + walk + [topology / halo exchange] + packing + forces",
+                           setup_s=round(t_setup, 3), generate_s=round(t_gen, 3)),
+            "step_breakdown_ms": breakdown,
+            "gpu_launches": (launches * args.steps) if launches is not None else None,
+            "gpu_launches_per_step": launches, "nccl_kernels_per_step": nccl_launches,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": 1.35e9 if (not distributed and args.nside == 256 and args.maxleaf == 32 and not args.clustered) else None,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload (profiles/r1e_ncu_rows_kernel_256_final.txt); null for other workloads", "kernel": "p2p_rows_kernel<TT=16,NSRC=2,STAGE=384,trunc,packed(FFMA2),4 blocks/SM,split polynomial>", "kernel_ms": kernel_ms,
-                         "flop_per_pair": FLOP_PER_PAIR,
+                         "traffic": traffic, "traffic_source": traffic_source,
+                         "kernel": "p2p_rows2_kernel<NSRC=1,STAGE=384,trunc,3 blocks/SM> (one pass per row, near + far bodies, FFMA2)",
+                         "kernel_ms": force_ms, "flop_per_pair": FLOP_PER_PAIR,
                          "peak_source": f"{props.multi_processor_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peaks_kind}); "
                                         "the file holds no FP32 figure, SURVEY.md section 8d defines this peak",
-                         "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (kernel_ms * 1e-3) / 1e9,
-                                 "peak_gbs": peaks["hbm_gbs"], "note": "compulsory particle/CSR/acc traffic of one launch; the kernel is FP32-pipe bound"}},
+                         "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (force_ms * 1e-3) / 1e9,
+                                 "peak_gbs": peaks["hbm_gbs"], "note": "compulsory particle/CSR/acc traffic of one step's launches; the kernel is FP32-pipe bound"}},
             "clocks": sampler.result(),
         }
-        if full_step:
-            out["config"]["full_step"] = full_step
-        if not args.no_cpu_baseline and not distributed:
-            rate, npr, nrow, dt, threads = cpu_oracle_rate(L, mass, args.cpu_pairs, os.cpu_count() or 1)
-            rate1, npr1, _, dt1, _ = cpu_oracle_rate(L, mass, max(args.cpu_pairs / 40, 1e8), 1)
+        if e2e_ms is not None:
+            out["e2e"] = {"value": all_pairs / (e2e_ms * 1e-3), "unit": "pair/s", "h2d_bytes_per_step": all_h2d, "d2h_bytes_per_step": all_d2h,
+                          "ms_per_step": e2e_ms, "build_ms": e2e_tm.get("build_ms"), "walk_ms": e2e_tm.get("walk_ms"),
+                          "csr_ms": e2e_tm.get("csr_ms"), "force_ms": e2e_tm.get("force_ms"), "comm_ms": e2e_tm.get("comm_ms"),
+                          "what": "pinned host positions of the rank's particles in, pinned host accelerations out (dist_device.run_device_step)"}
+        if history:
+            out["config"]["imbalance_tasks_history"] = history
+        if not args.no_cpu_baseline and world == 1 and args.nside <= 256 and not args.no_e2e:
+            # the CPU port on the leading rows of the same list; its accelerations double as a parity sample of THIS run
+            pos, _ = generate(args, 0, npart)
+            L = host_lists(args, pos, box, os.cpu_count() or 1)
+            rate, npr, nrow, dt, threads, ref = cpu_oracle_rate(L, mass, args.cpu_pairs, os.cpu_count() or 1)
+            rate1, npr1, _, dt1, _, _ = cpu_oracle_rate(L, mass, max(args.cpu_pairs / 40, 1e8), 1)
             out["cpu_baseline"] = {"value": rate, "unit": "pair/s", "cores": threads, "kind": "port",
-                                   "sample": f"first {nrow} of {T.nleaf} target leaves (complete CSR rows) = {npr} pairs in {dt:.1f} s, "
+                                   "sample": f"first {nrow} of {L.tree.nleaf} target leaves (complete CSR rows) = {npr} pairs in {dt:.1f} s, "
                                              "fp64 oracle (erfc/exp), OpenMP dynamic over target leaves",
                                    "single_thread": {"value": rate1, "unit": "pair/s", "sample": f"{npr1} pairs in {dt1:.1f} s"}}
+            T = L.tree
+            nsel = int(T.leaf_ipart[nrow - 1] + T.leaf_npart[nrow - 1])
+            # the e2e leg left the accelerations in the order of hpos (= pos); the host tree built from the same array is the
+            # device tree bit for bit, so its permutation maps them to the oracle's rows
+            got = acc_t.numpy()[T.perm[:nsel]]
+            d = np.linalg.norm(got - ref[:nsel], axis=1)
+            na = np.linalg.norm(ref[:nsel], axis=1)
+            out["parity"] = {"particles": nsel, "pairs": npr, "tasks_device": int(nt2), "tasks_host_lists": int(len(L.tt) + len(L.gtt)),
+                             "e1_max_err_over_max_of_own_and_mean_force": float((d / np.maximum(na, na.mean())).max()),
+                             "median_err_over_mean_force": float(np.median(d) / na.mean()), "tolerance": 1e-5,
+                             "against": "fp64 oracle on the identical list (the cpu_baseline sample)"}
         print_json(out)
-    if distributed:
+    if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ enum p2p_status {
     P2P_ERR_NODEVICE = -4   /* no CUDA device / driver: there is NO CPU fallback */
 };
 
-#define P2P_MAX_LEAF 32     /* largest TARGET leaf occupancy the kernels accept (ghost source leaves: 512) */
+#define P2P_MAX_LEAF 32     /* largest TARGET leaf occupancy the kernels accept (ghost source leaves: 384) */
 
 /* kernel variants, selectable for the ncu comparisons (default P2P_KERNEL_AUTO) */
 enum p2p_kernel_variant {
@@ -72,11 +72,27 @@ int p2p_set_kernel_variant(p2p_ctx* ctx, int variant);
  * the lists imply must stay below extent / 2 per axis).  Must precede p2p_upload_particles.
  * If never called, the box is derived from the uploaded particles (bounding cube, doubled). */
 int p2p_set_box(p2p_ctx* ctx, const double origin[3], double extent);
-/* kernel tuning knobs for the ncu sweeps: targets per pass (8/16), sources per lane (1/2/4), min
- * resident blocks per SM (3/4; +16 selects the even/odd split polynomial); 0 keeps the default */
+/* kernel tuning knobs for the ncu sweeps; 0 keeps the default.  targets_per_pass 0 / 32: the production kernel (one pass
+ * per row, near and far slice bodies; sources per lane 1 / 2, min resident blocks per SM 3 / 4); 8 / 16: the
+ * first-generation kernel in its final tuning (A/B baseline) */
 int p2p_set_tuning(p2p_ctx* ctx, int targets_per_pass, int sources_per_lane, int min_blocks);
+/* near / far classification of the list (truncated kernel only): a source leaf whose particles are all at
+ * r >= 2 r_s u_far from all particles of the target leaf is evaluated by the cheaper far-field body.
+ * u_far < 0: the default (1.25, what the far-field fit covers); 0: no far class; values below the default are refused */
+int p2p_set_far_threshold(p2p_ctx* ctx, double u_far);
 /* use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
 int p2p_set_stream(p2p_ctx* ctx, void* cuda_stream);
+/* The context owns TWO sets of list buffers (tasks, CSR, row schedule, pair counter, timing events); every list call
+ * works on the current one and this call exchanges them.  A multi-rank step walks and packs its remote (halo) list in
+ * one set, on a second stream, while the force kernel still consumes the local list in the other
+ * (replaces the ping-pong task buffers of 1_Indexing/src/fmm.c:365-400). */
+int p2p_swap_lists(p2p_ctx* ctx);
+/* force kernel blocks: 0 = persistent warps (default); k > 0 = a warp retires after k rows, so that kernels of
+ * higher-priority streams (NCCL, the halo walk) get SM slots while the force kernel runs */
+int p2p_set_force_blocks(p2p_ctx* ctx, int rows_per_warp);
+/* room for ghost leaves / particles behind the local ones, reserved BEFORE a force kernel is in flight (growing the
+ * particle array later would have to wait for it) */
+int p2p_reserve_ghosts(p2p_ctx* ctx, int nghostleaf, int64_t nghost);
 
 /* Local particles in tree order.  pos: npart rows of 3 doubles, consecutive rows `stride_doubles`
  * apart (3 for a packed array, 12 for the reference's Body AoS, 1_Indexing/inc/typesdef.h:48-57).
@@ -118,6 +134,9 @@ int p2p_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
 int p2p_accumulated_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
 /* copies of the device CSR for parity tests: row_ptr[nleaf+1] (int64), col[ntask] (int32) */
 int p2p_download_csr(p2p_ctx* ctx, int64_t* row_ptr, int* col);
+/* near / far class of every CSR column (1 = far, evaluated by the far-field body) and the number of near columns of
+ * every row (a row's near columns come first); NULL skips */
+int p2p_download_csr_class(p2p_ctx* ctx, unsigned char* is_far, int* row_near);
 /* milliseconds spent by the last p2p_compute / p2p_build_csr launch sequence (CUDA events) */
 int p2p_last_timings(p2p_ctx* ctx, float* ms_compute, float* ms_csr);
 
@@ -172,6 +191,20 @@ int p2p_tree_download(p2p_ctx* ctx, int64_t* perm, double* pos_sorted, int* leaf
  * does.  Image sources are listed under their LOCAL leaf id (the fixed-point coordinates wrap to the nearest
  * image; needs box > 2 (r_cut + leaf size), see p2p_csr_duplicates).  Tasks are APPENDED to the context's list. */
 int p2p_tree_walk(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]);
+/* the same walk restricted to the target leaves [leaf_lo, leaf_hi) (leaf_hi <= 0: all): a step can be split into target
+ * chunks whose lists are walked, packed and consumed one after the other, which bounds the list memory (1024^3 on one
+ * GPU lists 6.7e9 tasks); the union over a partition of the leaves is the task multiset of the full walk, and the M2L
+ * list accumulates over the chunks.  Needs a device-built tree. */
+int p2p_tree_walk_range(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                        int leaf_lo, int leaf_hi);
+/* Local lists and forces of the device-built tree in one call: walk (own tree and, with period > 0, its 26 images),
+ * packing and the force kernel (compute != 0), in as many target chunks as keep one chunk's list below the limit of
+ * p2p_set_chunk_tasks (default 2^29 tasks).  Accelerations accumulate; p2p_accumulated_counts gives the totals of the
+ * step, p2p_counts / p2p_download_csr only see the last chunk. */
+int p2p_forces_local(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3], int compute);
+int p2p_set_chunk_tasks(p2p_ctx* ctx, int64_t max_tasks);
+/* device milliseconds of the last step: tree build, walks, packing and force kernels (summed over the chunks) */
+int p2p_step_timings(p2p_ctx* ctx, float* ms_build, float* ms_walk, float* ms_csr, float* ms_force, int* nchunk);
 /* number of sources listed twice in a row of the packed list (0 unless the periodic box is too small) */
 int p2p_csr_duplicates(p2p_ctx* ctx, int64_t* ndup);
 /* accelerations in the ORDER OF THE POSITIONS GIVEN TO p2p_tree_build, packed rows of 3 doubles */
@@ -183,35 +216,45 @@ int p2p_download_acc_original(p2p_ctx* ctx, double* acc);
  * checks every pair it lists). */
 int p2p_step_device(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
                     const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc);
-/* ---- multi-rank device path: one tree per rank, every rank walks its own tree against all of them -----------
- * Replaces fmm_ext / fmm_remote (1_Indexing/src/fmm.c:1026-1145, 1_Indexing/src/remotes.c:740-809): instead of
- * pruning, shipping and re-walking 27 x P halo images, the ranks all-gather their tree TOPOLOGY (boxes + sons, a few
- * MB), each rank walks against every peer tree with the sender-side cuts of prepare_sendtree2 evaluated on the fly,
- * and only the particles of the leaves the lists actually reference travel afterwards (one all-to-all-v).
- * All pointers below are DEVICE pointers owned by the caller (e.g. torch tensors used with torch.distributed). */
-/* box [(nleaf + nnode)][6] doubles {centre, width}, son [nnode][2] ints (leaf l -> l, node n -> nleaf + n),
- * leaf [nleaf] {first particle, count}, bounds [nleaf][6] doubles = tight lo[3], hi[3] of each leaf's particles (for the
- * minimal-image check of a periodic walk); NULL skips */
-int p2p_tree_export(p2p_ctx* ctx, void* d_box, void* d_son, void* d_leaf, void* d_bounds);
-/* peers' exports concatenated in rank order; sources of rank `me` are listed under local leaf ids, those of rank p
- * under nleaf_local + (leaves of the ranks before p, skipping me) + leaf */
-int p2p_tree_walk_peers(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
-                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
-                        const void* d_son_all, const void* d_bounds_all /* may be NULL: no minimal-image check */);
-/* marks[g] = 1 (uint8) for every ghost leaf g (0-based behind the local leaves) that the task list references */
-int p2p_ghost_marks(p2p_ctx* ctx, void* d_marks);
-/* out[offset[l] ...) = fixed-point particles (int4) of every LOCAL leaf l with marks[l] != 0; offset: int64 per leaf */
-int p2p_gather_leaves(p2p_ctx* ctx, const void* d_marks, const void* d_offset, void* d_out);
-/* ghost particles as p2p_gather_leaves of their owners produced them, and the table of ALL ghost leaves
- * (int32 start relative to d_part, int32 count; count 0 for leaves nobody references) */
-int p2p_set_ghosts_device(p2p_ctx* ctx, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf);
+/* ---- multi-rank device path: one tree per rank, every rank walks its own tree against all of them -------------------
+ * Replaces fmm_ext / fmm_remote (1_Indexing/src/fmm.c:1026-1145, 1_Indexing/src/remotes.c:740-809): instead of pruning,
+ * shipping and re-walking 27 x P halo images, the ranks all-gather their tree TOPOLOGY (kd cells, tight leaf bounds, sons,
+ * leaf sizes: no particles), each rank walks against every peer tree with the sender-side cuts of prepare_sendtree2
+ * evaluated on the fly, and only the particles of the leaves the lists actually reference travel afterwards.
+ * All pointers below are DEVICE pointers owned by the caller (e.g. torch tensors used with torch.distributed).
+ * Every rank copies its topology into a block of fixed stride (p2p_topology_stride of the LARGEST tree of the job), one
+ * all_gather_into_tensor collects the P blocks, and p2p_tree_walk_peers_packed walks against them in place.  With
+ * include_me = 0 the rank's own tree is left out: its walk (p2p_tree_walk, own periodic images included) needs no
+ * communication, so the force kernel can work on the local list while topology, remote walk and halo particles are
+ * still on their way (p2p_swap_lists gives the remote list its own buffers).  p2p_set_rank tells the local walk which
+ * peer index this rank has (carried by the M2L tasks). */
+int p2p_set_rank(p2p_ctx* ctx, int rank, int nranks);
+int p2p_topology_stride(int nleaf_max, int nnode_max, int64_t* stride_bytes);
+int p2p_tree_export_packed(p2p_ctx* ctx, void* d_block, int nleaf_max, int nnode_max);
+int p2p_tree_walk_peers_packed(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                               int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_all, int nleaf_max,
+                               int nnode_max, int include_me);
+/* Leaf-granular halo fetch, planned on the device (csrc/halo.cuh); the host only learns the split sizes of the exchange.
+ *  plan_need : marks (one byte per ghost leaf, peers in rank order without me; DEVICE buffer of the caller, to be sent to the
+ *              owners) of the ghost leaves the current list references, the ghost leaf table behind the local leaves, and
+ *              need_total[p] = particles wanted from rank p
+ *  plan_give : d_asked = the marks the nreq = P - 1 other ranks sent (requester-major, nleaf bytes each) ->
+ *              give_total[q] = particles to send to the q-th requester
+ *  gather    : the requested leaves' fixed-point particles (int4), requester-major, into d_send
+ *  set_particles : what arrived (sender-major = ghost leaf order) becomes the ghost particles */
+int p2p_halo_plan_need(p2p_ctx* ctx, const void* d_topo_all, int npeer, int me, const int* peer_nleaf, int nleaf_max, int nnode_max,
+                       void* d_marks, int64_t* need_total);
+int p2p_halo_plan_give(p2p_ctx* ctx, const void* d_asked, int nreq, int64_t* give_total);
+int p2p_halo_gather(p2p_ctx* ctx, const void* d_asked, int nreq, void* d_send);
+int p2p_halo_set_particles(p2p_ctx* ctx, const void* d_recv, int64_t nbody);
 
 /* ---- particle routing on the device (domain_decomposition: prepare_body_inOrderOf_domain + exchange,
  * 1_Indexing/src/domains.c:163-377): the slab a rank holds is partitioned by the rank kd-tree with the reference's
  * in-place partition (same group order, same order inside a group), the groups travel as device buffers, and the
  * tree is built from what arrived -- particles never return to the host between routing and forces. ------------- */
-/* host slab -> resident device arrays; particle i carries the global id first_index + i through the exchange */
-int p2p_route_load(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t n, int64_t first_index);
+/* host slab -> resident device arrays; particle i carries the global id first_index + i through the exchange.
+ * append != 0 adds the piece behind the particles already resident (a slab uploaded piece by piece). */
+int p2p_route_load(p2p_ctx* ctx, const double* pos, int64_t stride, int64_t n, int64_t first_index, int append);
 /* split[2P-1] in heap order (p2p_domain_setup / p2p_domain_relax); P a power of two; sendcount[r] = group size for rank r */
 int p2p_route_partition(p2p_ctx* ctx, int nproc, const double* split, int* sendcount);
 /* copies of / into the resident arrays; DEVICE pointers owned by the caller: x, y, z doubles, idx int32 */
@@ -236,6 +279,8 @@ int p2p_resident_drift(p2p_ctx* ctx, double dd, double period);
 /* current positions / velocities (packed rows of 3 doubles) and ids (particle i of p2p_resident_load has id i), in the
  * resident (tree) order; NULL skips */
 int p2p_resident_download(p2p_ctx* ctx, double* pos, double* vel, int64_t* id);
+/* particles currently resident on this device (after p2p_route_load / _import / p2p_resident_load) */
+int p2p_resident_count(p2p_ctx* ctx, int64_t* n);
 
 /* ---- mid-field on the device: P2M / M2M / M2L / L2L / L2P --------------------------
  * The other half of the short-range FMM force (1_Indexing/src/operator.c; fmm_prepare, task_compute_m2l and the tail
@@ -249,12 +294,12 @@ int p2p_midfield_enable(p2p_ctx* ctx, int on, int literal_d6);
 /* P2M -> M2M -> M2L -> L2L -> L2P for the device-built tree and the last walk (single rank: local tree + periodic
  * images); p2p_download_acc_original then returns P2P + mid-field.  *nm2l: number of M2L tasks. */
 int p2p_midfield_compute(p2p_ctx* ctx, int64_t* nm2l);
-/* multi-rank: the local multipoles (P2M + M2M) copied to d_M [(nleaf + nnode)][20] doubles (DEVICE memory, e.g. for an
- * all-gather next to p2p_tree_export), then M2L -> L2L -> L2P with the boxes and multipoles of ALL ranks (concatenated
- * in rank order like the arrays of p2p_tree_walk_peers, whose M2L list is used) */
+/* multi-rank: the local multipoles (P2M + M2M) copied to d_M [(nleaf + nnode)][20] doubles (DEVICE memory: this rank's
+ * block of an all-gather), then M2L -> L2L -> L2P with the boxes (packed topology blocks) and multipoles (blocks of
+ * (nleaf_max + nnode_max) x 20 doubles) of ALL ranks; the M2L list is the one the local and the remote walk left */
 int p2p_midfield_multipoles(p2p_ctx* ctx, void* d_M);
-int p2p_midfield_compute_peers(p2p_ctx* ctx, int npeer, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
-                               const void* d_M_all, int64_t* nm2l);
+int p2p_midfield_compute_peers_packed(p2p_ctx* ctx, int npeer, const void* d_topo_all, int nleaf_max, int nnode_max, const void* d_M_all,
+                                      int64_t* nm2l);
 /* multipoles and local expansions, [leaf][20] / [node][20] in the reference's coefficient order
  * (1_Indexing/inc/operator.h:24-67); NULL skips; *ms: device time of p2p_midfield_compute */
 int p2p_midfield_download(p2p_ctx* ctx, double* leaf_M, double* node_M, double* leaf_L, double* node_L, float* ms);

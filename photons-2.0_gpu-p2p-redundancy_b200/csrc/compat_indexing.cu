@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include <vector>
 
 #include "../../include/p2p_b200.h"
@@ -89,6 +90,28 @@ int copyMemGPU(double* h_pos, int* h_leaf, int* h_int, int ntasks, int verbosity
     }
     g_first_task.assign((size_t)nleaf, -1);
     for (int n = ntasks - 1; n >= 0; n--) g_first_task[(size_t)h_int[2 * n]] = n;
+    // the fixed-point frame is derived from the VALID slots only (leaf l, j < npart[l]): the padding of the chunked
+    // array is never read by the reference kernel and may hold anything (bounding cube, four times padded)
+    {
+        double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+        bool first = true;
+        for (int l = 0; l < nleaf; l++)
+            for (int j = 0; j < g_leaf_npart[(size_t)l]; j++) {
+                const double* q = h_pos + ((size_t)l * g_max_parts + j) * 3;
+                for (int k = 0; k < 3; k++) {
+                    if (first || q[k] < lo[k]) lo[k] = q[k];
+                    if (first || q[k] > hi[k]) hi[k] = q[k];
+                }
+                first = false;
+            }
+        double w = 0.0;
+        for (int k = 0; k < 3; k++) w = hi[k] - lo[k] > w ? hi[k] - lo[k] : w;
+        if (!(w > 0.0) || !std::isfinite(w)) w = 1.0;
+        const double extent = 4.0 * w;
+        double origin[3];
+        for (int k = 0; k < 3; k++) origin[k] = 0.5 * (lo[k] + hi[k]) - 0.5 * extent;
+        if (p2p_set_box(g_ctx, origin, extent)) { printf("Error copy: %s\n", p2p_last_error()); return -1; }
+    }
     // r_s fixes the position scale, so it is applied before the upload; mass/eps arrive at launch
     if (p2p_set_physics(g_ctx, 1.0, 0.0, g_rs)) { printf("Error copy: %s\n", p2p_last_error()); return -1; }
     if (p2p_upload_particles(g_ctx, h_pos, 3, (int64_t)nleaf * g_max_parts) ||

@@ -106,15 +106,69 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const unsigned int* __r
     if (i0 <= n - 1 && n - 1 < i0 + 8) row_ptr[n] = (long long)run;  // owner of the last item closes the array
 }
 
+// Tight bounds of every leaf's particles in the fixed-point frame: {centre xyz, -} and {half extent xyz, -}, both rounded
+// outwards.  Differences are taken relative to the leaf's first particle, so a leaf that straddles the periodic wrap is
+// handled like any other (a leaf spans far less than half the frame).
+struct LeafBounds {
+    int4 c, h;
+};
+__global__ void leaf_bounds_fixed_kernel(const int2* __restrict__ leaf, int nleaf, const int4* __restrict__ part, LeafBounds* __restrict__ out) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaf) return;
+    const int2 L = leaf[l];
+    LeafBounds b;
+    b.c = make_int4(0, 0, 0, 0);
+    b.h = make_int4(0, 0, 0, 0);
+    if (L.y > 0) {
+        const int4 r = part[L.x];
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int p = L.x + 1; p < L.x + L.y; p++) {
+            const int4 q = part[p];
+            const int d[3] = {q.x - r.x, q.y - r.y, q.z - r.z};          // wraps to the minimal image
+            for (int k = 0; k < 3; k++) { lo[k] = min(lo[k], d[k]); hi[k] = max(hi[k], d[k]); }
+        }
+        const int r3[3] = {r.x, r.y, r.z};
+        int c[3], h[3];
+        for (int k = 0; k < 3; k++) {
+            const long long mid = ((long long)lo[k] + hi[k]) >> 1;       // floor
+            c[k] = (int)((unsigned)r3[k] + (unsigned)(int)mid);
+            h[k] = (int)(((long long)hi[k] - lo[k] + 2) >> 1);           // covers both ends after the floor
+        }
+        b.c = make_int4(c[0], c[1], c[2], 0);
+        b.h = make_int4(h[0], h[1], h[2], 0);
+    }
+    out[l] = b;
+}
+// squared gap between two leaves' bounds, in fixed-point steps (minimal image)
+__device__ __forceinline__ double bounds_gap2(const LeafBounds& a, const LeafBounds& b) {
+    const int d[3] = {b.c.x - a.c.x, b.c.y - a.c.y, b.c.z - a.c.z};
+    const int h[3] = {a.h.x + b.h.x, a.h.y + b.h.y, a.h.z + b.h.z};
+    double g2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const long long g = llabs((long long)d[k]) - (long long)h[k];
+        if (g > 0) g2 += (double)g * (double)g;
+    }
+    return g2;
+}
+
+// Scatter into the CSR rows.  With far2 > 0 (truncated kernel) every column is classified on the way: a source leaf whose
+// bounds are at least sqrt(far2) fixed-point steps from the target leaf's gets bit 31 (the force kernel's cheap far body
+// is valid for every particle pair of such a leaf pair); the unsigned row sort then puts the far columns last.
 __global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
-                                   unsigned long long* __restrict__ cursor, int* __restrict__ col) {
+                                   unsigned long long* __restrict__ cursor, int* __restrict__ col, const LeafBounds* __restrict__ lb,
+                                   double far2) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
         if ((unsigned)t >= (unsigned)nrow || (unsigned)s >= (unsigned)nsrc) continue;
+        unsigned v = (unsigned)s;
+        if (far2 > 0.0) {
+            const LeafBounds a = lb[t], b = lb[s];
+            if (bounds_gap2(a, b) >= far2) v |= 0x80000000u;
+        }
         unsigned long long p = atomicAdd(cursor + t, 1ull);
-        col[p] = s;
+        col[p] = (int)v;
     }
 }
 
@@ -122,10 +176,11 @@ __global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __rest
 constexpr int kSortCap = 2048;
 
 __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __restrict__ row_ptr, int nrow,
-                                                            int* __restrict__ col, unsigned int* __restrict__ unsorted) {
-    __shared__ int sh[4][kSortCap];
+                                                            int* __restrict__ col_, unsigned int* __restrict__ unsorted) {
+    __shared__ unsigned int sh[4][kSortCap];
+    unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);     // unsigned order: far columns (bit 31) last
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int* a = sh[w];
+    unsigned int* a = sh[w];
     for (int row = blockIdx.x * 4 + w; row < nrow; row += gridDim.x * 4) {
         const long long b = row_ptr[row];
         const int len = (int)(row_ptr[row + 1] - b);
@@ -133,13 +188,13 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
         if (len > kSortCap) { if (lane == 0) atomicAdd(unsorted, 1u); continue; }
         int m = 1;
         while (m < len) m <<= 1;
-        for (int i = lane; i < m; i += 32) a[i] = i < len ? col[b + i] : INT_MAX;
+        for (int i = lane; i < m; i += 32) a[i] = i < len ? col[b + i] : 0xffffffffu;
         __syncwarp();
         for (int k = 2; k <= m; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int t = lane; t < (m >> 1); t += 32) {         // one compare-exchange per lane and step: no idle partner lanes
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                    const int x = a[i], y = a[p];
+                    const unsigned int x = a[i], y = a[p];
                     const bool up = (i & k) == 0;
                     if ((x > y) == up) { a[i] = y; a[p] = x; }
                 }
@@ -148,6 +203,33 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
         }
         for (int i = lane; i < len; i += 32) col[b + i] = a[i];
         __syncwarp();
+    }
+}
+
+// Rows above kSortCap columns (dense clumps): one block per row, bitonic network in global memory in the form whose
+// compare-exchanges all put the smaller key at the lower index, so that positions beyond the row's length act as +inf
+// without being stored.
+__global__ void __launch_bounds__(256) csr_sort_long_rows_kernel(const long long* __restrict__ row_ptr, int nrow, int* __restrict__ col_) {
+    unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);
+    for (int row = blockIdx.x; row < nrow; row += gridDim.x) {
+        const long long b = row_ptr[row];
+        const long long len = row_ptr[row + 1] - b;
+        if (len <= kSortCap) continue;
+        long long m = 1;
+        while (m < len) m <<= 1;
+        for (long long k = 2; k <= m; k <<= 1) {
+            for (long long j = k >> 1; j > 0; j >>= 1) {
+                for (long long t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                    const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const long long p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);      // first step of a merge: mirror partner
+                    if (p < len) {
+                        const unsigned int x = col[b + i], y = col[b + p];
+                        if (x > y) { col[b + i] = y; col[b + p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
     }
 }
 
@@ -181,7 +263,8 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
                                                          const int2* __restrict__ leaf, int nrow,
                                                          unsigned long long* __restrict__ npairs,
                                                          unsigned long long* __restrict__ row_work,
-                                                         unsigned int* __restrict__ hist, const int* __restrict__ band_rows_p) {
+                                                         unsigned int* __restrict__ hist, const int* __restrict__ band_rows_p,
+                                                         int* __restrict__ row_mid) {
     const int band_rows = *band_rows_p;
     unsigned long long s = 0;
     const int lane = threadIdx.x & 31;
@@ -190,10 +273,16 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
         const long long b = row_ptr[row], e = row_ptr[row + 1];
         const unsigned long long nt = (unsigned long long)leaf[row].y;
         unsigned long long ns = 0;
-        for (long long i = b + lane; i < e; i += 32) ns += (unsigned long long)leaf[col[i]].y;
-        for (int d = 16; d >= 1; d >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, d);
+        int near = 0;                                    // columns without the far bit: the row's leading part after the sort
+        for (long long i = b + lane; i < e; i += 32) {
+            const unsigned int c = (unsigned int)col[i];
+            ns += (unsigned long long)leaf[c & 0x7fffffffu].y;
+            near += (c >> 31) == 0;
+        }
+        for (int d = 16; d >= 1; d >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, d); near += __shfl_xor_sync(0xffffffffu, near, d); }
         const unsigned long long w = nt * ns;
         if (lane == 0) {
+            row_mid[row] = near;
             row_work[row] = w;
             if (w) atomicAdd(hist + (row / band_rows) * kWorkBuckets + min((int)nt, kWorkBuckets - 1), 1u);
             s += w;

@@ -20,7 +20,7 @@ struct p2p_dtree {
     int maxleaf = 0, nleaf = 0, nnode = 0, cap = 0, direct_start = 0, nlevel = 0;
     bool valid = false, built_here = false;
     DevBuf<double> box;
-    DevBuf<int> son, node_npart, leaf_npart, leaf_ipart;
+    DevBuf<int> son, node_npart, leaf_npart, leaf_ipart, node_leaf0, node_nleaf;
     DevBuf<double> node_split;
     // build
     DevBuf<double> x[3];
@@ -34,6 +34,7 @@ struct p2p_dtree {
     DevBuf<long long> cinc;
     // mid-field (M2L lists from the walk, multipoles, local expansions)
     bool m2l_on = false, literal_d6 = false, mid_valid = false;
+    int self_rank = 0;           // this rank's index among the peers (tags the M2L tasks of the local walk)
     DevBuf<int> mt, ms, mq;
     DevBuf<double> tb;                // tight particle bounds of the local leaves (minimal-image check of the walk)
     long long nm2l = 0;
@@ -62,12 +63,17 @@ struct p2p_dtree {
     bool block_mode = true;
     float ms_build = 0.f, ms_walk = 0.f;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    // p2p_forces_local: sums over its target chunks
+    float sum_walk = 0.f, sum_csr = 0.f, sum_force = 0.f;
+    int last_chunks = 0;
+    long long max_chunk_tasks = 1LL << 29;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 void p2p_dtree_release(p2p_dtree* t) {
     if (!t) return;
     t->box.release(); t->son.release(); t->node_npart.release(); t->leaf_npart.release(); t->leaf_ipart.release();
-    t->node_split.release();
+    t->node_split.release(); t->node_leaf0.release(); t->node_nleaf.release();
     for (int k = 0; k < 3; k++) t->x[k].release();
     t->perm.release(); t->seg.release(); t->seg_next.release(); t->slot.release(); t->flag.release(); t->G.release(); t->tile.release();
     t->t_start.release(); t->t_len.release(); t->t_parent.release(); t->t_np0.release(); t->t_child.release(); t->t_nleaf.release();
@@ -87,6 +93,7 @@ void p2p_dtree_release(p2p_dtree* t) {
     if (t->d_maxw) cudaFree(t->d_maxw);
     if (t->e0) cudaEventDestroy(t->e0);
     if (t->e1) cudaEventDestroy(t->e1);
+    for (cudaEvent_t e : t->chunk_ev) cudaEventDestroy(e);
     delete t;
 }
 
@@ -171,7 +178,7 @@ int p2p_tree_upload(p2p_ctx* c, int maxleaf, int nleaf, int nnode, int first_lea
     CU(cudaMemcpyAsync(t->box.p, box.data(), box.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(t->son.p, son.data(), son.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));           // the staging vectors die here
-    t->npart = c->npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->valid = true; t->built_here = false;
+    t->npart = c->npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->valid = true; t->built_here = false; t->nm2l = 0;
     return 0;
 }
 
@@ -312,17 +319,19 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     CU(t->box.reserve(6 * ((size_t)nleaf + nnode), st));
     CU(t->son.reserve(2 * (size_t)nnode, st));
     CU(t->node_npart.reserve((size_t)nnode, st)); CU(t->node_split.reserve((size_t)nnode, st));
+    CU(t->node_leaf0.reserve((size_t)nnode, st)); CU(t->node_nleaf.reserve((size_t)nnode, st));
     CU(t->leaf_npart.reserve((size_t)nleaf + 1, st)); CU(t->leaf_ipart.reserve((size_t)nleaf + 1, st));
     p2p::dt::TreeOut O;
     O.nleaf = nleaf; O.box = t->box.p; O.son = t->son.p; O.node_npart = t->node_npart.p; O.node_split = t->node_split.p;
     O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p; O.max_width = t->d_maxw;
+    O.node_leaf0 = t->node_leaf0.p; O.node_nleaf = t->node_nleaf.p;
     CU(cudaMemsetAsync(t->d_maxw, 0, sizeof(int), st));
     for (int lvl = 0; lvl < t->nlevel; lvl++)
         p2p::dt::assign_down_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, O, lvl_begin[lvl], lvl_count[lvl], (direct_start + lvl) % 3,
                                                                                bdl[0], bdl[1], bdl[2], bdr[0], bdr[1], bdr[2]);
     CU(cudaGetLastError());
     // ---- hand over to the force path: fixed-point particles in tree order, leaves, zeroed accelerations
-    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false; c->nleaf = nleaf;
+    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false; c->nleaf = nleaf; c->bounds_n = 0;
     CU(c->part.reserve((size_t)npart + 1, st));
     CU(c->acc.reserve((size_t)npart + 1, st));
     CU(c->leaf.reserve((size_t)nleaf + 1, st));
@@ -332,7 +341,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     if (nleaf) p2p::dt::leaf_pack_kernel<<<blocks(nleaf, 256), 256, 0, st>>>(O.leaf_npart, O.leaf_ipart, nleaf, c->leaf.p, t->d_scalar + 1);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), st));
-    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(c->d_npairs_acc, 0, sizeof(unsigned long long), st));
     c->acc_tasks = 0;
     c->max_target_leaf = maxleaf;
     if ((r = p2p_update_occupancy(c))) return r;
@@ -343,7 +352,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     t->max_leaf_width = wmaxf;
     CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
-    t->valid = true; t->built_here = true; t->mid_valid = false;
+    t->valid = true; t->built_here = true; t->mid_valid = false; t->nm2l = 0;
     t->lvl_begin = lvl_begin; t->lvl_count = lvl_count;
     return 0;
 }
@@ -353,25 +362,31 @@ extern "C" {
 
 // ---- particle routing on the device (domain_decomposition: prepare_body_inOrderOf_domain + exchange) -----------------
 // host slab -> resident arrays; perm[i] = first_index + i (the particle's global id, carried through the exchange)
-int p2p_route_load(p2p_ctx* c, const double* pos, int64_t stride, int64_t n, int64_t first_index) {
+int p2p_route_load(p2p_ctx* c, const double* pos, int64_t stride, int64_t n, int64_t first_index, int append) {
     USE(c);
     if (n < 0 || (n && !pos) || stride < 3 || first_index < 0 || first_index + n > 0x7fffffffLL) return fail(P2P_ERR_ARG, "bad slab");
     p2p_dtree* t;
     int r = get_tree(c, &t);
     if (r) return r;
     cudaStream_t st = c->stream;
-    t->valid = false; t->resident = 0;
+    // append != 0: behind the particles already resident (a slab uploaded in pieces, so that neither the host nor the
+    // staging buffer ever holds more than one piece)
+    const long long base = append ? t->resident : 0;
+    if (base + n > 0x7fffffffLL) return fail(P2P_ERR_ARG, "more than 2^31 particles per device");
+    t->valid = false;
+    if (!append) t->resident = 0;
     if (n == 0) return 0;
     CU(c->stage.reserve((size_t)n * 24, st));
     if (stride == 3) CU(cudaMemcpyAsync(c->stage.p, pos, (size_t)n * 24, cudaMemcpyHostToDevice, st));
     else CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, st));
-    for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)n, st));
-    CU(t->perm.reserve((size_t)n, st)); CU(t->seg.reserve((size_t)n, st));
-    p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->x[0].p, t->x[1].p, t->x[2].p,
-                                                                 t->perm.p, t->seg.p);
-    p2p::dt::iota_offset_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n, (int)first_index);
+    for (int k = 0; k < 3; k++) CU(t->x[k].reserve((size_t)(base + n), st, (size_t)base));
+    CU(t->perm.reserve((size_t)(base + n), st, (size_t)base)); CU(t->seg.reserve((size_t)(base + n), st, (size_t)base));
+    p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->x[0].p + base, t->x[1].p + base,
+                                                                 t->x[2].p + base, t->perm.p + base, t->seg.p + base);
+    p2p::dt::iota_offset_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p + base, n, (int)first_index);
     CU(cudaGetLastError());
-    t->resident = n; t->perm_is_local = false;
+    CU(cudaStreamSynchronize(st));              // the caller may reuse `pos` (pageable memory is staged by the driver)
+    t->resident = base + n; t->perm_is_local = false;
     return 0;
 }
 
@@ -420,6 +435,12 @@ int p2p_route_partition(p2p_ctx* c, int nproc, const double* split, int* sendcou
     CU(cudaMemcpyAsync(sendcount, A.t_len + begin, (size_t)nproc * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     dsplit.release();
+    return 0;
+}
+
+int p2p_resident_count(p2p_ctx* c, int64_t* n) {
+    if (!c || !n) return fail(P2P_ERR_ARG, "null pointer");
+    *n = c->dtree ? c->dtree->resident : 0;
     return 0;
 }
 
@@ -516,12 +537,9 @@ int p2p_resident_forces(p2p_ctx* c, int maxleaf, const double bdl[3], const doub
     CU(cudaGetLastError());
     for (int k = 0; k < 3; k++) { std::swap(t->v[k].p, t->vtmp[k].p); std::swap(t->v[k].cap, t->vtmp[k].cap); }
     std::swap(t->gid.p, t->gidtmp.p); std::swap(t->gid.cap, t->gidtmp.cap);
-    if ((r = p2p_clear_tasks(c))) return r;
     double tc[3], tw[3];
     for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }
-    if ((r = p2p_tree_walk(c, theta, rcut, period, tc, tw))) return r;
-    if ((r = p2p_build_csr(c))) return r;
-    return p2p_compute(c);
+    return p2p_forces_local(c, theta, rcut, period, tc, tw, 1);
 }
 
 // vel += acc * dkh for the resident particles (acc of the last p2p_resident_forces)
@@ -660,10 +678,12 @@ namespace {
 // breadth-first walk from the given items; appends the tasks to the context's list
 int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector<ull>& init, size_t task_guess) {
     cudaStream_t st = c->stream;
-    t->mid_valid = false; t->nm2l = 0; t->walk_period = P.period;
+    // the M2L list ACCUMULATES over the walks of one tree (target chunks, local then remote phase); a tree build empties it
+    const size_t m0 = (size_t)t->nm2l;
+    t->mid_valid = false; t->walk_period = P.period;
     if (t->m2l_on) {
-        const size_t mcap = std::max<size_t>(task_guess, 1 << 16);
-        CU(t->mt.reserve(mcap, st)); CU(t->ms.reserve(mcap, st)); CU(t->mq.reserve(mcap, st));
+        const size_t mcap = m0 + std::max<size_t>(task_guess, 1 << 16);
+        CU(t->mt.reserve(mcap, st, m0)); CU(t->ms.reserve(mcap, st, m0)); CU(t->mq.reserve(mcap, st, m0));
     }
     size_t fcap = std::max<size_t>(task_guess / 2, 1 << 16);
     size_t tcap = std::max<size_t>(task_guess, 1 << 16);
@@ -682,8 +702,8 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
             const ull cap_out = t->frontier[cur ^ 1].cap;
             const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
             const unsigned grid = (unsigned)std::min<ull>((n_in + 255) / 256, (ull)c->num_sm * 16);
-            P.mt = t->m2l_on ? t->mt.p : nullptr; P.ms = t->ms.p; P.mq = t->mq.p;
-            P.cap_m2l = t->m2l_on ? std::min(t->mt.cap, std::min(t->ms.cap, t->mq.cap)) : 0;
+            P.mt = t->m2l_on ? t->mt.p + m0 : nullptr; P.ms = t->ms.p + m0; P.mq = t->mq.p + m0;
+            P.cap_m2l = t->m2l_on ? std::min(t->mt.cap, std::min(t->ms.cap, t->mq.cap)) - m0 : 0;
             p2p::dt::walk_level_kernel<<<grid, 256, 0, st>>>(t->frontier[cur].p, n_in, t->frontier[cur ^ 1].p, cap_out, t->d_wcount,
                                                              c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, P);
             CU(cudaGetLastError());
@@ -692,8 +712,8 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
             const ull n_out = t->h_wcount[0], nt = t->h_wcount[1], nm = t->h_wcount[2];
             if (n_out <= cap_out && nt <= cap_task && nm <= P.cap_m2l) { items += n_in; n_in = n_out; ntask = nt; nm2l = nm; nviol = t->h_wcount[3]; break; }
             if (nm > P.cap_m2l) {
-                const size_t want = (size_t)(nm + nm / 2);
-                CU(t->mt.reserve(want, st, (size_t)nm2l)); CU(t->ms.reserve(want, st, (size_t)nm2l)); CU(t->mq.reserve(want, st, (size_t)nm2l));
+                const size_t want = m0 + (size_t)(nm + nm / 2);
+                CU(t->mt.reserve(want, st, m0 + (size_t)nm2l)); CU(t->ms.reserve(want, st, m0 + (size_t)nm2l)); CU(t->mq.reserve(want, st, m0 + (size_t)nm2l));
             }
             // a buffer was too small: grow it and repeat this level from the same input
             if (n_out > cap_out) CU(t->frontier[cur ^ 1].reserve((size_t)(n_out + n_out / 4), st));
@@ -715,7 +735,7 @@ int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector
     c->ntask += (long long)ntask;
     c->csr_valid = false;
     t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
-    t->nm2l = (long long)nm2l;
+    t->nm2l = (long long)(m0 + nm2l);
     if (nviol)
         return fail(P2P_ERR_ARG, "%llu listed leaf pair(s) span half the period or more: the periodic box is too small for minimal-image "
                     "sources (needs roughly box > 2 (r_cut + 2 leaf widths))", nviol);
@@ -751,136 +771,126 @@ extern "C" {
 // are listed under their LOCAL leaf id: the fixed-point coordinates wrap to the nearest image.  Tasks are appended to
 // the context's list (p2p_build_csr packs them).
 int p2p_tree_walk(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3]) {
+    return p2p_tree_walk_range(c, theta, rcut, period, tcenter, twidth, 0, 0);
+}
+
+// the same walk restricted to the target leaves [leaf_lo, leaf_hi) (leaf_hi <= 0: all of them)
+int p2p_tree_walk_range(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                        int leaf_lo, int leaf_hi) {
     USE(c);
     int r = walk_checks(c, theta, rcut, period, tcenter, twidth);
     if (r) return r;
     p2p_dtree* t = c->dtree;
     const int nleaf = t->nleaf;
     if (nleaf == 0) return 0;
+    if (leaf_hi > 0 && (!t->built_here || leaf_lo < 0 || leaf_lo >= leaf_hi || leaf_hi > nleaf))
+        return fail(P2P_ERR_ARG, "bad target range [%d, %d) (needs a device-built tree with %d leaves)", leaf_lo, leaf_hi, nleaf);
     if (period > 0.0 && t->npart <= t->maxleaf)
         return fail(P2P_ERR_ARG, "image walk of a tree whose root holds <= maxleaf particles is undefined in the reference");
     p2p::dt::WalkParams P;
     memset(&P, 0, sizeof P);
     P.box = t->box.p; P.son = t->son.p; P.nleaf = nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
     for (int k = 0; k < 3; k++) { P.tc[k] = tcenter ? tcenter[k] : 0.0; P.tw[k] = twidth ? twidth[k] : 0.0; }
-    P.sbox = t->box.p; P.sson = t->son.p; P.me = 0; P.npeer = 1; P.snleaf[0] = nleaf;
+    const int me = t->self_rank;              // 0 unless p2p_set_rank said otherwise: the peer index the M2L tasks carry
+    P.sbox = t->box.p; P.sson = t->son.p; P.me = me; P.npeer = me + 1; P.snleaf[me] = nleaf;
     if (period > 0.0) {
         if ((r = leaf_bounds(c, t))) return r;
         P.tb = t->tb.p; P.stb = t->tb.p;
     }
+    if (leaf_hi > 0) { P.node_leaf0 = t->node_leaf0.p; P.node_nleaf = t->node_nleaf.p; P.t_lo = leaf_lo; P.t_hi = leaf_hi; }
     std::vector<ull> init;
     const int root = nleaf;
-    init.push_back(p2p::dt::item(root, root, 0, 0));
-    if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, 0, s));
-    if (t->literal_d6) init.push_back(p2p::dt::item(root, root, 0, 27));     // the reference's zero-shift self exchange (defect D6)
-    return walk_impl(c, t, P, init, (size_t)nleaf * (period > 0.0 ? 192 : 160) * (t->literal_d6 ? 2 : 1));
+    init.push_back(p2p::dt::item(root, root, me, 0));
+    if (period > 0.0) for (int s = 1; s < 27; s++) init.push_back(p2p::dt::item(root, root, me, s));
+    if (t->literal_d6) init.push_back(p2p::dt::item(root, root, me, 27));    // the reference's zero-shift self exchange (defect D6)
+    const size_t rows = leaf_hi > 0 ? (size_t)(leaf_hi - leaf_lo) : (size_t)nleaf;
+    return walk_impl(c, t, P, init, rows * (period > 0.0 ? 192 : 160) * (t->literal_d6 ? 2 : 1));
 }
 
-// ---- multi-rank: one tree per rank, every rank walks its tree against all of them --------------------------------
-// copies of the device tree's walk arrays into caller-owned DEVICE memory (e.g. torch tensors that an all-gather
-// will send): box [(nleaf + nnode)][6] doubles, son [nnode][2] ints (unified ids), leaf [nleaf] {first particle, count}
-int p2p_tree_export(p2p_ctx* c, void* d_box, void* d_son, void* d_leaf, void* d_bounds) {
+// ---- multi-rank: one tree per rank, every rank walks its tree against all of them; ONE topology buffer per rank for ONE all-gather ---------------------------------------------------------
+// (block layout: p2p_topo_layout in p2p_ctx.h)
+int p2p_set_rank(p2p_ctx* c, int rank, int nranks) {
+    USE(c);
+    if (nranks < 1 || nranks > p2p::dt::kMaxPeers || rank < 0 || rank >= nranks) return fail(P2P_ERR_ARG, "bad rank (at most %d ranks)", p2p::dt::kMaxPeers);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    t->self_rank = rank;
+    return 0;
+}
+
+int p2p_topology_stride(int nleaf_max, int nnode_max, int64_t* stride_bytes) {
+    if (nleaf_max < 0 || nnode_max < 0 || !stride_bytes) return fail(P2P_ERR_ARG, "bad arguments");
+    long long a, b, d, s;
+    p2p_topo_layout(nleaf_max, nnode_max, &a, &b, &d, &s);
+    *stride_bytes = s;
+    return 0;
+}
+
+int p2p_tree_export_packed(p2p_ctx* c, void* d_block, int nleaf_max, int nnode_max) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->valid) return fail(P2P_ERR_STATE, "no device tree");
+    if (!d_block || t->nleaf > nleaf_max || t->nnode > nnode_max) return fail(P2P_ERR_ARG, "tree larger than the block layout");
+    long long off_tb, off_son, off_leaf, stride;
+    p2p_topo_layout(nleaf_max, nnode_max, &off_tb, &off_son, &off_leaf, &stride);
+    char* dst = reinterpret_cast<char*>(d_block);
     const size_t nu = (size_t)t->nleaf + t->nnode;
-    if (d_box) CU(cudaMemcpyAsync(d_box, t->box.p, nu * 48, cudaMemcpyDeviceToDevice, c->stream));
-    if (d_son) CU(cudaMemcpyAsync(d_son, t->son.p, (size_t)t->nnode * 8, cudaMemcpyDeviceToDevice, c->stream));
-    if (d_leaf && t->nleaf) CU(cudaMemcpyAsync(d_leaf, c->leaf.p, (size_t)t->nleaf * 8, cudaMemcpyDeviceToDevice, c->stream));
-    if (d_bounds && t->nleaf) {
+    CU(cudaMemcpyAsync(dst, t->box.p, nu * 48, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(dst + off_son, t->son.p, (size_t)t->nnode * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (t->nleaf) {
         int r = leaf_bounds(c, t);
         if (r) return r;
-        CU(cudaMemcpyAsync(d_bounds, t->tb.p, (size_t)t->nleaf * 48, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(dst + off_tb, t->tb.p, (size_t)t->nleaf * 48, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(dst + off_leaf, c->leaf.p, (size_t)t->nleaf * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
     return 0;
 }
 
-// The local tree against the trees of ALL ranks (device arrays concatenated in rank order; peer `me` must be this
-// rank's own export) for the zero displacement and, with period > 0, the 26 periodic displacements: what
-// fmm_task + fmm_ext do through 27 P ring exchanges (1_Indexing/src/fmm.c:1026-1145, remotes.c:740-809), without
-// moving a single halo particle first.  Sources of rank `me` are listed under local leaf ids, those of rank p under
-// nleaf_local + (leaves of the ranks before p, skipping me) + leaf: the ghost leaf table p2p_set_ghosts_device expects.
-int p2p_tree_walk_peers(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
-                        int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all, const void* d_son_all,
-                        const void* d_bounds_all) {
+// p2p_tree_walk_peers over the P gathered blocks.  include_me = 0 skips this rank's own tree (its walk, images included,
+// is p2p_tree_walk, which can run -- and feed the force kernel -- before any topology has arrived).
+int p2p_tree_walk_peers_packed(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3],
+                               int npeer, int me, const int* peer_nleaf, const int* peer_nnode, const void* d_all, int nleaf_max,
+                               int nnode_max, int include_me) {
     USE(c);
     int r = walk_checks(c, theta, rcut, period, tcenter, twidth);
     if (r) return r;
     p2p_dtree* t = c->dtree;
-    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || me < 0 || me >= npeer || !peer_nleaf || !peer_nnode || !d_box_all || !d_son_all ||
-        !tcenter || !twidth)
+    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || me < 0 || me >= npeer || !peer_nleaf || !peer_nnode || !d_all || !tcenter || !twidth)
         return fail(P2P_ERR_ARG, "bad peer arrays (at most %d ranks)", p2p::dt::kMaxPeers);
     if (peer_nleaf[me] != t->nleaf || peer_nnode[me] != t->nnode) return fail(P2P_ERR_ARG, "peer %d is not this rank's tree", me);
+    long long off_tb, off_son, off_leaf, stride;
+    p2p_topo_layout(nleaf_max, nnode_max, &off_tb, &off_son, &off_leaf, &stride);
     p2p::dt::WalkParams P;
     memset(&P, 0, sizeof P);
     P.box = t->box.p; P.son = t->son.p; P.nleaf = t->nleaf; P.theta = theta; P.rcut = rcut; P.period = period > 0.0 ? period : 0.0;
     for (int k = 0; k < 3; k++) { P.tc[k] = tcenter[k]; P.tw[k] = twidth[k]; }
-    P.sbox = reinterpret_cast<const double*>(d_box_all); P.sson = reinterpret_cast<const int*>(d_son_all); P.me = me; P.npeer = npeer;
-    if (period > 0.0 && d_bounds_all) {
+    P.sbox = reinterpret_cast<const double*>(d_all); P.sson = reinterpret_cast<const int*>(d_all); P.me = me; P.npeer = npeer;
+    if (period > 0.0) {
         if ((r = leaf_bounds(c, t))) return r;
-        P.tb = t->tb.p; P.stb = reinterpret_cast<const double*>(d_bounds_all);
+        P.tb = t->tb.p; P.stb = reinterpret_cast<const double*>(d_all);
     }
-    long long ub = 0, nb = 0, lb = 0;
     int ghost = t->nleaf;
     std::vector<ull> init;
     for (int p = 0; p < npeer; p++) {
-        if (peer_nleaf[p] < 0 || peer_nnode[p] < 1) return fail(P2P_ERR_ARG, "peer %d has no tree", p);
+        if (peer_nleaf[p] < 0 || peer_nnode[p] < 1 || peer_nleaf[p] > nleaf_max || peer_nnode[p] > nnode_max)
+            return fail(P2P_ERR_ARG, "peer %d has no tree or exceeds the block layout", p);
         if ((long long)peer_nleaf[p] + peer_nnode[p] >= (1LL << 27)) return fail(P2P_ERR_ARG, "peer tree too large for the walk item encoding");
-        P.sbox_base[p] = ub; P.sson_base[p] = nb; P.snleaf[p] = peer_nleaf[p]; P.stb_base[p] = lb;
-        lb += peer_nleaf[p];
+        P.sbox_base[p] = (long long)p * stride / 48;
+        P.stb_base[p] = ((long long)p * stride + off_tb) / 48;
+        P.sson_base[p] = ((long long)p * stride + off_son) / 8;
+        P.snleaf[p] = peer_nleaf[p];
         P.ts_base[p] = p == me ? 0 : ghost;
         if (p != me) ghost += peer_nleaf[p];
-        ub += (long long)peer_nleaf[p] + peer_nnode[p];
-        nb += peer_nnode[p];
+        if (p == me && !include_me) continue;
         for (int s = 0; s < (period > 0.0 ? 27 : 1); s++) init.push_back(p2p::dt::item(t->nleaf, peer_nleaf[p], p, s));
         if (p == me && t->literal_d6) init.push_back(p2p::dt::item(t->nleaf, peer_nleaf[p], p, 27));   // zero-shift self exchange (defect D6)
     }
-    c->nghostleaf = ghost - t->nleaf;          // the ghost leaf table must follow (p2p_set_ghosts_device) before p2p_build_csr
+    c->nghostleaf = ghost - t->nleaf;          // the ghost leaf table follows (p2p_halo_plan_need) before the list is packed
     c->nghost = 0;
-    return walk_impl(c, t, P, init, (size_t)t->nleaf * 224);
-}
-
-// marks[g] = 1 for every ghost leaf g (0-based behind the local leaves) that the task list references
-int p2p_ghost_marks(p2p_ctx* c, void* d_marks) {
-    USE(c);
-    if (!d_marks && c->nghostleaf) return fail(P2P_ERR_ARG, "null marks");
-    if (c->nghostleaf) CU(cudaMemsetAsync(d_marks, 0, (size_t)c->nghostleaf, c->stream));
-    if (c->ntask && c->nghostleaf) {
-        p2p::dt::ghost_mark_kernel<<<blocks(c->ntask, 256), 256, 0, c->stream>>>(c->ts.p, c->ntask, c->nleaf,
-                                                                               reinterpret_cast<unsigned char*>(d_marks));
-        CU(cudaGetLastError());
-    }
-    return 0;
-}
-
-// out[offset[l] ...) = the fixed-point particles of every LOCAL leaf l with marks[l] != 0 (what a peer asked for)
-int p2p_gather_leaves(p2p_ctx* c, const void* d_marks, const void* d_offset, void* d_out) {
-    USE(c);
-    if (c->nleaf == 0) return 0;
-    if (!d_marks || !d_offset || !d_out) return fail(P2P_ERR_ARG, "null device pointer");
-    p2p::dt::gather_leaves_kernel<<<blocks((long long)c->nleaf * 32, 256), 256, 0, c->stream>>>(
-        c->leaf.p, c->nleaf, reinterpret_cast<const unsigned char*>(d_marks), reinterpret_cast<const long long*>(d_offset), c->part.p,
-        reinterpret_cast<int4*>(d_out));
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// ghost particles (fixed point, as p2p_gather_leaves of the owner produced them) and the table of ALL ghost leaves
-// ({first ghost particle, count}, count 0 for leaves nobody references), everything already on the device
-int p2p_set_ghosts_device(p2p_ctx* c, const void* d_part, int64_t nbody, const void* d_start, const void* d_count, int nghostleaf) {
-    USE(c);
-    if (nbody < 0 || nghostleaf < 0 || (nbody && !d_part) || (nghostleaf && (!d_start || !d_count))) return fail(P2P_ERR_ARG, "bad ghost arrays");
-    const long long base = c->npart;
-    CU(c->part.reserve((size_t)(base + nbody) + 1, c->stream, (size_t)base));
-    CU(c->leaf.reserve((size_t)c->nleaf + nghostleaf + 1, c->stream, (size_t)c->nleaf));
-    if (nbody) CU(cudaMemcpyAsync(c->part.p + base, d_part, (size_t)nbody * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
-    if (nghostleaf) {
-        p2p::dt::ghost_leaf_table_kernel<<<blocks(nghostleaf, 256), 256, 0, c->stream>>>(
-            reinterpret_cast<const int*>(d_start), reinterpret_cast<const int*>(d_count), nghostleaf, (int)base, c->leaf.p + c->nleaf);
-        CU(cudaGetLastError());
-    }
-    c->nghost = nbody; c->nghostleaf = nghostleaf; c->csr_valid = false;
-    return 0;
+    c->bounds_n = std::min(c->bounds_n, c->nleaf);
+    if (init.empty()) return 0;
+    return walk_impl(c, t, P, init, (size_t)t->nleaf * (include_me ? 224 : 32));
 }
 
 // number of (row, source) duplicates in the packed list: non-zero means two images of one leaf reached the same
@@ -949,7 +959,8 @@ int mid_upward(p2p_ctx* c, p2p_dtree* t) {
     return 0;
 }
 // M2L of the last walk's list with the given source trees, then L2L and L2P
-int mid_m2l_down(p2p_ctx* c, p2p_dtree* t, const double* sbox, const double* sM, const long long* sbase, int npeer) {
+int mid_m2l_down(p2p_ctx* c, p2p_dtree* t, const double* sbox, const double* sM, const long long* sbase, int npeer,
+                 const long long* sbase_M = nullptr) {
     cudaStream_t st = c->stream;
     const int nl = t->nleaf;
     const size_t nu = (size_t)nl + t->nnode;
@@ -959,7 +970,7 @@ int mid_m2l_down(p2p_ctx* c, p2p_dtree* t, const double* sbox, const double* sM,
         p2p::mf::M2LParams P;
         memset(&P, 0, sizeof P);
         P.mt = t->mt.p; P.ms = t->ms.p; P.mq = t->mq.p; P.ntask = t->nm2l; P.box = t->box.p; P.sbox = sbox; P.sM = sM;
-        for (int p = 0; p < npeer; p++) P.sbase[p] = sbase[p];
+        for (int p = 0; p < npeer; p++) { P.sbase[p] = sbase[p]; P.sbase_M[p] = sbase_M ? sbase_M[p] : sbase[p]; }
         P.period = t->walk_period; P.rs = c->rs; P.L = t->Lall.p;
         p2p::mf::m2l_kernel<<<blocks(t->nm2l, 128), 128, 0, st>>>(P);
     }
@@ -987,8 +998,8 @@ int p2p_midfield_compute(p2p_ctx* c, int64_t* nm2l) {
     CU(cudaEventRecord(t->e0, st));
     int r = mid_upward(c, t);
     if (r) return r;
-    const long long zero = 0;
-    if ((r = mid_m2l_down(c, t, t->box.p, t->Mall.p, &zero, 1))) return r;
+    long long zero[p2p::dt::kMaxPeers] = {0};          // the M2L tasks carry peer index self_rank: every slot is the local tree
+    if ((r = mid_m2l_down(c, t, t->box.p, t->Mall.p, zero, p2p::dt::kMaxPeers))) return r;
     CU(cudaEventRecord(t->e1, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&t->ms_mid, t->e0, t->e1));
@@ -1007,20 +1018,21 @@ int p2p_midfield_multipoles(p2p_ctx* c, void* d_M) {
     if (d_M) CU(cudaMemcpyAsync(d_M, t->Mall.p, ((size_t)t->nleaf + t->nnode) * p2p::mf::NM * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
-// ... and M2L -> L2L -> L2P with the multipoles and boxes of ALL ranks (concatenated in rank order like the arrays of
-// p2p_tree_walk_peers, whose M2L list is used)
-int p2p_midfield_compute_peers(p2p_ctx* c, int npeer, const int* peer_nleaf, const int* peer_nnode, const void* d_box_all,
-                               const void* d_M_all, int64_t* nm2l) {
+// ... and M2L -> L2L -> L2P with the boxes (packed topology blocks, p2p_tree_export_packed) and multipoles (blocks of
+// (nleaf_max + nnode_max) x 20 doubles) of ALL ranks; the M2L list is the one the local and the remote walk left
+int p2p_midfield_compute_peers_packed(p2p_ctx* c, int npeer, const void* d_topo_all, int nleaf_max, int nnode_max, const void* d_M_all,
+                                      int64_t* nm2l) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "the mid-field needs a device-built tree");
     if (!t->m2l_on) return fail(P2P_ERR_STATE, "enable the M2L lists (p2p_midfield_enable) before the walk");
-    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || !peer_nleaf || !peer_nnode || !d_box_all || !d_M_all) return fail(P2P_ERR_ARG, "bad peer arrays");
-    long long sbase[p2p::dt::kMaxPeers], ub = 0;
-    for (int p = 0; p < npeer; p++) { sbase[p] = ub; ub += (long long)peer_nleaf[p] + peer_nnode[p]; }
+    if (npeer < 1 || npeer > p2p::dt::kMaxPeers || !d_topo_all || !d_M_all) return fail(P2P_ERR_ARG, "bad peer arrays");
+    long long off_tb, off_son, off_leaf, stride, sbase[p2p::dt::kMaxPeers], sbase_M[p2p::dt::kMaxPeers];
+    p2p_topo_layout(nleaf_max, nnode_max, &off_tb, &off_son, &off_leaf, &stride);
+    for (int p = 0; p < npeer; p++) { sbase[p] = (long long)p * stride / 48; sbase_M[p] = (long long)p * ((long long)nleaf_max + nnode_max); }
     cudaStream_t st = c->stream;
     CU(cudaEventRecord(t->e0, st));
-    int r = mid_m2l_down(c, t, reinterpret_cast<const double*>(d_box_all), reinterpret_cast<const double*>(d_M_all), sbase, npeer);
+    int r = mid_m2l_down(c, t, reinterpret_cast<const double*>(d_topo_all), reinterpret_cast<const double*>(d_M_all), sbase, npeer, sbase_M);
     if (r) return r;
     CU(cudaEventRecord(t->e1, st));
     CU(cudaStreamSynchronize(st));
@@ -1045,18 +1057,79 @@ int p2p_midfield_download(p2p_ctx* c, double* leaf_M, double* node_M, double* le
     return 0;
 }
 
+// Local lists and forces of the device-built tree: walk (own tree and, with period > 0, its 26 images), packing and the
+// force kernel, in TARGET CHUNKS (ranges of leaves) sized so that one chunk's list stays below max_chunk_tasks
+// (p2p_set_chunk_tasks): the task list of 1024^3 particles on one GPU would take 6.7e9 x 12 bytes.  The accelerations
+// accumulate; p2p_accumulated_counts gives the totals, p2p_step_timings the device times summed over the chunks.
+int p2p_forces_local(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3], int compute) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->valid || !t->built_here) return fail(P2P_ERR_STATE, "p2p_forces_local needs a device-built tree");
+    const int nleaf = t->nleaf;
+    const long long est = (long long)nleaf * (period > 0.0 ? 200 : 170);
+    int nchunk = (int)std::min<long long>((est + t->max_chunk_tasks - 1) / t->max_chunk_tasks, std::max(nleaf, 1));
+    if (nchunk < 1) nchunk = 1;
+    while ((int)t->chunk_ev.size() < 4 * nchunk) { cudaEvent_t e; CU(cudaEventCreate(&e)); t->chunk_ev.push_back(e); }
+    t->sum_walk = t->sum_csr = t->sum_force = 0.f;
+    t->last_chunks = nchunk;
+    int r;
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int lo = (int)((long long)nleaf * ch / nchunk), hi = (int)((long long)nleaf * (ch + 1) / nchunk);
+        if ((r = p2p_clear_tasks(c))) return r;
+        if (nchunk == 1) r = p2p_tree_walk_range(c, theta, rcut, period, tcenter, twidth, 0, 0);
+        else if (hi > lo) r = p2p_tree_walk_range(c, theta, rcut, period, tcenter, twidth, lo, hi);
+        if (r) return r;
+        t->sum_walk += t->ms_walk;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch], c->stream));
+        if ((r = p2p_build_csr(c))) return r;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 1], c->stream));
+        if (compute && (r = p2p_compute(c))) return r;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 2], c->stream));
+    }
+    return 0;
+}
+
+int p2p_set_chunk_tasks(p2p_ctx* c, int64_t max_tasks) {
+    USE(c);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    if (max_tasks < 1024) return fail(P2P_ERR_ARG, "chunk size too small");
+    t->max_chunk_tasks = max_tasks;
+    return 0;
+}
+
+// device times of the last step: tree build, walks, packing, force kernels (summed over the chunks of p2p_forces_local);
+// synchronises the stream
+int p2p_step_timings(p2p_ctx* c, float* ms_build, float* ms_walk, float* ms_csr, float* ms_force, int* nchunk) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t) return fail(P2P_ERR_STATE, "no device tree");
+    CU(cudaStreamSynchronize(c->stream));
+    float csr = 0.f, force = 0.f;
+    for (int ch = 0; ch < t->last_chunks && 4 * ch + 2 < (int)t->chunk_ev.size(); ch++) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, t->chunk_ev[4 * ch], t->chunk_ev[4 * ch + 1]) == cudaSuccess) csr += a;
+        if (cudaEventElapsedTime(&b, t->chunk_ev[4 * ch + 1], t->chunk_ev[4 * ch + 2]) == cudaSuccess) force += b;
+    }
+    cudaGetLastError();
+    if (ms_build) *ms_build = t->ms_build;
+    if (ms_walk) *ms_walk = t->sum_walk;
+    if (ms_csr) *ms_csr = csr;
+    if (ms_force) *ms_force = force;
+    if (nchunk) *nchunk = t->last_chunks;
+    return 0;
+}
+
 // The whole short-range P2P step of one rank in one call: positions (caller's order) in, accelerations (same order)
 // out; tree build, walk (with the 26 periodic images when period > 0), packing and forces on the device.
 int p2p_step_device(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart, int maxleaf, const double bdl[3],
                     const double bdr[3], int direct_start, double theta, double rcut, double period, double* acc) {
     int r;
     if ((r = p2p_tree_build(c, pos, stride, npart, maxleaf, bdl, bdr, direct_start))) return r;
-    if ((r = p2p_clear_tasks(c))) return r;
     double tc[3], tw[3];
     for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }   // the local root cell (toptree.c:18-45)
-    if ((r = p2p_tree_walk(c, theta, rcut, period, tc, tw))) return r;
-    if ((r = p2p_build_csr(c))) return r;
-    if ((r = p2p_compute(c))) return r;
+    if ((r = p2p_forces_local(c, theta, rcut, period, tc, tw, 1))) return r;
     return p2p_download_acc_original(c, acc);
 }
 

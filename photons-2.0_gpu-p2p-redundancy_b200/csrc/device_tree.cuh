@@ -825,6 +825,8 @@ struct TreeOut {
     int* leaf_npart;
     int* leaf_ipart;
     int* max_width;                  // float bits of the largest leaf width (non-negative floats order like integers); informational
+    int* node_leaf0;                 // first leaf and number of leaves of every node's subtree (leaves are numbered left to right),
+    int* node_nleaf;                 // for walks restricted to a range of target leaves
 };
 
 // top-down: final ids, kd cells, output arrays
@@ -862,6 +864,8 @@ __global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int 
     double* nb = O.box + 6 * (size_t)(O.nleaf + id);
     for (int k = 0; k < 3; k++) { nb[k] = ncen[k]; nb[3 + k] = nwid[k]; }
     O.node_npart[id] = A.t_len[t];
+    O.node_leaf0[id] = leafbase;
+    O.node_nleaf[id] = A.t_nleaf[t];
     const double split = A.t_split[t];
     O.node_split[id] = split;
     if (A.t_len[t] == 0) { O.son[2 * id] = O.son[2 * id + 1] = -1; return; }
@@ -957,7 +961,24 @@ struct WalkParams {
     int* ms;
     int* mq;
     ull cap_m2l;
+    // walk restricted to the target leaves [t_lo, t_hi) (t_hi <= 0: all): items whose target subtree misses the range are
+    // dropped when they are generated, so a step can be split into target chunks whose lists are walked, packed and consumed
+    // one after the other (bounded list memory); the union over a partition of the leaves is the full task multiset
+    const int* node_leaf0;
+    const int* node_nleaf;
+    int t_lo, t_hi;
 };
+
+__device__ __forceinline__ bool target_in_range(const WalkParams& P, int id) {
+    int l0 = id, n = 1;
+    if (id >= P.nleaf) { l0 = __ldg(P.node_leaf0 + (id - P.nleaf)); n = __ldg(P.node_nleaf + (id - P.nleaf)); }
+    return l0 < P.t_hi && l0 + n > P.t_lo;
+}
+// an M2L task whose target spans several chunks belongs to the chunk that holds the target's first leaf
+__device__ __forceinline__ bool target_starts_in_range(const WalkParams& P, int id) {
+    const int l0 = id >= P.nleaf ? __ldg(P.node_leaf0 + (id - P.nleaf)) : id;
+    return l0 >= P.t_lo && l0 < P.t_hi;
+}
 
 __constant__ int c_shift[28][3];   // [27] = zero displacement walked with the remote rules (the reference's zero-shift self exchange)
 
@@ -1110,6 +1131,15 @@ __global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__
                 }
             }
         }
+        if (P.t_hi > 0) {
+            if (nchild && ci[0] != ci[nchild - 1]) {            // the target side was opened: keep the children that meet the range
+                int m = 0;
+                for (int k = 0; k < nchild; k++)
+                    if (target_in_range(P, ci[k])) { ci[m] = ci[k]; cj[m] = cj[k]; m++; }
+                nchild = m;
+            }
+            if (m2l) m2l = target_starts_in_range(P, im);
+        }
         // claim output slots: per warp totals, ONE atomic per block and counter (all walkers of the chip add to the same three
         // words; per-warp atomics made the walk atomic-throughput bound), then per-warp and per-lane offsets
         int incl = nchild;
@@ -1163,28 +1193,6 @@ __global__ void leaf_bounds_kernel(const int2* __restrict__ leaf, int nleaf, con
         o[k] = L.y > 0 ? org[k] + (double)lo[k] * step : 1.0;
         o[3 + k] = L.y > 0 ? org[k] + (double)hi[k] * step : 0.0;
     }
-}
-
-// ---- multi-rank helpers: which ghost leaves does the list reference, and the particles of requested leaves
-__global__ void ghost_mark_kernel(const int* __restrict__ ts, long long ntask, int nleaf_local, unsigned char* __restrict__ marks) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntask) return;
-    const int s = ts[i];
-    if (s >= nleaf_local) marks[s - nleaf_local] = 1;
-}
-
-// one warp per requested leaf: copy its particles to out[offset[leaf] ...)
-__global__ void gather_leaves_kernel(const int2* __restrict__ leaf, int nleaf, const unsigned char* __restrict__ marks,
-                                     const long long* __restrict__ offset, const int4* __restrict__ part, int4* __restrict__ out) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= nleaf || !marks[w]) return;
-    const int2 L = leaf[w];
-    for (int k = lane; k < L.y; k += 32) out[offset[w] + k] = part[L.x + k];
-}
-
-__global__ void ghost_leaf_table_kernel(const int* __restrict__ start, const int* __restrict__ count, int n, int start_off, int2* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_int2(start[i] + start_off, count[i]);
 }
 
 // after sorting: a source listed twice in a row (the same leaf reached through two different images) cannot be

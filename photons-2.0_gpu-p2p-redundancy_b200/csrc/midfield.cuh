@@ -174,7 +174,8 @@ struct M2LParams {
     const double* box;        // local tree
     const double* sbox;       // source trees (concatenated, as in the walk)
     const double* sM;         // source multipoles (concatenated like sbox, NM per id)
-    long long sbase[16];
+    long long sbase[16];      // first box of rank p in sbox
+    long long sbase_M[16];    // first multipole of rank p in sM
     double period, rs;
     double* L;                // [local unified id][NM], accumulated with atomics
 };
@@ -196,7 +197,9 @@ __global__ void m2l_kernel(M2LParams P) {
     radial_factors(x[0] * x[0] + x[1] * x[1] + x[2] * x[2], P.rs, f);
     derivative_tensor(x, f, D);
 #pragma unroll
-    for (int n = 0; n < NM; n++) M[n] = P.sM[NM * s + n];
+    const size_t sm = (size_t)(P.sbase_M[peer] + P.ms[i]);
+#pragma unroll
+    for (int n = 0; n < NM; n++) M[n] = P.sM[NM * sm + n];
     double* L = P.L + NM * (size_t)t;
 #pragma unroll
     for (int n = 0; n < NM; n++) {

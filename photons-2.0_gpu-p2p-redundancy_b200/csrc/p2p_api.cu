@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "csr_pack.cuh"
+#include "halo.cuh"
 #include "p2p_ctx.h"
 #include "p2p_gcoef.h"
 #include "p2p_kernel.cuh"
@@ -113,6 +114,9 @@ int upload_ints(p2p_ctx* c, const int* a, const int* b, long long n, int** da, i
 }
 
 constexpr int kStage = 384;   // particles per staging buffer: 2 x 6 KB + targets per warp -> 16 warps / SM fit
+// defaults of the second-generation kernel (sweeps: profiles/r2_sweep_*.txt): one source per lane (half the code size of two:
+// the clustered box runs many different row occupancies at once and the instruction cache holds them), 3 blocks / SM
+constexpr int kDefaultNsrc = 1, kDefaultMinBlocks = 3;
 
 template <int TT, int NSRC, bool TRUNC, bool PACKED, int MINB, int POLY, int STAGE = kStage>
 int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
@@ -130,22 +134,37 @@ int launch_rows(p2p_ctx* c, const p2p::KernelParams& P) {
     return 0;
 }
 
-// Instantiated tunings.  Production default: TT 16 (8 for leaves <= 8), 2 sources per lane, 4 blocks / SM.
-// The sweep set (tools/sweep.py) adds 1 / 4 sources per lane, 3 blocks / SM and the split polynomial
-// for the truncated packed kernel only, to keep the build time bounded.
+// First-generation kernel (16 targets per pass, one slice body): kept as the scalar cross-check variant and as the
+// A/B baseline of the sweeps (tools/sweep.py), in its final round-1 tuning only.
 template <int TT, bool TRUNC, bool PACKED>
-int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb, int poly) {
-    if constexpr (TRUNC && PACKED) {
-        if (poly == 3) return minb == 3 ? launch_rows<TT, 2, true, true, 3, 3>(c, P) : launch_rows<TT, 2, true, true, 4, 3>(c, P);
-        if (poly == 1) {
-            if (nsrc == 4) return minb == 3 ? launch_rows<TT, 4, true, true, 3, 1>(c, P) : launch_rows<TT, 4, true, true, 4, 1>(c, P);
-            return minb == 3 ? launch_rows<TT, 2, true, true, 3, 1>(c, P) : launch_rows<TT, 2, true, true, 4, 1>(c, P);
-        }
-        if (nsrc == 1) return minb == 3 ? launch_rows<TT, 1, true, true, 3, 0>(c, P) : launch_rows<TT, 1, true, true, 4, 0>(c, P);
-        if (nsrc == 4) return minb == 3 ? launch_rows<TT, 4, true, true, 3, 0>(c, P) : launch_rows<TT, 4, true, true, 4, 0>(c, P);
-        return minb == 3 ? launch_rows<TT, 2, true, true, 3, 0>(c, P) : launch_rows<TT, 2, true, true, 4, 0>(c, P);
+int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P) {
+    return launch_rows<TT, 2, TRUNC, PACKED, 4, (TRUNC && PACKED) ? 1 : 0>(c, P);
+}
+
+// Second-generation kernel (p2p_rows2_kernel): one pass per row, near and far slice bodies.
+template <int NSRC, bool TRUNC, int MINB>
+int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
+    auto kern = p2p::p2p_rows2_kernel<NSRC, kStage, TRUNC, MINB>;
+    const int smem = 4 * (int)sizeof(p2p::WarpSmem2<kStage>);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) return fail(P2P_ERR_CUDA, "force kernel does not fit on an SM (smem %d)", smem);
+    long long want = ((long long)P.nrow + 3) / 4;
+    long long grid = std::min<long long>((long long)c->num_sm * per_sm, std::max<long long>(want, 1));
+    if (P.rows_per_warp > 0) grid = std::max<long long>((want + P.rows_per_warp - 1) / P.rows_per_warp, 1);   // every row finds a warp
+    kern<<<(unsigned)grid, 128, smem, c->stream>>>(P);
+    CU(cudaGetLastError());
+    c->last_blocks_per_sm = per_sm;
+    return 0;
+}
+template <bool TRUNC>
+int launch_cfg2(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb) {
+    if constexpr (TRUNC) {
+        if (nsrc == 2) return launch_rows2<2, true, 3>(c, P);
+        return minb == 4 ? launch_rows2<1, true, 4>(c, P) : launch_rows2<1, true, 3>(c, P);
     } else {
-        return launch_rows<TT, 2, TRUNC, PACKED, 4, 0>(c, P);
+        return launch_rows2<1, false, 3>(c, P);
     }
 }
 
@@ -184,14 +203,17 @@ int p2p_create(p2p_ctx** out, int device) {
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_counter, 4 * sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_npairs, 2 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_npairs, 0, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_npairs, sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_npairs, 0, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_npairs_acc, sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_npairs_acc, 0, sizeof(unsigned long long)));
     CU(cudaMallocHost(&c->h_flags, 8 * sizeof(unsigned int)));
+    memset(c->h_flags, 0, 8 * sizeof(unsigned int));
     CU(cudaMalloc(&c->d_counter2, 4 * sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_bad, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_bad, 2 * sizeof(unsigned int)));       // [0] tasks with ids out of range, [1] oversize source leaf met by the force kernel
     CU(cudaMalloc(&c->d_occ, 64 * sizeof(unsigned int)));
     CU(cudaMemset(c->d_occ, 0, 64 * sizeof(unsigned int)));
-    CU(cudaMemset(c->d_bad, 0, sizeof(unsigned int)));
+    CU(cudaMemset(c->d_bad, 0, 2 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_npairs2, sizeof(unsigned long long)));
     {   // the copy / packing stream outranks the force kernel's: its small kernels take the room left for them first
         int lo = 0, hi = 0;
@@ -203,10 +225,18 @@ int p2p_create(p2p_ctx** out, int device) {
         CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_bounds, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_bounds, c->own_stream));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreate(&c->ev2));
     CU(cudaEventCreate(&c->ev3));
+    CU(cudaEventCreate(&c->ev0_b));
+    CU(cudaEventCreate(&c->ev1_b));
+    CU(cudaEventCreate(&c->ev2_b));
+    CU(cudaEventCreate(&c->ev3_b));
+    CU(cudaMallocHost(&c->h_halo, 64 * sizeof(long long)));
+    CU(cudaMalloc(&c->d_halo, 64 * sizeof(long long)));
     *out = c;
     return 0;
 }
@@ -219,10 +249,11 @@ int p2p_destroy(p2p_ctx* c) {
     c->itmp.release(); c->row_ptr.release(); c->cnt.release(); c->cursor.release(); c->tile.release(); c->stage.release();
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_npairs) cudaFree(c->d_npairs);
+    if (c->d_npairs_acc) cudaFree(c->d_npairs_acc);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     c->acc64.release();
-    c->row_work.release(); c->row_work2.release(); c->order.release(); c->order2.release(); c->whist.release(); c->whist2.release();
+    c->row_work.release(); c->row_work2.release(); c->order.release(); c->order2.release(); c->row_mid.release(); c->row_mid2.release(); c->lbounds.release(); c->whist.release(); c->whist2.release();
     c->tt2.release(); c->ts2.release(); c->col2.release(); c->row_ptr2.release(); c->cnt2.release(); c->cursor2.release(); c->tile2.release();
     if (c->d_counter2) cudaFree(c->d_counter2);
     if (c->d_bad) cudaFree(c->d_bad);
@@ -231,7 +262,12 @@ int p2p_destroy(p2p_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int k = 0; k < 2; k++) { if (c->ev_packed[k]) cudaEventDestroy(c->ev_packed[k]); if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]); }
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_bounds) cudaEventDestroy(c->ev_bounds);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    cudaEventDestroy(c->ev0_b); cudaEventDestroy(c->ev1_b); cudaEventDestroy(c->ev2_b); cudaEventDestroy(c->ev3_b);
+    if (c->h_halo) cudaFreeHost(c->h_halo);
+    if (c->d_halo) cudaFree(c->d_halo);
+    c->halo_cnt.release(); c->halo_off.release(); c->halo_tile.release(); c->halo_cursor.release();
     if (c->dtree) p2p_dtree_release(c->dtree);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -254,12 +290,17 @@ int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
 }
 
 int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
-    // min_blocks: 3 or 4; adding 16 selects the even/odd split polynomial (sweeps only)
-    const int poly = minb / 16;                 // +16: split polynomial (21-op form); +48: same with the EX2 sign made on the ALU pipe
-    minb %= 16;
-    if (!c || (tt && tt != 8 && tt != 16) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 4) || (minb != 0 && minb != 3 && minb != 4) || poly > 3 || poly == 2)
-        return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 8/16, sources_per_lane 1/2/4, min_blocks 3/4)");
-    c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb; c->tune_poly = poly;
+    // tt 0 / 32: second-generation kernel (nsrc 1 / 2, min_blocks 3 / 4); tt 8 / 16: first-generation kernel in its final tuning
+    if (!c || (tt && tt != 8 && tt != 16 && tt != 32) || (nsrc != 0 && nsrc != 1 && nsrc != 2) || (minb != 0 && minb != 3 && minb != 4))
+        return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 0/32 or 8/16, sources_per_lane 1/2, min_blocks 3/4)");
+    c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb;
+    return 0;
+}
+
+int p2p_set_far_threshold(p2p_ctx* c, double u_far) {
+    if (!c || !(u_far <= 0.0 || u_far >= P2P_U_FAR - 1e-12)) return fail(P2P_ERR_ARG, "far threshold must be 0 (off), < 0 (default) or >= %g", (double)P2P_U_FAR);
+    c->far_u = u_far;
+    c->csr_valid = false;
     return 0;
 }
 
@@ -275,17 +316,45 @@ int p2p_set_stream(p2p_ctx* c, void* s) {
     return 0;
 }
 
+int p2p_swap_lists(p2p_ctx* c) {
+    if (!c) return fail(P2P_ERR_ARG, "null context");
+    std::swap(c->tt, c->tt2); std::swap(c->ts, c->ts2); std::swap(c->col, c->col2); std::swap(c->row_ptr, c->row_ptr2);
+    std::swap(c->cnt, c->cnt2); std::swap(c->cursor, c->cursor2); std::swap(c->tile, c->tile2); std::swap(c->row_work, c->row_work2);
+    std::swap(c->order, c->order2); std::swap(c->row_mid, c->row_mid2); std::swap(c->whist, c->whist2);
+    std::swap(c->d_counter, c->d_counter2); std::swap(c->d_npairs, c->d_npairs2);
+    std::swap(c->ntask, c->ntask_b); std::swap(c->npairs, c->npairs_b); std::swap(c->csr_valid, c->csr_valid_b);
+    std::swap(c->ev0, c->ev0_b); std::swap(c->ev1, c->ev1_b); std::swap(c->ev2, c->ev2_b); std::swap(c->ev3, c->ev3_b);
+    std::swap(c->ms_compute, c->ms_compute_b); std::swap(c->ms_csr, c->ms_csr_b);
+    std::swap(c->timed_compute, c->timed_compute_b); std::swap(c->timed_csr, c->timed_csr_b);
+    return 0;
+}
+
+int p2p_set_force_blocks(p2p_ctx* c, int rows_per_warp) {
+    if (!c || rows_per_warp < 0) return fail(P2P_ERR_ARG, "bad rows_per_warp");
+    c->rows_per_warp = rows_per_warp;
+    return 0;
+}
+
+int p2p_reserve_ghosts(p2p_ctx* c, int nghostleaf, int64_t nghost) {
+    USE(c);
+    if (nghostleaf < 0 || nghost < 0) return fail(P2P_ERR_ARG, "bad ghost capacities");
+    CU(c->part.reserve((size_t)(c->npart + nghost) + 1, c->stream, (size_t)c->npart));
+    CU(c->leaf.reserve((size_t)c->nleaf + nghostleaf + 1, c->stream, (size_t)c->nleaf));
+    CU(c->lbounds.reserve(2 * ((size_t)c->nleaf + nghostleaf) + 2, c->stream, 2 * (size_t)std::min(c->bounds_n, c->nleaf)));
+    return 0;
+}
+
 int p2p_upload_particles(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart) {
     USE(c);
     if (npart < 0 || (npart && !pos) || stride < 3) return fail(P2P_ERR_ARG, "bad particle array");
-    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false;
+    c->npart = npart; c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false; c->bounds_n = 0;
     CU(c->part.reserve((size_t)npart + 1, c->stream));
     CU(c->acc.reserve((size_t)npart + 1, c->stream));
     if (!c->box_set) auto_box(c, pos, stride, npart);
     int r = upload_xyz(c, pos, stride, npart, c->part.p);
     if (r) return r;
     CU(cudaMemsetAsync(c->acc.p, 0, (size_t)npart * sizeof(float4), c->stream));
-    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->d_npairs_acc, 0, sizeof(unsigned long long), c->stream));
     c->acc_tasks = 0;
     return 0;
 }
@@ -301,7 +370,7 @@ int p2p_upload_leaves(p2p_ctx* c, const int* leaf_npart, const int* leaf_ipart, 
         mx = std::max(mx, leaf_npart[i]);
     }
     if (mx > P2P_MAX_LEAF) return fail(P2P_ERR_ARG, "leaf occupancy %d exceeds P2P_MAX_LEAF %d", mx, P2P_MAX_LEAF);
-    c->nleaf = nleaf; c->nghostleaf = 0; c->nghost = 0; c->max_target_leaf = mx; c->csr_valid = false;
+    c->nleaf = nleaf; c->nghostleaf = 0; c->nghost = 0; c->max_target_leaf = mx; c->csr_valid = false; c->bounds_n = 0;
     CU(c->leaf.reserve((size_t)nleaf + 1, c->stream));
     int *dc, *ds;
     int r = upload_ints(c, leaf_npart, leaf_ipart, nleaf, &dc, &ds);
@@ -333,7 +402,7 @@ static int append_ghost_leaves(p2p_ctx* c, const int* start, const int* count, i
     if (first_id) *first_id = first;
     c->nghostleaf += nleaf;
     c->nghost += nbody;
-    c->csr_valid = false;
+    c->csr_valid = false; c->bounds_n = std::min(c->bounds_n, first);
     return 0;
 }
 
@@ -368,7 +437,7 @@ int p2p_append_ghosts_device(p2p_ctx* c, const void* d_xyzm, int64_t nbody, cons
 
 int p2p_clear_ghosts(p2p_ctx* c) {
     if (!c) return fail(P2P_ERR_ARG, "null context");
-    c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false;
+    c->nghost = 0; c->nghostleaf = 0; c->csr_valid = false; c->bounds_n = std::min(c->bounds_n, c->nleaf);
     return 0;
 }
 
@@ -417,7 +486,7 @@ struct ListSet {                       // one set of task / CSR buffers (the con
     DevBuf<long long>* row_ptr;
     DevBuf<unsigned int>* cnt;
     DevBuf<unsigned long long>*cursor, *tile, *row_work;
-    DevBuf<int>* order;
+    DevBuf<int>*order, *row_mid;
     DevBuf<unsigned int>* whist;
     unsigned int* d_counter;           // [0] row scheduler, [1] unsorted rows, [2] rows in the work-ordered schedule
     unsigned long long* d_npairs;
@@ -434,10 +503,10 @@ int band_rows() {
 }
 ListSet list_set(p2p_ctx* c, int k) {
     if (k == 0)
-        return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, &c->row_work, &c->order, &c->whist,
+        return ListSet{&c->tt, &c->ts, &c->col, &c->row_ptr, &c->cnt, &c->cursor, &c->tile, &c->row_work, &c->order, &c->row_mid, &c->whist,
                        c->d_counter, c->d_npairs};
-    return ListSet{&c->tt2, &c->ts2, &c->col2, &c->row_ptr2, &c->cnt2, &c->cursor2, &c->tile2, &c->row_work2, &c->order2, &c->whist2,
-                   c->d_counter2, c->d_npairs2};
+    return ListSet{&c->tt2, &c->ts2, &c->col2, &c->row_ptr2, &c->cnt2, &c->cursor2, &c->tile2, &c->row_work2, &c->order2, &c->row_mid2,
+                   &c->whist2, c->d_counter2, c->d_npairs2};
 }
 
 int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
@@ -449,15 +518,46 @@ int reserve_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     CU(L.tile->reserve((size_t)((nrow + p2p::kScanTile - 1) / p2p::kScanTile) + 1, st));
     CU(L.row_work->reserve((size_t)nrow + 1, st));
     CU(L.order->reserve((size_t)nrow + 1, st));
+    CU(L.row_mid->reserve((size_t)nrow + 1, st));
     CU(L.whist->reserve(2 * (size_t)p2p::kWorkBuckets * (nrow / p2p::kMinBandRows + 1) + 128, st));
     return 0;
 }
 
-// count -> scan -> scatter -> sort -> pair count of the n tasks in L.tt / L.ts, all on stream st
+// squared near / far threshold in fixed-point steps (0: the kernel has no far class -- plain Newtonian kernel, first-
+// generation or scalar variant)
+double far_threshold2(const p2p_ctx* c) {
+    const bool v2 = c->variant != P2P_KERNEL_SCALAR && (c->tune_tt == 0 || c->tune_tt == 32);
+    if (!(c->rs > 0.0) || !v2 || c->far_u == 0.0 || !(c->extent > 0.0)) return 0.0;
+    const double u = c->far_u > 0.0 ? c->far_u : (double)P2P_U_FAR;
+    const double d = u * 2.0 * c->rs / (c->extent / 4294967296.0);
+    return d * d;
+}
+
+// tight fixed-point bounds of all leaves (local + ghost), recomputed when particles or leaves changed
+int leaf_bounds_fixed(p2p_ctx* c, cudaStream_t st) {
+    const int n = c->nleaf + c->nghostleaf, have = c->bounds_n;
+    if (have >= n) return 0;
+    // only the leaves that are new (the ghost leaves of a halo that arrived after the local list was packed): the entries
+    // of the leaves before them may be in use by a packing kernel on another stream
+    CU(c->lbounds.reserve(2 * (size_t)n + 2, st, 2 * (size_t)have));
+    p2p::leaf_bounds_fixed_kernel<<<(n - have + 127) / 128, 128, 0, st>>>(c->leaf.p + have, n - have, c->part.p,
+                                                                             reinterpret_cast<p2p::LeafBounds*>(c->lbounds.p) + have);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_bounds, st));
+    c->bounds_n = n;
+    return 0;
+}
+
+// count -> scan -> scatter (+ near / far classification) -> sort -> pair count of the n tasks in L.tt / L.ts, all on stream st
 int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     const int nrow = c->nleaf;
     int r = reserve_csr(c, L, n, st);
     if (r) return r;
+    const double far2 = far_threshold2(c);
+    if (far2 > 0.0) {
+        if ((r = leaf_bounds_fixed(c, st))) return r;
+        CU(cudaStreamWaitEvent(st, c->ev_bounds, 0));      // bounds of earlier leaves may have been computed on another stream
+    }
     const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
     CU(cudaMemsetAsync(L.cnt->p, 0, ((size_t)nrow + 1) * 4, st));
     CU(cudaMemsetAsync(L.d_counter, 0, 4 * sizeof(unsigned int), st));
@@ -480,11 +580,13 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     p2p::scan_apply_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p, L.row_ptr->p, L.cursor->p);
     CU(cudaGetLastError());
     if (n) {
-        p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p);
+        p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p,
+                                                   reinterpret_cast<const p2p::LeafBounds*>(c->lbounds.p), far2);
         p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p, nrow, L.col->p, L.d_counter + 1);
+        p2p::csr_sort_long_rows_kernel<<<c->num_sm * 2, 256, 0, st>>>(L.row_ptr->p, nrow, L.col->p);
         int* d_band = reinterpret_cast<int*>(L.whist->p + 2 * (size_t)p2p::kWorkBuckets * nband);
         p2p::band_rows_kernel<<<1, 32, 0, st>>>(c->d_occ, nrow, c->num_sm * 16, band_rows(), d_band);
-        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p, d_band);
+        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p, d_band, L.row_mid->p);
         p2p::work_bucket_offsets_kernel<<<1, 1024, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets * nband, nband, L.d_counter + 2);
         p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p, c->leaf.p, nrow,
                                                                           L.whist->p + p2p::kWorkBuckets * nband, L.order->p, d_band);
@@ -498,7 +600,7 @@ int p2p_build_csr(p2p_ctx* c) {
     USE(c);
     CU(cudaEventRecord(c->ev2, c->stream));
     const ListSet L = list_set(c, 0);
-    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(unsigned int), c->stream));
+    CU(cudaMemsetAsync(c->d_bad, 0, 2 * sizeof(unsigned int), c->stream));
     int r = pack_csr(c, L, c->ntask, c->stream);
     if (r) return r;
     CU(cudaMemcpyAsync(c->h_flags + 2, c->d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
@@ -520,6 +622,10 @@ static int check_flags(p2p_ctx* c) {
         return fail(P2P_ERR_ARG, "%u task(s) reference leaves outside [0,%d) x [0,%d)", c->h_flags[2], c->nleaf,
                     c->nleaf + c->nghostleaf);
     }
+    if (c->h_flags[3] != 0) {
+        c->h_flags[3] = 0;
+        return fail(P2P_ERR_ARG, "a source leaf holds more than %d particles (ghost leaf table not validated?): its pairs were skipped", kStage);
+    }
     return 0;
 }
 
@@ -531,6 +637,7 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     memset(&P, 0, sizeof P);
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = L.row_ptr->p; P.col = L.col->p; P.acc = c->acc.p;
     P.counter = L.d_counter; P.n_active = L.d_counter + 2; P.row_order = L.order->p; P.nrow = c->nleaf;
+    P.row_mid = L.row_mid->p; P.err = c->d_bad + 1; P.rows_per_warp = c->rows_per_warp;
     const bool trunc = c->rs > 0.0;
     // kernel length unit: 2 r_s / sqrt(log2 e) for the truncated kernel (then exp(-u^2) = 2^(-r'^2) and the
     // polynomial argument is r' = u sqrt(log2 e)), the box extent otherwise
@@ -542,7 +649,11 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     if (trunc) {
         // rinv' Q(u) = rinv' + v (c0 + c1 v + ...), v = r' : c_j = q_{j+2} / sl2e^(j+2)
         for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] / pow(sl2e, j + 2));
-        P.far_coord = 24.0f * (float)sl2e;
+        static_assert(p2p::kFarDegree == P2P_FAR_DEGREE, "far-field polynomial degree");
+        for (int j = 0; j < p2p::kFarTerms; j++) P.cf[j] = (float)P2P_GFAR[j];
+        P.far_shift = (float)P2P_FAR_SHIFT;
+        // dummy (padding) source: 2^(-r^2) flushes to exactly 0 there while r^8 still fits FP32, whatever the extent of the target leaf
+        P.far_coord = 1000.0f * (float)sl2e;
     } else {
         P.far_coord = 1.0e18f;
     }
@@ -551,25 +662,30 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     int r = 0;
     if (c->nleaf > 0 && ntask > 0) {
         const bool packed = c->variant != P2P_KERNEL_SCALAR;
-        // defaults from the 128^3 sweeps (profiles/): 16 targets per pass, 2 sources per lane, 4 blocks / SM
-        int tt = c->tune_tt ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
-        int nsrc = c->tune_nsrc ? c->tune_nsrc : 2;
-        int minb = c->tune_minb ? c->tune_minb : 4;
-        const int poly = c->tune_minb ? c->tune_poly : 1;      // default: split polynomial, EX2 sign by a packed multiply (sweep v12)
+        const bool v2 = packed && (c->tune_tt == 0 || c->tune_tt == 32);
         cudaStream_t keep = c->stream;
-        c->stream = st;                                         // launch_rows launches on c->stream
-        if (tt == 8) {
-            if (trunc) r = packed ? launch_cfg<8, true, true>(c, P, nsrc, minb, poly) : launch_cfg<8, true, false>(c, P, nsrc, minb, poly);
-            else r = packed ? launch_cfg<8, false, true>(c, P, nsrc, minb, poly) : launch_cfg<8, false, false>(c, P, nsrc, minb, poly);
+        c->stream = st;                                         // the launchers use c->stream
+        if (v2) {
+            const int nsrc = c->tune_nsrc ? c->tune_nsrc : kDefaultNsrc;
+            const int minb = c->tune_minb ? c->tune_minb : kDefaultMinBlocks;
+            r = trunc ? launch_cfg2<true>(c, P, nsrc, minb) : launch_cfg2<false>(c, P, nsrc, minb);
         } else {
-            if (trunc) r = packed ? launch_cfg<16, true, true>(c, P, nsrc, minb, poly) : launch_cfg<16, true, false>(c, P, nsrc, minb, poly);
-            else r = packed ? launch_cfg<16, false, true>(c, P, nsrc, minb, poly) : launch_cfg<16, false, false>(c, P, nsrc, minb, poly);
+            const int tt = (c->tune_tt == 8 || c->tune_tt == 16) ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
+            if (tt == 8) {
+                if (trunc) r = packed ? launch_cfg<8, true, true>(c, P) : launch_cfg<8, true, false>(c, P);
+                else r = packed ? launch_cfg<8, false, true>(c, P) : launch_cfg<8, false, false>(c, P);
+            } else {
+                if (trunc) r = packed ? launch_cfg<16, true, true>(c, P) : launch_cfg<16, true, false>(c, P);
+                else r = packed ? launch_cfg<16, false, true>(c, P) : launch_cfg<16, false, false>(c, P);
+            }
         }
         c->stream = keep;
     }
     if (r) return r;
-    p2p::add_counter_kernel<<<1, 32, 0, st>>>(L.d_npairs, c->d_npairs + 1);   // no host sync
+    p2p::add_counter_kernel<<<1, 32, 0, st>>>(L.d_npairs, c->d_npairs_acc);   // no host sync
     CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_flags + 3, c->d_bad + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    c->flags_pending = true;
     c->acc_tasks += ntask;
     return 0;
 }
@@ -589,7 +705,7 @@ int p2p_compute(p2p_ctx* c) {
 int p2p_accumulated_counts(p2p_ctx* c, int64_t* ntask, int64_t* npairs) {
     USE(c);
     unsigned long long v = 0;
-    CU(cudaMemcpyAsync(&v, c->d_npairs + 1, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&v, c->d_npairs_acc, sizeof v, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int r = check_flags(c);
     if (r) return r;
@@ -601,7 +717,7 @@ int p2p_accumulated_counts(p2p_ctx* c, int64_t* ntask, int64_t* npairs) {
 int p2p_zero_acc(p2p_ctx* c) {
     USE(c);
     if (c->npart) CU(cudaMemsetAsync(c->acc.p, 0, (size_t)c->npart * sizeof(float4), c->stream));
-    CU(cudaMemsetAsync(c->d_npairs + 1, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->d_npairs_acc, 0, sizeof(unsigned long long), c->stream));
     c->acc_tasks = 0;
     return 0;
 }
@@ -666,6 +782,27 @@ int p2p_download_csr(p2p_ctx* c, int64_t* row_ptr, int* col) {
     if (row_ptr) CU(cudaMemcpyAsync(row_ptr, c->row_ptr.p, ((size_t)c->nleaf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     if (col && c->ntask) CU(cudaMemcpyAsync(col, c->col.p, (size_t)c->ntask * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (col) for (long long i = 0; i < c->ntask; i++) col[i] &= 0x7fffffff;       // bit 31: near / far class of the column
+    return 0;
+}
+
+int p2p_download_csr_class(p2p_ctx* c, unsigned char* is_far, int* row_near) {
+    USE(c);
+    if (!c->csr_valid) return fail(P2P_ERR_STATE, "no CSR built");
+    if (is_far && c->ntask) {
+        int* tmp = (int*)malloc((size_t)c->ntask * 4);
+        if (!tmp) return fail(P2P_ERR_ARG, "out of host memory");
+        cudaError_t e = cudaMemcpyAsync(tmp, c->col.p, (size_t)c->ntask * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) for (long long i = 0; i < c->ntask; i++) is_far[i] = (unsigned char)((unsigned)tmp[i] >> 31);
+        free(tmp);
+        CU(e);
+    }
+    if (row_near && c->nleaf) {
+        if (c->ntask) CU(cudaMemcpyAsync(row_near, c->row_mid.p, (size_t)c->nleaf * 4, cudaMemcpyDeviceToHost, c->stream));
+        else memset(row_near, 0, (size_t)c->nleaf * 4);
+    }
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -718,7 +855,7 @@ int p2p_step_host_chunked(p2p_ctx* c, const double* pos, int64_t pos_stride, int
         CU(L.ts->reserve((size_t)maxn + 1, S0));
         if ((r = reserve_csr(c, L, maxn, S0))) return r;
     }
-    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(unsigned int), S0));
+    CU(cudaMemsetAsync(c->d_bad, 0, 2 * sizeof(unsigned int), S0));
     CU(cudaEventRecord(c->ev_ready, S0));                    // particles, leaves and ghosts are queued on S0
     CU(cudaStreamWaitEvent(S1, c->ev_ready, 0));
     CU(cudaEventRecord(c->ev0, S0));
@@ -744,6 +881,131 @@ int p2p_step_host_chunked(p2p_ctx* c, const double* pos, int64_t pos_stride, int
     CU(cudaMemcpyAsync(c->h_flags + 2, c->d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, S0));
     c->flags_pending = true;
     return p2p_download_acc(c, acc, acc_stride, accumulate);
+}
+
+// ---- halo planning of the multi-rank device path (halo.cuh) ------------------------------------------------------------
+namespace {
+// exclusive scan of c->halo_cnt[0, n) into c->halo_off[0, n]
+int halo_scan(p2p_ctx* c, long long n, cudaStream_t st) {
+    if (n > 0x7fffffffLL) return fail(P2P_ERR_ARG, "halo plan too large");
+    const int ntile = (int)((n + p2p::kScanTile - 1) / p2p::kScanTile);
+    CU(c->halo_off.reserve((size_t)n + 2, st));
+    CU(c->halo_cursor.reserve((size_t)n + 2, st));
+    CU(c->halo_tile.reserve((size_t)ntile + 2, st));
+    if (n == 0) { CU(cudaMemsetAsync(c->halo_off.p, 0, sizeof(long long), st)); return 0; }
+    p2p::scan_tile_sums_kernel<<<ntile, 256, 0, st>>>(c->halo_cnt.p, (int)n, c->halo_tile.p);
+    p2p::scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(c->halo_tile.p, ntile);
+    p2p::scan_apply_kernel<<<ntile, 256, 0, st>>>(c->halo_cnt.p, (int)n, c->halo_tile.p, c->halo_off.p, c->halo_cursor.p);
+    CU(cudaGetLastError());
+    return 0;
+}
+// totals of the nseg segments [bound[s], bound[s + 1]) of the scan -> host (synchronises the stream)
+int halo_totals(p2p_ctx* c, const int* bound, int nseg, long long* out, cudaStream_t st) {
+    if (nseg < 0 || nseg > 31) return fail(P2P_ERR_ARG, "too many halo segments");
+    if (nseg == 0) return 0;
+    int* hb = reinterpret_cast<int*>(c->h_halo + 32);
+    for (int s = 0; s <= nseg; s++) hb[s] = bound[s];
+    CU(cudaMemcpyAsync(c->d_halo + 32, hb, (size_t)(nseg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    p2p::halo_segment_totals_kernel<<<1, 32, 0, st>>>(c->halo_off.p, reinterpret_cast<const int*>(c->d_halo + 32), nseg, c->d_halo);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_halo, c->d_halo, (size_t)nseg * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int s = 0; s < nseg; s++) out[s] = c->h_halo[s];
+    return 0;
+}
+}  // namespace
+
+int p2p_halo_plan_need(p2p_ctx* c, const void* d_topo_all, int npeer, int me, const int* peer_nleaf, int nleaf_max, int nnode_max,
+                       void* d_marks, int64_t* need_total) {
+    USE(c);
+    if (npeer < 1 || npeer > p2p::kHaloPeers || me < 0 || me >= npeer || !peer_nleaf || !need_total || (npeer > 1 && (!d_topo_all || !d_marks)))
+        return fail(P2P_ERR_ARG, "bad halo plan arguments");
+    cudaStream_t st = c->stream;
+    long long off_tb, off_son, off_leaf, stride;
+    p2p_topo_layout(nleaf_max, nnode_max, &off_tb, &off_son, &off_leaf, &stride);
+    p2p::PeerMap M;
+    memset(&M, 0, sizeof M);
+    int G = 0, bound[p2p::kHaloPeers + 1];
+    for (int p = 0; p < npeer; p++) {
+        need_total[p] = 0;
+        if (p == me) continue;
+        M.first[M.nslot] = G;
+        M.leaf_off[M.nslot] = ((long long)p * stride + off_leaf) / 8;
+        bound[M.nslot] = G;
+        M.nslot++;
+        G += peer_nleaf[p];
+    }
+    M.first[M.nslot] = G;
+    bound[M.nslot] = G;
+    if (G != c->nghostleaf) return fail(P2P_ERR_STATE, "the peer walk announced %d ghost leaves, the peers hold %d", c->nghostleaf, G);
+    c->nghost = 0;
+    if (G == 0) return 0;
+    CU(c->halo_cnt.reserve((size_t)G + 1, st));
+    CU(cudaMemsetAsync(d_marks, 0, (size_t)G, st));
+    if (c->ntask) p2p::halo_mark_kernel<<<(unsigned)((c->ntask + 255) / 256), 256, 0, st>>>(c->ts.p, c->ntask, c->nleaf, reinterpret_cast<unsigned char*>(d_marks));
+    p2p::halo_need_counts_kernel<<<(G + 255) / 256, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(d_marks), G, M,
+                                                                 reinterpret_cast<const int2*>(d_topo_all), c->halo_cnt.p);
+    CU(cudaGetLastError());
+    int r = halo_scan(c, G, st);
+    if (r) return r;
+    CU(c->leaf.reserve((size_t)c->nleaf + G + 1, st, (size_t)c->nleaf));
+    p2p::halo_ghost_table_kernel<<<(G + 255) / 256, 256, 0, st>>>(c->halo_off.p, c->halo_cnt.p, G, (int)c->npart, kStage, c->leaf.p + c->nleaf,
+                                                                 c->d_bad + 1);
+    CU(cudaGetLastError());
+    long long tot[p2p::kHaloPeers];
+    if ((r = halo_totals(c, bound, M.nslot, tot, st))) return r;
+    long long sum = 0;
+    for (int p = 0, s = 0; p < npeer; p++) {
+        if (p == me) continue;
+        need_total[p] = tot[s];
+        sum += tot[s++];
+    }
+    if (c->npart + sum > 0x7fffffffLL) return fail(P2P_ERR_ARG, "local + ghost particles exceed 2^31");
+    c->nghost = sum;
+    c->csr_valid = false;
+    c->bounds_n = std::min(c->bounds_n, c->nleaf);
+    CU(c->part.reserve((size_t)(c->npart + sum) + 1, st, (size_t)c->npart));
+    return 0;
+}
+
+int p2p_halo_plan_give(p2p_ctx* c, const void* d_asked, int nreq, int64_t* give_total) {
+    USE(c);
+    if (nreq < 0 || nreq > 31 || (nreq && (!d_asked || !give_total))) return fail(P2P_ERR_ARG, "bad halo plan arguments");
+    cudaStream_t st = c->stream;
+    const long long n = (long long)nreq * c->nleaf;
+    for (int q = 0; q < nreq; q++) give_total[q] = 0;
+    if (n == 0) return 0;
+    CU(c->halo_cnt.reserve((size_t)n + 1, st));
+    p2p::halo_give_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const unsigned char*>(d_asked), n, c->nleaf, c->leaf.p,
+                                                                              c->halo_cnt.p);
+    CU(cudaGetLastError());
+    int r = halo_scan(c, n, st);
+    if (r) return r;
+    int bound[32];
+    for (int q = 0; q <= nreq; q++) bound[q] = q * c->nleaf;
+    long long tot[32];
+    if ((r = halo_totals(c, bound, nreq, tot, st))) return r;
+    for (int q = 0; q < nreq; q++) give_total[q] = tot[q];
+    return 0;
+}
+
+int p2p_halo_gather(p2p_ctx* c, const void* d_asked, int nreq, void* d_send) {
+    USE(c);
+    const long long n = (long long)nreq * c->nleaf;
+    if (n == 0) return 0;
+    if (!d_asked || !d_send) return fail(P2P_ERR_ARG, "null device pointer");
+    p2p::halo_gather_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const unsigned char*>(d_asked), n, c->nleaf, c->leaf.p,
+                                                                                      c->halo_off.p, c->part.p, reinterpret_cast<int4*>(d_send));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int p2p_halo_set_particles(p2p_ctx* c, const void* d_recv, int64_t nbody) {
+    USE(c);
+    if (nbody != c->nghost) return fail(P2P_ERR_STATE, "%lld ghost particles arrived, the plan expects %lld", (long long)nbody, c->nghost);
+    if (nbody && !d_recv) return fail(P2P_ERR_ARG, "null device pointer");
+    if (nbody) CU(cudaMemcpyAsync(c->part.p + c->npart, d_recv, (size_t)nbody * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
 }
 
 void* p2p_device_particles(p2p_ctx* c) { return c ? c->part.p : nullptr; }

@@ -42,6 +42,9 @@ namespace p2p {
 
 constexpr int kStages = 2;
 constexpr int kPolyTerms = 9;          // R(v) = c[0] + c[1] v + ... + c[8] v^8
+constexpr int kFarDegree = 6;          // H(t) = cf[0] + ... + cf[6] t^6, t = 1 / (w + far_shift)
+constexpr int kFarTerms = kFarDegree + 1;
+constexpr unsigned kFarBit = 0x80000000u;
 
 struct KernelParams {
     const int4* part;        // fixed-point positions + mass bits, local then ghost particles
@@ -59,6 +62,13 @@ struct KernelParams {
     float c[kPolyTerms];     // q[k+2] / log2(e)^((k+2)/2): coefficients in the kernel's length unit
     float out_scale;         // mass / unit^2
     float far_coord;         // coordinate offset that makes a dummy source contribute exactly 0
+    // near / far split of every CSR row (csr_pack.cuh): the first row_mid[row] columns are NEAR source leaves, the rest
+    // FAR ones (every particle pair of the leaf pair at u >= P2P_U_FAR); columns carry the class in bit 31
+    const int* row_mid;
+    unsigned int* err;       // sticky error flag (a source leaf larger than the stage was skipped)
+    int rows_per_warp;       // 0: persistent warps; k: a warp retires after k rows (second-generation kernel)
+    float cf[kFarTerms];     // far-field polynomial H(t), t = 1 / (r'^2 + far_shift) (tools/fit_gfactor.py)
+    float far_shift;
 };
 
 // MUFU.RSQ / MUFU.EX2.  The file is compiled with --use_fast_math, under which rsqrtf / exp2f ARE the bare
@@ -211,7 +221,7 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, u
                                            long long e_end, int lane) {
     int cnt = 0, start = 0;
     if (e + lane < e_end) {
-        const int s = __ldg(P.col + e + lane);
+        const int s = (int)((unsigned)__ldg(P.col + e + lane) & ~kFarBit);
         const int2 ld = __ldg(P.leaf + s);
         start = ld.x;
         cnt = ld.y;
@@ -227,7 +237,13 @@ __device__ __forceinline__ int issue_chunk(const KernelParams& P, int4* stage, u
     const unsigned fit = __ballot_sync(0xffffffffu, lane < nl && incl <= STAGE);
     const int nfit = __popc(fit);                     // leaves are taken in order, so `fit` is a prefix mask
     int total = __shfl_sync(0xffffffffu, incl, nfit > 0 ? nfit - 1 : 0);
-    if (nfit == 0) total = 0;
+    if (nfit == 0) {
+        // the next source leaf alone exceeds the stage (only unvalidated device-side ghost tables can do that): skip it
+        // and raise the flag the host reads at its next synchronisation point, instead of spinning on it forever
+        total = 0;
+        if (lane == 0) atomicOr(P.err, 1u);
+        e += 1;
+    }
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)total * 16u);
     __syncwarp();
     // Source leaves that follow each other in the particle array (consecutive leaf ids of one tree do)
@@ -441,6 +457,269 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows_kernel(const KernelParams 
             }
             __syncwarp();
         }
+    }
+}
+
+
+// ================================================================================================
+// Second-generation row kernel: ONE pass per row (all <= 32 targets of the leaf in registers, so every source is
+// staged and converted once per row instead of once per 16 targets), and two slice bodies per row:
+//   NEAR  source leaves: the full kernel (eps clamp, rsqrt, exp2, degree-10 polynomial): 22 FP32-pipe instructions per pair,
+//   FAR   source leaves (tight leaf bounds at least 2 r_s P2P_U_FAR apart, 2/3 of all pairs): no clamp, no rsqrt --
+//         f = 2^(-w) H(t) with t = MUFU.RCP(w + 1/2) and a degree-6 polynomial (relative error 1.3e-7): 17 instructions,
+//         the shift and the negation of the exponent folded into FFMAs.
+// The 32 x 3 accumulators of a lane are reduced over the warp by a transposing butterfly (31 shuffles per
+// component instead of 160), which leaves target j's sum in lane j.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool TRUNC>
+__device__ __forceinline__ void pair_near2(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty,
+                                           float2 tz, float2& ax, float2& ay, float2& az) {
+    const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
+    const float2 q2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    float2 r2;
+    r2.x = fmaxf(q2.x, P.eps2);
+    r2.y = fmaxf(q2.y, P.eps2);
+    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    float2 f;
+    if (TRUNC) {
+        const float2 a = __fmul2_rn(r2, make_float2(-1.f, -1.f));
+        const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        const float2 v = __fmul2_rn(r2, rinv);
+        // (a Newton step on rinv, 3 more instructions, changed the measured force error by 2 %: MUFU.RSQ is not what limits it)
+        float2 E = make_float2(P.c[8], P.c[8]), O = make_float2(P.c[7], P.c[7]);
+        E = __ffma2_rn(E, r2, make_float2(P.c[6], P.c[6]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[5], P.c[5]));
+        E = __ffma2_rn(E, r2, make_float2(P.c[4], P.c[4]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[3], P.c[3]));
+        E = __ffma2_rn(E, r2, make_float2(P.c[2], P.c[2]));
+        O = __ffma2_rn(O, r2, make_float2(P.c[1], P.c[1]));
+        const float2 c0r = __ffma2_rn(rinv, rinv, make_float2(P.c[0], P.c[0]));   // c0 + rinv^2
+        E = __ffma2_rn(E, r2, c0r);
+        const float2 T = __ffma2_rn(v, O, E);                                     // rinv^2 + R(v)
+        f = __fmul2_rn(__fmul2_rn(e, rinv), T);
+    } else {
+        f = __fmul2_rn(__fmul2_rn(rinv, rinv), rinv);
+    }
+    ax = __ffma2_rn(dx, f, ax);
+    ay = __ffma2_rn(dy, f, ay);
+    az = __ffma2_rn(dz, f, az);
+}
+
+__device__ __forceinline__ void pair_far2(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty, float2 tz,
+                                          float2& ax, float2& ay, float2& az) {
+    const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
+    const float2 sh = make_float2(P.far_shift, P.far_shift);
+    const float2 ws = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __ffma2_rn(dx, dx, sh)));     // w + shift
+    const float2 a = __ffma2_rn(ws, make_float2(-1.f, -1.f), sh);                         // -w
+    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    const float2 t = make_float2(rcp_approx(ws.x), rcp_approx(ws.y));
+    float2 p = make_float2(P.cf[kFarDegree], P.cf[kFarDegree]);
+#pragma unroll
+    for (int k = kFarDegree - 1; k >= 0; k--) p = __ffma2_rn(p, t, make_float2(P.cf[k], P.cf[k]));
+    const float2 f = __fmul2_rn(e, p);
+    ax = __ffma2_rn(dx, f, ax);
+    ay = __ffma2_rn(dy, f, ay);
+    az = __ffma2_rn(dz, f, az);
+}
+
+constexpr int kRowTargets = 32;         // = P2P_MAX_LEAF
+
+template <int STAGE>
+struct alignas(128) WarpSmem2 {
+    int4 stage[kStages][STAGE];
+    TargetPair tgt[kRowTargets / 2];
+    uint64_t full[kStages];
+};
+
+// sum over the warp of v[j] (j = 0..31, one value per target and lane); returns target `lane`'s total
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float keep = up ? v[i + o] : v[i];
+            const float send = up ? v[i] : v[i + o];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+// All chunks and slices of the columns [e, e_end) of one row against the first 2 K targets, with the NEAR or the FAR body.
+template <int K, bool FAR, int NSRC, int STAGE, bool TRUNC>
+__device__ __forceinline__ void run_range2(const KernelParams& P, WarpSmem2<STAGE>& S, const int4 c4, long long e, const long long e_end,
+                                           const int lane, uint32_t& phase0, uint32_t& phase1, float2 (&ax)[kRowTargets / 2],
+                                           float2 (&ay)[kRowTargets / 2], float2 (&az)[kRowTargets / 2]) {
+    constexpr int SLICE = 32 * NSRC;
+    float sx[NSRC], sy[NSRC], sz[NSRC];
+#pragma unroll
+    for (int q = 0; q < NSRC; q++) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+    int have = 0;                                 // sources [0, have) of the slice are already in registers
+    auto load_source = [&](const int4* buf, int idx, int q) {
+        const int4 s4 = buf[idx];
+        sx[q] = (float)(s4.x - c4.x) * P.k_fix;
+        sy[q] = (float)(s4.y - c4.y) * P.k_fix;
+        sz[q] = (float)(s4.z - c4.z) * P.k_fix;
+    };
+    auto compute_slice = [&]() {
+#pragma unroll
+        for (int p = 0; p < K; p++) {
+            const float4 txy = S.tgt[p].xy;
+            const float2 tz = S.tgt[p].z;
+#pragma unroll
+            for (int q = 0; q < NSRC; q++) {
+                if (FAR)
+                    pair_far2(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]), make_float2(txy.x, txy.y),
+                              make_float2(txy.z, txy.w), tz, ax[p], ay[p], az[p]);
+                else
+                    pair_near2<TRUNC>(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]),
+                                              make_float2(txy.x, txy.y), make_float2(txy.z, txy.w), tz, ax[p], ay[p], az[p]);
+            }
+        }
+    };
+    int np0 = 0, np1 = 0, cur = 0;
+    fence_proxy_async();
+    np0 = issue_chunk<STAGE>(P, S.stage[0], &S.full[0], e, e_end, lane);
+    bool more = e < e_end;
+    for (;;) {                                            // chunks of the range
+        if (more) {
+            // the other stage was fully consumed (its values are in registers) before this point
+            fence_proxy_async();
+            const int n = issue_chunk<STAGE>(P, S.stage[cur ^ 1], &S.full[cur ^ 1], e, e_end, lane);
+            if (cur) np0 = n; else np1 = n;
+        }
+        const bool last_chunk = !more;
+        more = e < e_end;
+        if (cur) { mbar_wait(&S.full[1], phase1); phase1 ^= 1u; } else { mbar_wait(&S.full[0], phase0); phase0 ^= 1u; }
+        const int4* buf = S.stage[cur];
+        const int n = cur ? np1 : np0;
+        int pos = 0;
+        for (;;) {                                        // slices; ONE call site of the slice code
+            bool run, more_slices;
+            if (have == 0 && n - pos >= SLICE) {
+#pragma unroll
+                for (int q = 0; q < NSRC; q++) load_source(buf, pos + q * 32 + lane, q);
+                pos += SLICE;
+                run = true;
+                more_slices = pos < n;
+            } else {
+                // chunk boundary: top up the carried slice / keep the leftover for the next chunk
+                const int avail = n - pos;
+                const bool full = have + avail >= SLICE;
+                const int take = full ? SLICE - have : avail;
+#pragma unroll
+                for (int q = 0; q < NSRC; q++) {
+                    const int k = q * 32 + lane - have;
+                    if (k >= 0 && k < take) load_source(buf, pos + k, q);
+                }
+                pos += take;
+                have += take;
+                run = full;
+                if (!full && last_chunk && have > 0) {    // ragged tail of the range: pad with dummies
+#pragma unroll
+                    for (int q = 0; q < NSRC; q++) {
+                        if (q * 32 + lane >= have) { sx[q] = P.far_coord; sy[q] = 0.f; sz[q] = 0.f; }
+                    }
+                    run = true;
+                }
+                if (run) have = 0;
+                more_slices = full;
+            }
+            if (run) compute_slice();
+            if (!more_slices) break;
+        }
+        __syncwarp();
+        if (last_chunk) break;
+        cur ^= 1;
+    }
+}
+
+template <int NSRC, int STAGE, bool TRUNC, int MINB>
+__global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpSmem2<STAGE>& S = reinterpret_cast<WarpSmem2<STAGE>*>(smem_raw)[wid];
+    constexpr int TP = kRowTargets / 2;
+
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    uint32_t phase0 = 0, phase1 = 0;
+    const unsigned int n_active = __ldg(P.n_active);
+    // non-persistent mode: the block retires after a few rows per warp, so that the block scheduler can hand its slot to a
+    // kernel of a higher-priority stream (NCCL, the halo walk and packing of a multi-rank step) while this kernel runs
+    int budget = P.rows_per_warp > 0 ? P.rows_per_warp : 0x7fffffff;
+
+    for (; budget > 0; budget--) {
+        int row = -1;
+        if (lane == 0) {
+            const unsigned int idx = atomicAdd(P.counter, 1u);
+            if (idx < n_active) row = __ldg(P.row_order + idx);
+        }
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row < 0) break;
+        const int2 tl = __ldg(P.leaf + row);
+        const int nt = min(tl.y, kRowTargets);
+        const long long e_begin = __ldg(P.row_ptr + row);
+        const long long e_end = __ldg(P.row_ptr + row + 1);
+        if (nt <= 0 || e_begin >= e_end) continue;
+        const long long e_mid = TRUNC ? e_begin + __ldg(P.row_mid + row) : e_end;
+        // reference point of the row: its first target particle (fixed-point)
+        const int4 c4 = __ldg(P.part + tl.x);
+        {   // targets -> shared: negated, relative to c4; padding slots repeat the first target
+            const int4 t4 = __ldg(P.part + tl.x + (lane < nt ? lane : 0));
+            float* base = reinterpret_cast<float*>(&S.tgt[lane >> 1]);
+            base[0 + (lane & 1)] = -(float)(t4.x - c4.x) * P.k_fix;
+            base[2 + (lane & 1)] = -(float)(t4.y - c4.y) * P.k_fix;
+            base[4 + (lane & 1)] = -(float)(t4.z - c4.z) * P.k_fix;
+        }
+        __syncwarp();
+
+        float2 ax[TP], ay[TP], az[TP];
+#pragma unroll
+        for (int j = 0; j < TP; j++) ax[j] = ay[j] = az[j] = make_float2(0.f, 0.f);
+
+        switch ((nt + 1) >> 1) {                              // target pairs of this row (warp-uniform)
+#define P2P_CASE(k)                                                                                                             \
+    case k:                                                                                                                     \
+        if (e_mid > e_begin) run_range2<k, false, NSRC, STAGE, TRUNC>(P, S, c4, e_begin, e_mid, lane, phase0, phase1, ax, ay, az); \
+        if (TRUNC && e_end > e_mid) run_range2<k, true, NSRC, STAGE, TRUNC>(P, S, c4, e_mid, e_end, lane, phase0, phase1, ax, ay, az); \
+        break;
+            P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
+            P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
+#undef P2P_CASE
+            default: break;
+        }
+
+        // transposing butterfly: afterwards lane j holds target j's sums
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < TP; j++) { v[2 * j] = ax[j].x; v[2 * j + 1] = ax[j].y; }
+        const float rx = transpose_reduce32(v, lane);
+#pragma unroll
+        for (int j = 0; j < TP; j++) { v[2 * j] = ay[j].x; v[2 * j + 1] = ay[j].y; }
+        const float ry = transpose_reduce32(v, lane);
+#pragma unroll
+        for (int j = 0; j < TP; j++) { v[2 * j] = az[j].x; v[2 * j + 1] = az[j].y; }
+        const float rz = transpose_reduce32(v, lane);
+        if (lane < nt) {
+            float4* dst = P.acc + tl.x + lane;
+            float4 a = *dst;
+            a.x = fmaf(rx, P.out_scale, a.x);
+            a.y = fmaf(ry, P.out_scale, a.y);
+            a.z = fmaf(rz, P.out_scale, a.z);
+            *dst = a;
+        }
+        __syncwarp();
     }
 }
 

@@ -50,6 +50,7 @@ def load_library():
     L.p2p_set_kernel_variant.argtypes = [C.c_void_p, C.c_int]
     L.p2p_set_box.argtypes = [C.c_void_p, _dp, C.c_double]
     L.p2p_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.p2p_set_far_threshold.argtypes = [C.c_void_p, C.c_double]
     L.p2p_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.p2p_upload_particles.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64]
     L.p2p_upload_leaves.argtypes = [C.c_void_p, _ip, _ip, C.c_int]
@@ -61,6 +62,7 @@ def load_library():
     L.p2p_counts.argtypes = [C.c_void_p, _lp, _lp]
     L.p2p_accumulated_counts.argtypes = [C.c_void_p, _lp, _lp]
     L.p2p_download_csr.argtypes = [C.c_void_p, _lp, _ip]
+    L.p2p_download_csr_class.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), _ip]
     L.p2p_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.p2p_step_host.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, _ip, _ip, C.c_int, _ip, _ip, C.c_int64, _dp,
                                 C.c_int64, C.c_int]
@@ -76,7 +78,7 @@ def load_library():
     L.p2p_csr_duplicates.argtypes = [C.c_void_p, _lp]
     L.p2p_download_acc_original.argtypes = [C.c_void_p, _dp]
     L.p2p_tree_set_option.argtypes = [C.c_void_p, C.c_int]
-    L.p2p_route_load.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int64]
+    L.p2p_route_load.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int]
     L.p2p_route_partition.argtypes = [C.c_void_p, C.c_int, _dp, _ip]
     L.p2p_route_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.p2p_route_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -90,15 +92,26 @@ def load_library():
     L.p2p_midfield_enable.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.p2p_midfield_compute.argtypes = [C.c_void_p, _lp]
     L.p2p_midfield_multipoles.argtypes = [C.c_void_p, C.c_void_p]
-    L.p2p_midfield_compute_peers.argtypes = [C.c_void_p, C.c_int, _ip, _ip, C.c_void_p, C.c_void_p, _lp]
     L.p2p_midfield_download.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.POINTER(C.c_float)]
-    L.p2p_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.p2p_tree_walk_peers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
-                                      C.c_void_p, C.c_void_p, C.c_void_p]
-    L.p2p_ghost_marks.argtypes = [C.c_void_p, C.c_void_p]
-    L.p2p_gather_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.p2p_set_ghosts_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
     L.p2p_device_acc.argtypes = [C.c_void_p]
+    L.p2p_resident_count.argtypes = [C.c_void_p, _lp]
+    L.p2p_forces_local.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int]
+    L.p2p_set_chunk_tasks.argtypes = [C.c_void_p, C.c_int64]
+    L.p2p_step_timings.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 4 + [_ip]
+    L.p2p_swap_lists.argtypes = [C.c_void_p]
+    L.p2p_set_force_blocks.argtypes = [C.c_void_p, C.c_int]
+    L.p2p_reserve_ghosts.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    L.p2p_tree_walk_range.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int]
+    L.p2p_set_rank.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.p2p_topology_stride.argtypes = [C.c_int, C.c_int, _lp]
+    L.p2p_tree_export_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.p2p_tree_walk_peers_packed.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int, C.c_int, _ip, _ip,
+                                             C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.p2p_halo_plan_need.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _ip, C.c_int, C.c_int, C.c_void_p, _lp]
+    L.p2p_halo_plan_give.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _lp]
+    L.p2p_halo_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.p2p_halo_set_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.p2p_midfield_compute_peers_packed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, _lp]
     _lib = L
     return L
 
@@ -156,6 +169,10 @@ class P2PContext:
 
     def set_tuning(self, targets_per_pass=0, sources_per_lane=0, min_blocks=0):
         self._chk(self._L.p2p_set_tuning(self._h, int(targets_per_pass), int(sources_per_lane), int(min_blocks)))
+
+    def set_far_threshold(self, u_far=-1.0):
+        """near / far split of the list in u = r / 2 r_s (< 0: default, 0: every source leaf through the full kernel body)"""
+        self._chk(self._L.p2p_set_far_threshold(self._h, float(u_far)))
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self._L.p2p_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
@@ -233,12 +250,26 @@ class P2PContext:
         self._chk(self._L.p2p_accumulated_counts(self._h, C.byref(nt), C.byref(npairs)))
         return nt.value, npairs.value
 
-    def download_csr(self):
+    def download_csr(self, raw=False):
+        """(row_ptr, col) of the packed list.  On the device a row holds its near source leaves first, then its far ones
+        (download_csr_class), each class in ascending order; raw=False returns the canonical form (whole rows ascending)."""
         nt, _ = self.counts()
         row = np.zeros(self.nleaf + 1, np.int64)
         col = np.zeros(max(nt, 1), np.int32)
         self._chk(self._L.p2p_download_csr(self._h, row.ctypes.data_as(_lp), col.ctypes.data_as(_ip)))
-        return row, col[:nt]
+        col = col[:nt]
+        if not raw and nt:
+            rid = np.repeat(np.arange(self.nleaf), np.diff(row))
+            col = col[np.lexsort((col, rid))]
+        return row, col
+
+    def download_csr_class(self):
+        """(is_far per CSR column, number of near columns per row): the near / far split the force kernel uses"""
+        nt, _ = self.counts()
+        far = np.zeros(max(nt, 1), np.uint8)
+        near = np.zeros(max(self.nleaf, 1), np.int32)
+        self._chk(self._L.p2p_download_csr_class(self._h, far.ctypes.data_as(C.POINTER(C.c_ubyte)), near.ctypes.data_as(_ip)))
+        return far[:nt], near[:self.nleaf]
 
     def last_timings(self):
         a, b = C.c_float(), C.c_float()
@@ -357,10 +388,11 @@ class P2PContext:
         return acc
 
     # ---- particle routing on the device (multi-rank)
-    def route_load(self, pos, first_index):
+    def route_load(self, pos, first_index, append=False):
+        """host slab -> resident device arrays (global ids first_index ...); append=True adds a further piece of the slab"""
         pos = _f64(pos)
         self._chk(self._L.p2p_route_load(self._h, pos.ctypes.data_as(_dp), pos.shape[1] if pos.ndim == 2 else 3, pos.shape[0],
-                                         int(first_index)))
+                                         int(first_index), 1 if append else 0))
 
     def route_partition(self, nproc, split):
         sp = np.ascontiguousarray(split, np.float64)
@@ -426,13 +458,6 @@ class P2PContext:
     def midfield_multipoles(self, d_M):
         self._chk(self._L.p2p_midfield_multipoles(self._h, d_M))
 
-    def midfield_compute_peers(self, peer_nleaf, peer_nnode, d_box_all, d_M_all):
-        nl, nn = _i32(peer_nleaf), _i32(peer_nnode)
-        n = C.c_int64()
-        self._chk(self._L.p2p_midfield_compute_peers(self._h, len(nl), nl.ctypes.data_as(_ip), nn.ctypes.data_as(_ip), d_box_all, d_M_all,
-                                                     C.byref(n)))
-        return n.value
-
     def midfield_download(self):
         info = self.tree_info()
         nl, nn = info["nleaf"], info["nnode"]
@@ -444,24 +469,82 @@ class P2PContext:
         return out
 
     # ---- multi-rank device path (device pointers, e.g. tensor.data_ptr())
-    def tree_export(self, d_box, d_son, d_leaf, d_bounds=None):
-        self._chk(self._L.p2p_tree_export(self._h, d_box, d_son, d_leaf, d_bounds))
+    # ---- multi-rank exchange: packed topology, local / remote phases, device-side halo plan
+    def resident_count(self):
+        n = C.c_int64()
+        self._chk(self._L.p2p_resident_count(self._h, C.byref(n)))
+        return n.value
 
-    def tree_walk_peers(self, theta, rcut, period, tcenter, twidth, me, peer_nleaf, peer_nnode, d_box_all, d_son_all, d_bounds_all=None):
-        tc, tw = np.ascontiguousarray(tcenter, np.float64), np.ascontiguousarray(twidth, np.float64)
+    def forces_local(self, theta, rcut, period, tcenter, twidth, compute=True):
+        """walk (own tree + own periodic images), packing and forces of the device-built tree, in target chunks"""
+        tc, tw = _f64(tcenter), _f64(twidth)
+        self._chk(self._L.p2p_forces_local(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp), tw.ctypes.data_as(_dp),
+                                           1 if compute else 0))
+
+    def set_chunk_tasks(self, max_tasks):
+        self._chk(self._L.p2p_set_chunk_tasks(self._h, int(max_tasks)))
+
+    def step_timings(self):
+        v = [C.c_float() for _ in range(4)]
+        n = C.c_int()
+        self._chk(self._L.p2p_step_timings(self._h, *[C.byref(x) for x in v], C.byref(n)))
+        return dict(build_ms=v[0].value, walk_ms=v[1].value, csr_ms=v[2].value, force_ms=v[3].value, chunks=n.value)
+
+    def swap_lists(self):
+        self._chk(self._L.p2p_swap_lists(self._h))
+
+    def set_force_blocks(self, rows_per_warp=0):
+        self._chk(self._L.p2p_set_force_blocks(self._h, int(rows_per_warp)))
+
+    def reserve_ghosts(self, nghostleaf, nghost):
+        self._chk(self._L.p2p_reserve_ghosts(self._h, int(nghostleaf), int(nghost)))
+
+    def tree_walk_range(self, theta, rcut, period, tcenter, twidth, leaf_lo, leaf_hi):
+        tc, tw = _f64(tcenter), _f64(twidth)
+        self._chk(self._L.p2p_tree_walk_range(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp), tw.ctypes.data_as(_dp),
+                                              int(leaf_lo), int(leaf_hi)))
+
+    def set_rank(self, rank, nranks):
+        self._chk(self._L.p2p_set_rank(self._h, int(rank), int(nranks)))
+
+    def topology_stride(self, nleaf_max, nnode_max):
+        v = C.c_int64()
+        self._chk(self._L.p2p_topology_stride(int(nleaf_max), int(nnode_max), C.byref(v)))
+        return v.value
+
+    def tree_export_packed(self, d_block, nleaf_max, nnode_max):
+        self._chk(self._L.p2p_tree_export_packed(self._h, C.c_void_p(d_block), int(nleaf_max), int(nnode_max)))
+
+    def tree_walk_peers_packed(self, theta, rcut, period, tcenter, twidth, me, peer_nleaf, peer_nnode, d_all, nleaf_max, nnode_max, include_me):
+        tc, tw = _f64(tcenter), _f64(twidth)
         nl, nn = _i32(peer_nleaf), _i32(peer_nnode)
-        self._chk(self._L.p2p_tree_walk_peers(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp),
-                                              tw.ctypes.data_as(_dp), len(nl), int(me), nl.ctypes.data_as(_ip),
-                                              nn.ctypes.data_as(_ip), d_box_all, d_son_all, d_bounds_all))
+        self._chk(self._L.p2p_tree_walk_peers_packed(self._h, float(theta), float(rcut), float(period), tc.ctypes.data_as(_dp),
+                                                     tw.ctypes.data_as(_dp), len(nl), int(me), nl.ctypes.data_as(_ip), nn.ctypes.data_as(_ip),
+                                                     C.c_void_p(d_all), int(nleaf_max), int(nnode_max), int(include_me)))
 
-    def ghost_marks(self, d_marks):
-        self._chk(self._L.p2p_ghost_marks(self._h, d_marks))
+    def halo_plan_need(self, d_topo_all, me, peer_nleaf, nleaf_max, nnode_max, d_marks):
+        nl = _i32(peer_nleaf)
+        out = np.zeros(len(nl), np.int64)
+        self._chk(self._L.p2p_halo_plan_need(self._h, C.c_void_p(d_topo_all), len(nl), int(me), nl.ctypes.data_as(_ip), int(nleaf_max),
+                                             int(nnode_max), C.c_void_p(d_marks), out.ctypes.data_as(_lp)))
+        return out
 
-    def gather_leaves(self, d_marks, d_offset, d_out):
-        self._chk(self._L.p2p_gather_leaves(self._h, d_marks, d_offset, d_out))
+    def halo_plan_give(self, d_asked, nreq):
+        out = np.zeros(max(nreq, 1), np.int64)
+        self._chk(self._L.p2p_halo_plan_give(self._h, C.c_void_p(d_asked), int(nreq), out.ctypes.data_as(_lp)))
+        return out[:nreq]
 
-    def set_ghosts_device(self, d_part, nbody, d_start, d_count, nghostleaf):
-        self._chk(self._L.p2p_set_ghosts_device(self._h, d_part, int(nbody), d_start, d_count, int(nghostleaf)))
+    def halo_gather(self, d_asked, nreq, d_send):
+        self._chk(self._L.p2p_halo_gather(self._h, C.c_void_p(d_asked), int(nreq), C.c_void_p(d_send)))
+
+    def halo_set_particles(self, d_recv, nbody):
+        self._chk(self._L.p2p_halo_set_particles(self._h, C.c_void_p(d_recv), int(nbody)))
+
+    def midfield_compute_peers_packed(self, npeer, d_topo_all, nleaf_max, nnode_max, d_M_all):
+        n = C.c_int64()
+        self._chk(self._L.p2p_midfield_compute_peers_packed(self._h, int(npeer), C.c_void_p(d_topo_all), int(nleaf_max), int(nnode_max),
+                                                            C.c_void_p(d_M_all), C.byref(n)))
+        return n.value
 
     def tree_set_option(self, seq_sum_plain_max=-1):
         self._chk(self._L.p2p_tree_set_option(self._h, int(seq_sum_plain_max)))

@@ -1,14 +1,23 @@
-"""Multi-rank short-range step with the list producers ON THE DEVICES (csrc/device_tree.cuh).
+"""Multi-rank short-range step with the list producers ON THE DEVICES (csrc/device_tree.cuh, csrc/halo.cuh).
 
 The reference ships 27 x P pruned halo images around a ring and re-walks each of them
-(1_Indexing/src/fmm.c:1026-1145, 1_Indexing/src/remotes.c:740-809).  Here every rank
-  1. builds its kd-tree on its GPU (p2p_tree_build),
-  2. all-gathers the tree TOPOLOGY of all ranks (kd cells + sons + leaf sizes: a few MB, no particles),
-  3. walks its tree against every rank's tree for all 27 displacements on the GPU, evaluating the sender-side
-     cuts of prepare_sendtree2 on the fly (p2p_tree_walk_peers) -- the task multiset is the reference's,
-  4. asks each owner only for the leaves its list references (all-to-all of one byte per leaf), and
-  5. receives exactly those particles (all-to-all-v of fixed-point int4), already in the global periodic frame,
-then packs the list and runs the force kernel.  NCCL over NVLink on the GPUs; with the gloo backend (CPU test rigs,
+(1_Indexing/src/fmm.c:1026-1145, 1_Indexing/src/remotes.c:740-809), strictly one after the other.  Here every rank
+
+  local phase (needs no communication; compute stream)
+    1. builds its kd-tree on its GPU,
+    2. walks it against itself and its own periodic images, packs that list and launches the force kernel on it;
+  remote phase (second, high-priority stream; hidden behind the local force kernel)
+    3. copies its tree TOPOLOGY (kd cells, tight leaf bounds, sons, leaf sizes) into one block and all-gathers the blocks
+       (ONE collective, no particles),
+    4. walks its tree against every other rank's tree for all 27 displacements on the GPU, evaluating the sender-side
+       cuts of prepare_sendtree2 on the fly (p2p_tree_walk_peers_packed) -- the task multiset is the reference's,
+    5. asks each owner only for the leaves its list references (all-to-all of one byte per leaf), and
+    6. receives exactly those particles (all-to-all-v of fixed-point int4; the marks, counts, offsets and the gather run
+       as kernels, the host only learns the split sizes),
+    7. packs the remote list into the context's second list set and runs the force kernel on it after the local one.
+
+The local force kernel runs in its non-persistent form (p2p_set_force_blocks), so NCCL's kernels and the small kernels of
+the remote phase get SM slots while it computes.  NCCL over NVLink on the GPUs; with the gloo backend (CPU test rigs,
 several ranks sharing one GPU) the same exchanges are staged through host memory."""
 import time
 
@@ -28,14 +37,19 @@ def _all_gather_v(t, sizes, group):
     P, mx = len(sizes), int(max(sizes))
     buf = torch.zeros(mx, dtype=t.dtype, device=t.device)
     buf[:t.numel()] = t
-    if _nccl(group):
-        out = torch.empty(P * mx, dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, buf, group=group)
-    else:
-        parts = [torch.empty(mx, dtype=t.dtype) for _ in range(P)]
-        dist.all_gather(parts, buf.cpu(), group=group)
-        out = torch.cat(parts).to(t.device)
+    out = _all_gather_blocks(buf, P, group)
     return [out[p * mx:p * mx + int(sizes[p])] for p in range(P)]
+
+
+def _all_gather_blocks(mine, P, group):
+    """equal-sized 1-D blocks of every rank, concatenated in rank order (one collective)"""
+    if _nccl(group):
+        out = torch.empty(P * mine.numel(), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out
+    parts = [torch.empty(mine.numel(), dtype=mine.dtype) for _ in range(P)]
+    dist.all_gather(parts, mine.cpu(), group=group)
+    return torch.cat(parts).to(mine.device)
 
 
 def _all_to_all_v(send, in_split, out_split, group):
@@ -49,31 +63,61 @@ def _all_to_all_v(send, in_split, out_split, group):
     return out.to(send.device)
 
 
-def _stream_of(ctx, dev):
-    if not ctx.stream_ptr:                      # torch ops, collectives and the library's kernels share one stream
-        ctx._torch_stream = torch.cuda.Stream(device=dev)
-        ctx.set_stream(ctx._torch_stream.cuda_stream)
-    return torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+def _gather_host_ints(vals, group, dev):
+    """a few host integers of every rank -> int64 array [P, len(vals)] on the host (one tiny collective)"""
+    P = dist.get_world_size(group)
+    mine = torch.tensor([int(v) for v in vals], dtype=torch.int64)
+    if _nccl(group):
+        out = torch.empty(P * len(vals), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine.to(dev), group=group)
+        return out.cpu().numpy().reshape(P, len(vals))
+    parts = [torch.empty(len(vals), dtype=torch.int64) for _ in range(P)]
+    dist.all_gather(parts, mine, group=group)
+    return torch.stack(parts).numpy()
+
+
+class Streams:
+    """The two streams of a rank's step (created once per context): compute (tree build, local walk, packing, force
+    kernels) and comm (exchanges, remote walk and packing; higher priority)."""
+
+    def __init__(self, ctx):
+        dev = torch.device("cuda", ctx.device)
+        self.dev = dev
+        if ctx.stream_ptr:
+            self.main = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+        else:
+            self.main = torch.cuda.Stream(device=dev)
+            ctx.set_stream(self.main.cuda_stream)
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.main_ptr = ctx.stream_ptr
+        self.ghost_guess = 0
+
+
+def _streams_of(ctx):
+    s = getattr(ctx, "_dist_streams", None)
+    if s is None or s.main_ptr != ctx.stream_ptr:
+        s = Streams(ctx)
+        ctx._dist_streams = s
+    return s
 
 
 def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl, bdr, direct_start, theta=0.4, periodic=True,
-                    truncated=True, group=None, acc_out=None, timings=None, midfield=False, literal_d6=False, p2p=True):
+                    truncated=True, group=None, acc_out=None, timings=None, midfield=False, literal_d6=False, p2p=True, overlap=True):
     """One rank's part of the step.  local_pos: this rank's particles (host, float64, caller's order; pinned for full
     PCIe rate); bdl/bdr/direct_start: its domain box and first split direction (host.domain_setup).
     midfield: also the multipole part (P2M/M2M on every rank, all-gather of the multipoles, M2L/L2L/L2P); literal_d6 and
     p2p=False are test knobs (replay the reference's zero-shift self exchange; skip the P2P forces).
     Returns (acc in the order of local_pos, ntask, npairs)."""
-    dev = torch.device("cuda", ctx.device)
-    stream = _stream_of(ctx, dev)
+    S = _streams_of(ctx)
     t0 = time.perf_counter()
     rs, rcut, eps = host.derived_params(box, nside, npart_total)
     ctx.set_physics(mass, eps, rs if truncated else 0.0)
     ctx.set_box([0.0, 0.0, 0.0], box)
     bdl, bdr = np.asarray(bdl, np.float64), np.asarray(bdr, np.float64)
-    with torch.cuda.stream(stream):
+    with torch.cuda.stream(S.main):
         ctx.midfield_enable(midfield, literal_d6)
         ctx.tree_build(local_pos, maxleaf, bdl, bdr, direct_start)
-        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings, midfield, p2p)
+        ntask, npairs = lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings, midfield, p2p, overlap, t0)
         acc = ctx.download_acc_original(acc_out)
     if timings is not None:
         timings["total_s"] = time.perf_counter() - t0
@@ -81,7 +125,7 @@ def run_device_step(ctx, local_pos, npart_total, box, maxleaf, nside, mass, bdl,
 
 
 def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside, mass, split, theta=0.4, periodic=True, truncated=True,
-                   group=None, timings=None, pinned_out=None):
+                   group=None, timings=None, pinned_out=None, overlap=True):
     """The same step starting one stage earlier: `slab_pos` is the slab of the global particle array this rank happens to
     hold (global ids first_index ...), `split` the rank kd-tree (host.domain_setup / host.domain_relax).  The slab is
     partitioned on the device exactly as the reference's prepare_body_inOrderOf_domain does, the groups are exchanged as
@@ -89,8 +133,8 @@ def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside,
     pinned_out: optional dict reused between steps for pinned result buffers (grown on demand).
     Returns (acc in TREE order, global ids of the tree positions, ntask, npairs)."""
     P, me = dist.get_world_size(group), dist.get_rank(group)
-    dev = torch.device("cuda", ctx.device)
-    stream = _stream_of(ctx, dev)
+    S = _streams_of(ctx)
+    dev = S.dev
     t0 = time.perf_counter()
     rs, rcut, eps = host.derived_params(box, nside, npart_total)
     ctx.set_physics(mass, eps, rs if truncated else 0.0)
@@ -98,27 +142,12 @@ def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside,
     center, width, direct = host.domain_boxes(P, box, split)
     dom = host.domain_of_rank(P, me)
     bdl, bdr = center[dom] - 0.5 * width[dom], center[dom] + 0.5 * width[dom]
-    with torch.cuda.stream(stream):
-        n = slab_pos.shape[0]
+    with torch.cuda.stream(S.main):
         ctx.route_load(slab_pos, first_index)
-        send = ctx.route_partition(P, split)
-        bufs = [torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(3)] + [torch.empty(max(n, 1), dtype=torch.int32, device=dev)]
-        ctx.route_export(*[b.data_ptr() for b in bufs])
-        s_t = torch.from_numpy(send.astype(np.int64))
-        r_t = torch.empty(P, dtype=torch.int64)
-        if _nccl(group):
-            rd = torch.empty(P, dtype=torch.int64, device=dev)
-            dist.all_to_all_single(rd, s_t.to(dev), group=group)
-            r_t = rd.cpu()
-        else:
-            dist.all_to_all_single(r_t, s_t, group=group)
-        recv = [int(v) for v in r_t]
-        got = [_all_to_all_v(b[:n], [int(v) for v in send], recv, group) for b in bufs]
-        nloc = int(sum(recv))
-        ctx.route_import(*[g.data_ptr() for g in got], nloc)
+        nloc = migrate(ctx, P, split, group, dev)
         t_route = time.perf_counter() - t0
         ctx.tree_build_resident(maxleaf, bdl, bdr, int(direct[dom]))
-        ntask, npairs = _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings)
+        ntask, npairs = lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings, False, True, overlap, t0)
         if pinned_out is not None:
             if pinned_out.get("n", 0) < nloc:
                 pinned_out["acc"] = torch.empty((int(nloc * 1.1) + 16, 3), dtype=torch.float64).pin_memory()
@@ -135,87 +164,120 @@ def route_and_step(ctx, slab_pos, first_index, npart_total, box, maxleaf, nside,
     return acc, idx, ntask, npairs
 
 
-def _lists_halo_forces(ctx, dev, t0, rcut, box, bdl, bdr, theta, periodic, group, timings, midfield=False, p2p=True):
-    """after the tree build: topology all-gather, walk against every rank's tree, halo fetch, packing, forces"""
+def migrate(ctx, P, split, group, dev):
+    """The particles resident on this rank's GPU (p2p_route_load, or the previous step's after the drift) move to the ranks
+    that own them under the rank kd-tree `split`: device partition with the reference's order, all-to-all-v of x, y, z and
+    the global id as device buffers, import in source-rank order (1_Indexing/src/domains.c:163-377).  Returns the new count."""
+    n = ctx.resident_count()
+    send = ctx.route_partition(P, split)
+    if P == 1:
+        return n
+    bufs = [torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(3)] + [torch.empty(max(n, 1), dtype=torch.int32, device=dev)]
+    ctx.route_export(*[b.data_ptr() for b in bufs])
+    recv = _gather_host_ints(send, group, dev)[:, dist.get_rank(group)]
+    got = [_all_to_all_v(b[:n], [int(v) for v in send], [int(v) for v in recv], group) for b in bufs]
+    nloc = int(recv.sum())
+    ctx.route_import(*[g.data_ptr() for g in got], nloc)
+    return nloc
+
+
+def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=None, midfield=False, p2p=True, overlap=True, t0=None):
+    """after the tree build: local phase (own tree and images) and remote phase (topology all-gather, walk against every
+    other rank's tree, halo fetch), packing and forces.  Returns (ntask, npairs) of this rank."""
     P, me = dist.get_world_size(group), dist.get_rank(group)
-    if True:
-        info = ctx.tree_info()
-        nl, nn = info["nleaf"], info["nnode"]
-        t1 = time.perf_counter()
-        # ---- topology of every rank
-        mine = torch.tensor([nl, nn, np.float64(info["max_leaf_width"]).view(np.int64)], dtype=torch.int64)
-        sizes = [torch.empty(3, dtype=torch.int64) for _ in range(P)]
-        if _nccl(group):
-            g = [torch.empty(3, dtype=torch.int64, device=dev) for _ in range(P)]
-            dist.all_gather(g, mine.to(dev), group=group)
-            sizes = [x.cpu() for x in g]
-        else:
-            dist.all_gather(sizes, mine, group=group)
-        nls = [int(s[0]) for s in sizes]
-        nns = [int(s[1]) for s in sizes]
-        box_t = torch.empty((nl + nn) * 6, dtype=torch.float64, device=dev)
-        son_t = torch.empty(nn * 2, dtype=torch.int32, device=dev)
-        leaf_t = torch.empty(nl * 2, dtype=torch.int32, device=dev)
-        tb_t = torch.empty(nl * 6, dtype=torch.float64, device=dev)
-        ctx.tree_export(box_t.data_ptr(), son_t.data_ptr(), leaf_t.data_ptr(), tb_t.data_ptr())
-        boxes = _all_gather_v(box_t, [(a + b) * 6 for a, b in zip(nls, nns)], group)
-        sons = _all_gather_v(son_t, [2 * b for b in nns], group)
-        leaves = _all_gather_v(leaf_t, [2 * a for a in nls], group)
-        box_all, son_all = torch.cat(boxes), torch.cat(sons)
-        tb_all = torch.cat(_all_gather_v(tb_t, [6 * a for a in nls], group))
+    S = _streams_of(ctx)
+    A, B, dev = S.main, (S.comm if overlap else S.main), S.dev
+    t0 = time.perf_counter() if t0 is None else t0
+    period = box if periodic else 0.0
+    tc, tw = 0.5 * (bdr + bdl), bdr - bdl
+    info = ctx.tree_info()
+    nl, nn = info["nleaf"], info["nnode"]
+    ctx.set_rank(me, P)
+    t1 = time.perf_counter()
+    ev = {k: torch.cuda.Event(enable_timing=True) for k in ("c0", "c1", "c2", "c3", "w0", "w1", "x0", "x1")}
+    if P > 1:
+        sizes = _gather_host_ints([nl, nn], group, dev)
+        nls, nns = [int(v) for v in sizes[:, 0]], [int(v) for v in sizes[:, 1]]
+        nlmax, nnmax = max(nls), max(nns)
+        G = sum(nls) - nl
+        ctx.reserve_ghosts(G, max(S.ghost_guess, ctx.npart // 8))
+    built = torch.cuda.Event()
+    built.record(A)
+    # ---- local phase: my tree against itself and its own periodic images (walk, packing, force kernel; in target chunks
+    # when the list would not fit)
+    ctx.set_force_blocks(1 if (P > 1 and overlap) else 0)
+    ctx.forces_local(theta, rcut, period, tc, tw, p2p)
+    ctx.set_force_blocks(0)
+    t2 = time.perf_counter()
+    local_done = torch.cuda.Event()
+    local_done.record(A)
+    nbody = 0
+    topo_bytes = 0
+    remote_walk_ms = 0.0
+    if P > 1:
+        # ---- remote phase on the comm stream, while the local force kernel runs
+        B.wait_event(built)
+        with torch.cuda.stream(B):
+            ctx.set_stream(B.cuda_stream)
+            ctx.swap_lists()
+            ctx.clear_tasks()
+            ev["c0"].record(B)
+            stride = ctx.topology_stride(nlmax, nnmax)
+            mine = torch.empty(stride, dtype=torch.uint8, device=dev)
+            ctx.tree_export_packed(mine.data_ptr(), nlmax, nnmax)
+            topo = _all_gather_blocks(mine, P, group)
+            topo_bytes = int(topo.numel())
+            if midfield:
+                M_mine = torch.zeros((nlmax + nnmax) * 20, dtype=torch.float64, device=dev)
+                ctx.midfield_multipoles(M_mine.data_ptr())
+                M_all = _all_gather_blocks(M_mine, P, group)
+            ev["c1"].record(B)
+            ev["w0"].record(B)
+            ctx.tree_walk_peers_packed(theta, rcut, period, tc, tw, me, nls, nns, topo.data_ptr(), nlmax, nnmax, 0)
+            remote_walk_ms = ctx.tree_info()["ms_walk"]
+            ev["w1"].record(B)
+            ev["c2"].record(B)
+            marks = torch.empty(max(G, 1), dtype=torch.uint8, device=dev)
+            need = ctx.halo_plan_need(topo.data_ptr(), me, nls, nlmax, nnmax, marks.data_ptr())
+            asked = _all_to_all_v(marks[:G], [nls[p] if p != me else 0 for p in range(P)], [nl if q != me else 0 for q in range(P)], group)
+            give = ctx.halo_plan_give(asked.data_ptr(), P - 1)
+            others = [p for p in range(P) if p != me]
+            n_give = int(give.sum())
+            send = torch.empty(max(n_give, 1) * 4, dtype=torch.int32, device=dev)
+            ctx.halo_gather(asked.data_ptr(), P - 1, send.data_ptr())
+            in_split, out_split = [0] * P, [0] * P
+            for i, p in enumerate(others):
+                in_split[p], out_split[p] = 4 * int(give[i]), 4 * int(need[p])
+            ghosts = _all_to_all_v(send[:4 * n_give], in_split, out_split, group)
+            nbody = int(need.sum())
+            ctx.halo_set_particles(ghosts.data_ptr() if nbody else None, nbody)
+            S.ghost_guess = max(S.ghost_guess, int(1.25 * nbody))
+            ev["c3"].record(B)
+            ctx.build_csr()
+            B.wait_event(local_done)        # both force kernels accumulate into the same accelerations
+            if p2p:
+                ctx.compute()
+            if midfield:
+                ctx.midfield_compute_peers_packed(P, topo.data_ptr(), nlmax, nnmax, M_all.data_ptr())
+            remote_done = torch.cuda.Event()
+            remote_done.record(B)
+        A.wait_event(remote_done)
+        ctx.set_stream(A.cuda_stream)
+        nt_r = ctx.counts()[0]
+        ms_force_r, ms_csr_r = ctx.last_timings()
+        ctx.swap_lists()
+    else:
+        nt_r = 0
+        ms_force_r = ms_csr_r = 0.0
         if midfield:
-            M_t = torch.empty((nl + nn) * 20, dtype=torch.float64, device=dev)
-            ctx.midfield_multipoles(M_t.data_ptr())
-            M_all = torch.cat(_all_gather_v(M_t, [(a + b) * 20 for a, b in zip(nls, nns)], group))
-        t2 = time.perf_counter()
-        # ---- lists: my tree against every rank's tree, all displacements
-        ctx.clear_tasks()
-        ctx.tree_walk_peers(theta, rcut, box if periodic else 0.0, 0.5 * (bdr + bdl), bdr - bdl, me, nls, nns, box_all.data_ptr(),
-                            son_all.data_ptr(), tb_all.data_ptr())
-        t3 = time.perf_counter()
-        # ---- which remote leaves do I need; which of mine do the others need
-        others = [p for p in range(P) if p != me]
-        G = sum(nls[p] for p in others)
-        marks = torch.zeros(max(G, 1), dtype=torch.uint8, device=dev)
-        ctx.ghost_marks(marks.data_ptr())
-        marks = marks[:G]
-        cnt_others = torch.cat([leaves[p].view(-1, 2)[:, 1] for p in others]).to(torch.int64) if others else torch.zeros(0, dtype=torch.int64, device=dev)
-        need = marks.to(torch.int64) * cnt_others                           # particles wanted per remote leaf
-        asked = _all_to_all_v(marks, [nls[p] if p != me else 0 for p in range(P)], [nl if q != me else 0 for q in range(P)], group)
-        cnt_me = leaves[me].view(-1, 2)[:, 1].to(torch.int64)
-        give = asked.view(len(others), nl).to(torch.int64) * cnt_me[None, :] if others else torch.zeros((0, nl), dtype=torch.int64, device=dev)
-        flat = give.reshape(-1)
-        off = torch.cumsum(flat, 0) - flat                                  # requester-major offsets into the send buffer
-        bounds = np.concatenate([[0], np.cumsum([nls[p] for p in others])]).astype(np.int64)
-        totals = torch.cat([give.sum(1), torch.stack([need[bounds[i]:bounds[i + 1]].sum() for i in range(len(others))])
-                            if others else torch.zeros(0, dtype=torch.int64, device=dev)]).tolist()
-        n_give, n_need = totals[:len(others)], totals[len(others):]
-        send = torch.empty(max(int(sum(n_give)), 1) * 4, dtype=torch.int32, device=dev)
-        askedv = asked.view(len(others), nl) if others else asked
-        for qi in range(len(others)):
-            ctx.gather_leaves(askedv[qi].data_ptr(), off[qi * nl:(qi + 1) * nl].data_ptr(), send.data_ptr())
-        in_split, out_split = [0] * P, [0] * P
-        for i, p in enumerate(others):
-            in_split[p], out_split[p] = 4 * int(n_give[i]), 4 * int(n_need[i])
-        ghosts = _all_to_all_v(send[:sum(in_split)], in_split, out_split, group)
-        start = (torch.cumsum(need, 0) - need).to(torch.int32)
-        count = need.to(torch.int32)
-        nbody = int(sum(n_need))
-        ctx.set_ghosts_device(ghosts.data_ptr() if nbody else None, nbody, start.data_ptr() if G else None,
-                              count.data_ptr() if G else None, G)
-        t4 = time.perf_counter()
-        # ---- pack, forces
-        ctx.build_csr()
-        if p2p:
-            ctx.compute()
-        ntask, npairs = ctx.counts()
-        if midfield:
-            ctx.midfield_compute_peers(nls, nns, box_all.data_ptr(), M_all.data_ptr())
+            ctx.midfield_compute()
+    ntask, npairs = ctx.accumulated_counts() if p2p else (ctx.counts()[0] + nt_r, 0)
     t5 = time.perf_counter()
     if timings is not None:
-        ms_force, ms_csr = ctx.last_timings()
-        timings.update(build_s=t1 - t0, topology_s=t2 - t1, walk_s=t3 - t2, halo_s=t4 - t3, force_s=t5 - t4,
-                       build_ms=info["ms_build"], walk_ms=ctx.tree_info()["ms_walk"], csr_ms=ms_csr, force_ms=ms_force,
-                       ghost_particles=nbody, ghost_leaves_referenced=int((count > 0).sum().item()) if G else 0,
-                       topology_bytes=int(box_all.numel() * 8 + son_all.numel() * 4))
+        st = ctx.step_timings()
+        comm_ms = (ev["c0"].elapsed_time(ev["c1"]) + ev["c2"].elapsed_time(ev["c3"])) if P > 1 else 0.0
+        timings.update(build_s=t1 - t0, local_phase_s=t2 - t1, remote_phase_s=t5 - t2, build_ms=info["ms_build"], walk_ms=st["walk_ms"] + remote_walk_ms,
+                       csr_ms=st["csr_ms"] + ms_csr_r, force_ms=st["force_ms"] + ms_force_r, force_local_ms=st["force_ms"], force_remote_ms=ms_force_r,
+                       comm_ms=comm_ms, remote_walk_ms=remote_walk_ms, chunks=st["chunks"],
+                       ghost_particles=nbody, remote_tasks=nt_r, topology_bytes=topo_bytes)
     return ntask, npairs

@@ -262,8 +262,8 @@ def run_device_step(ctx, pos, box, maxleaf, nside, mass, theta=0.4, periodic=Tru
     acc = ctx.step_device(pos, maxleaf, [0.0] * 3, [box] * 3, theta, rcut, box if periodic else 0.0, 0, acc_out)
     total = time.perf_counter() - t0
     info = ctx.tree_info()
-    ms_force, ms_csr = ctx.last_timings()
-    ntask, npairs = ctx.counts()
-    t = dict(total_s=total, build_ms=info["ms_build"], walk_ms=info["ms_walk"], csr_ms=ms_csr, force_ms=ms_force,
-             tree_levels=info["nlevel"], walk_items=info["walk_items"], leaves=info["nleaf"])
+    st = ctx.step_timings()                      # summed over the target chunks of the step
+    ntask, npairs = ctx.accumulated_counts()
+    t = dict(total_s=total, build_ms=st["build_ms"], walk_ms=st["walk_ms"], csr_ms=st["csr_ms"], force_ms=st["force_ms"], chunks=st["chunks"],
+             tree_levels=info["nlevel"], leaves=info["nleaf"])
     return acc, t, ntask, npairs

@@ -32,7 +32,8 @@ def test_indexing_abi(demo_pos, truncated):
     T, tt, ts, rs, eps = _demo_lists(demo_pos, 16)
     maxp = int(T.leaf_npart[:T.nleaf].max())
     # pack exactly like task_compute_p2p (1_Indexing/src/fmm.c:851-877)
-    particle_data = np.full((T.nleaf_cap, maxp, 3), np.nan)
+    # padding slots hold stale memory in the reference (never read by its kernel): NaN in one run, huge finite values in the other
+    particle_data = np.full((T.nleaf_cap, maxp, 3), 1e30 if truncated else np.nan)
     leaf_data = np.zeros((T.nleaf_cap, 2), np.int32)
     for l in range(T.nleaf):
         n, ip = T.leaf_npart[l], T.leaf_ipart[l]

@@ -274,3 +274,28 @@ def test_non_periodic_step_and_repeatability(ctx, demo_pos):
     want[O.perm] = ref
     na = np.linalg.norm(want, axis=1)
     assert (np.linalg.norm(a1 - want, axis=1) / np.maximum(na, na.mean())).max() < TOL
+
+
+def test_target_chunks_reproduce_the_unchunked_step(demo_pos):
+    """p2p_forces_local in target chunks (bounded list memory: 1024^3 on one GPU lists 6.7e9 tasks) == one chunk: the same
+    task and pair totals, the same M2L list, and -- every row lives in exactly one chunk -- bit-identical accelerations."""
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    bdl, bdr = np.zeros(3), np.full(3, DEMO_BOX)
+    out = []
+    for chunk_tasks in (1 << 29, 40000):
+        ctx = p2p_b200.P2PContext(0)
+        ctx.set_physics(DEMO_MASS, eps, rs)
+        ctx.set_box([0.0, 0.0, 0.0], DEMO_BOX)
+        ctx.set_chunk_tasks(chunk_tasks)
+        ctx.midfield_enable(True, False)
+        ctx.tree_build(demo_pos[::2].copy(), 4, bdl, bdr, 0)
+        ctx.forces_local(1.0, rcut, DEMO_BOX, 0.5 * (bdl + bdr), bdr - bdl)
+        nm2l = ctx.midfield_compute()
+        st = ctx.step_timings()
+        out.append((ctx.accumulated_counts(), nm2l, ctx.download_acc(), st["chunks"], ctx.download_acc_original()))
+        ctx.close()
+    assert out[0][3] == 1 and out[1][3] > 8
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1] > 0
+    assert np.array_equal(out[0][2], out[1][2])                      # P2P part (FP32, tree order): bit for bit
+    # with the mid-field (fp64 atomics: summation order differs)
+    assert np.abs(out[0][4] - out[1][4]).max() < 1e-10 * np.abs(out[0][4]).max()

@@ -59,10 +59,29 @@ def test_demo_local_list(ctx, demo_pos, golden, maxleaf, truncated, variant):
     acc = _run(ctx, T, tt, ts, DEMO_MASS, eps, rs, variant)
     g = next(c for c in golden["cases"] if c["maxleaf"] == maxleaf and c["nproc"] == 1)["ranks"][0]
     assert ctx.counts() == (g["local_tasks"], g["local_pairs"])                       # bit-exact counts
-    row, col = ctx.download_csr()
+    row, col = ctx.download_csr(raw=True)
     order = np.lexsort((ts, tt))
-    assert np.array_equal(col, ts[order])                                             # CSR == sorted list
     assert np.array_equal(row, np.searchsorted(tt[order], np.arange(T.nleaf + 1)))
+    far, near = ctx.download_csr_class()
+    rid = np.repeat(np.arange(T.nleaf), np.diff(row))
+    # CSR == the list: every row holds exactly its sources, near ones first, each class in ascending order
+    assert np.array_equal(col[np.lexsort((col, rid))], ts[order])
+    assert np.array_equal(np.lexsort((col, far, rid)), np.arange(len(col)))
+    assert np.array_equal(np.bincount(rid[far == 0], minlength=T.nleaf), near)
+    if truncated and variant == p2p_b200.binding.KERNEL_PACKED:
+        # classification: exactly the leaf pairs whose particles are ALL at least 2 r_s u_far apart (tight bounds, fixed point)
+        assert 0.3 < far.mean() < 0.9
+        lo = np.full((T.nleaf, 3), np.inf); hi = np.full((T.nleaf, 3), -np.inf)
+        pid = np.repeat(np.arange(T.nleaf), T.leaf_npart[:T.nleaf])
+        np.minimum.at(lo, pid, T.pos); np.maximum.at(hi, pid, T.pos)
+        gap = np.maximum(0.0, np.maximum(lo[rid] - hi[col], lo[col] - hi[rid]))
+        gap = np.sqrt((gap ** 2).sum(axis=1))
+        ok = np.isfinite(gap)
+        thr = 1.5 * 2.0 * rs
+        q = 4 * DEMO_BOX / 2 ** 32                                                    # rounding of the fixed-point bounds
+        assert (gap[ok & (far == 1)] >= thr - q).all() and (gap[ok & (far == 0)] < thr + q).all()
+    else:
+        assert not far.any()
     ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, DEMO_MASS, eps, rs)
     absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, DEMO_MASS, eps, rs, absterms=True)
     e1, e2 = _errors(acc, ref, absr)
@@ -228,3 +247,47 @@ def test_chunk_pipelined_host_step(demo_pos):
     with pytest.raises(p2p_b200.P2PError):
         ctx.step_host_chunked(T.pos, T.leaf_npart, T.leaf_ipart, tt, bad, off, L.ghost_pos, L.ghost_start, L.ghost_count)
     ctx.close()
+
+
+def test_long_rows_are_sorted_and_classified(ctx):
+    """A dense clump: rows with more sources than the shared-memory row sort holds (2048) go through the global-memory
+    network; the result must still be near-then-far, ascending, bit-reproducible, and equal to the oracle."""
+    rng = np.random.default_rng(5)
+    box = 64.0
+    pos = np.concatenate([rng.uniform(0, box, (4000, 3)), 32.0 + rng.normal(0, 0.4, (20000, 3))]) % box
+    pos = pos.astype(np.float32).astype(np.float64)
+    eps, rs, mass = 0.02, 0.35, 1.0
+    T = oracle.Tree(pos, 8, [0, 0, 0], [box] * 3, 0)
+    tt, ts = T.walk_p2p(THETA, 4.5 * rs)
+    assert np.bincount(tt).max() > 2048
+    acc = _run(ctx, T, tt, ts, mass, eps, rs, p2p_b200.binding.KERNEL_PACKED, box)
+    row, col = ctx.download_csr(raw=True)
+    far, near = ctx.download_csr_class()
+    rid = np.repeat(np.arange(T.nleaf), np.diff(row))
+    assert np.array_equal(np.lexsort((col, far, rid)), np.arange(len(col)))
+    assert far.any() and not far.all()
+    ctx.zero_acc(); ctx.compute()
+    assert np.array_equal(acc, ctx.download_acc())
+    ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs)
+    absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs, absterms=True)
+    assert ctx.counts() == (len(tt), npairs)
+    e1, e2 = _errors(acc, ref, absr)
+    assert e1 < TOL and e2 < TOL, (e1, e2)
+
+
+def test_far_body_equals_near_body(ctx, demo_pos):
+    """The far-field body (2^-w s P(s), no clamp, no rsqrt) against the full body on the same list: switching the far class
+    off must change no particle by more than a fraction of the tolerance."""
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    T = oracle.Tree(demo_pos, 32, [0, 0, 0], [DEMO_BOX] * 3, 0)
+    tt, ts = T.walk_p2p(THETA, rcut)
+    a_far = _run(ctx, T, tt, ts, DEMO_MASS, eps, rs, p2p_b200.binding.KERNEL_PACKED)
+    assert ctx.download_csr_class()[0].mean() > 0.3
+    ctx.set_far_threshold(0.0)
+    try:
+        a_near = _run(ctx, T, tt, ts, DEMO_MASS, eps, rs, p2p_b200.binding.KERNEL_PACKED)
+        assert not ctx.download_csr_class()[0].any()
+    finally:
+        ctx.set_far_threshold(-1.0)
+    n = np.linalg.norm(a_near, axis=1)
+    assert (np.linalg.norm(a_far - a_near, axis=1) / np.maximum(n, n.mean())).max() < 0.3 * TOL
