@@ -271,12 +271,23 @@ int p2p_download_index(p2p_ctx* ctx, int64_t* idx);
  * reference's (1_Indexing/src/photoNs.c:161-208: vel += acc dkh, pos += vel dd, wrap into [0, BOXSIZE) by its while
  * loops); like the reference (fmm_construct after the drift) every step's tree is built from the particle order the
  * previous step left.  The PM term (acc_pm) and the scale-factor integrals dk, dd belong to the caller. */
-int p2p_resident_load(p2p_ctx* ctx, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n);
+int p2p_resident_load(p2p_ctx* ctx, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n, int64_t first_id);
 int p2p_resident_forces(p2p_ctx* ctx, int maxleaf, const double bdl[3], const double bdr[3], int direct_start, double theta, double rcut,
                         double period);
+/* the build alone (velocities and ids carried along): a multi-rank step continues with the exchange instead of the local forces */
+int p2p_resident_build(p2p_ctx* ctx, int maxleaf, const double bdl[3], const double bdr[3], int direct_start);
+/* vel += (P2P + mid-field) dkh.  With the M2L lists enabled (p2p_midfield_enable) p2p_resident_forces also computes the
+ * mid-field, and the kick fails with P2P_ERR_STATE if it is missing (a multi-rank step computes it with
+ * p2p_midfield_compute_peers_packed): the pairs the walk hands to the expansions must not be dropped silently. */
 int p2p_resident_kick(p2p_ctx* ctx, double dkh);
+/* multi-rank resident stepping: after the drift the particles migrate to their owners WITH velocities and ids
+ * (domain_decomposition every step, 1_Indexing/src/domains.c:298-377): partition by the rank kd-tree (sendcount[r] = group
+ * for rank r), export / import of the state as DEVICE arrays of the caller: 6 doubles arrays x, y, z, vx, vy, vz and int32 ids */
+int p2p_resident_partition(p2p_ctx* ctx, int nproc, const double* split, int* sendcount);
+int p2p_resident_export(p2p_ctx* ctx, void* const d_xv[6], void* d_id);
+int p2p_resident_import(p2p_ctx* ctx, const void* const d_xv[6], const void* d_id, int64_t n);
 int p2p_resident_drift(p2p_ctx* ctx, double dd, double period);
-/* current positions / velocities (packed rows of 3 doubles) and ids (particle i of p2p_resident_load has id i), in the
+/* current positions / velocities (packed rows of 3 doubles) and ids (particle i of p2p_resident_load has id first_id + i), in the
  * resident (tree) order; NULL skips */
 int p2p_resident_download(p2p_ctx* ctx, double* pos, double* vel, int64_t* id);
 /* particles currently resident on this device (after p2p_route_load / _import / p2p_resident_load) */

@@ -209,6 +209,17 @@ int reserve_build(p2p_ctx* c, p2p_dtree* t, long long npart, size_t ncap, p2p::d
 }
 
 int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const double bdl[3], const double bdr[3], int direct_start);
+
+// velocities and ids of the resident particles follow the permutation perm[] (tree build or routing partition) applied to the positions
+int resident_carry(p2p_ctx* c, p2p_dtree* t) {
+    const long long n = t->resident;
+    p2p::dt::carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(t->perm.p, n, t->v[0].p, t->v[1].p, t->v[2].p, t->gid.p, t->vtmp[0].p,
+                                                                              t->vtmp[1].p, t->vtmp[2].p, t->gidtmp.p);
+    CU(cudaGetLastError());
+    for (int k = 0; k < 3; k++) { std::swap(t->v[k].p, t->vtmp[k].p); std::swap(t->v[k].cap, t->vtmp[k].cap); }
+    std::swap(t->gid.p, t->gidtmp.p); std::swap(t->gid.cap, t->gidtmp.cap);
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -488,10 +499,10 @@ int p2p_tree_build_resident(p2p_ctx* c, int maxleaf, const double bdl[3], const 
 }
 
 // ---- device-resident stepping: positions, velocities and ids live in HBM between steps ---------------
-// pos / vel: host rows of 3 doubles (vel may be NULL = at rest); particle i gets id i
-int p2p_resident_load(p2p_ctx* c, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n) {
+// pos / vel: host rows of 3 doubles (vel may be NULL = at rest); particle i gets id first_id + i
+int p2p_resident_load(p2p_ctx* c, const double* pos, int64_t pos_stride, const double* vel, int64_t vel_stride, int64_t n, int64_t first_id) {
     USE(c);
-    if (n < 1 || n > 0x7fffffffLL || !pos || pos_stride < 3 || (vel && vel_stride < 3)) return fail(P2P_ERR_ARG, "bad arrays");
+    if (n < 1 || first_id < 0 || first_id + n > 0x7fffffffLL || !pos || pos_stride < 3 || (vel && vel_stride < 3)) return fail(P2P_ERR_ARG, "bad arrays");
     p2p_dtree* t;
     int r = get_tree(c, &t);
     if (r) return r;
@@ -510,16 +521,15 @@ int p2p_resident_load(p2p_ctx* c, const double* pos, int64_t pos_stride, const d
     CU(cudaMemcpy2DAsync(c->stage.p, 24, pos, (size_t)pos_stride * 8, 24, (size_t)n, cudaMemcpyHostToDevice, st));
     p2p::dt::soa_from_aos_kernel<<<blocks(n, 256), 256, 0, st>>>(reinterpret_cast<const double*>(c->stage.p), n, t->x[0].p, t->x[1].p, t->x[2].p,
                                                                  t->perm.p, t->seg.p);
-    p2p::dt::iota_kernel<<<blocks(n, 256), 256, 0, st>>>(t->gid.p, n);
+    p2p::dt::iota_offset_kernel<<<blocks(n, 256), 256, 0, st>>>(t->gid.p, n, (int)first_id);
     CU(cudaGetLastError());
     t->resident = n; t->perm_is_local = false; t->stepping = true;
     return 0;
 }
 
-// short-range forces of the resident particles: tree build from their current order (the reference too rebuilds from the
-// order the previous step left, fmm_construct after the drift), velocities and ids carried along, walk, packing, forces
-int p2p_resident_forces(p2p_ctx* c, int maxleaf, const double bdl[3], const double bdr[3], int direct_start, double theta, double rcut,
-                        double period) {
+// tree of the resident particles, built from their current order (the reference too rebuilds from the order the previous
+// step left, fmm_construct after the drift); velocities and ids follow the build's permutation
+int p2p_resident_build(p2p_ctx* c, int maxleaf, const double bdl[3], const double bdr[3], int direct_start) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->stepping || t->resident < 1) return fail(P2P_ERR_STATE, "p2p_resident_load first");
@@ -532,23 +542,81 @@ int p2p_resident_forces(p2p_ctx* c, int maxleaf, const double bdl[3], const doub
     p2p::dt::iota_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n);
     int r = build_core(c, t, n, maxleaf, bdl, bdr, direct_start);
     if (r) return r;
-    p2p::dt::carry_kernel<<<blocks(n, 256), 256, 0, st>>>(t->perm.p, n, t->v[0].p, t->v[1].p, t->v[2].p, t->gid.p, t->vtmp[0].p, t->vtmp[1].p,
-                                                          t->vtmp[2].p, t->gidtmp.p);
-    CU(cudaGetLastError());
-    for (int k = 0; k < 3; k++) { std::swap(t->v[k].p, t->vtmp[k].p); std::swap(t->v[k].cap, t->vtmp[k].cap); }
-    std::swap(t->gid.p, t->gidtmp.p); std::swap(t->gid.cap, t->gidtmp.cap);
-    double tc[3], tw[3];
-    for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }
-    return p2p_forces_local(c, theta, rcut, period, tc, tw, 1);
+    return resident_carry(c, t);
 }
 
-// vel += acc * dkh for the resident particles (acc of the last p2p_resident_forces)
+// short-range forces of the resident particles of ONE rank: build, walk, packing, forces and -- when the M2L lists are
+// enabled (p2p_midfield_enable) -- the mid-field, which the kick then includes
+int p2p_resident_forces(p2p_ctx* c, int maxleaf, const double bdl[3], const double bdr[3], int direct_start, double theta, double rcut,
+                        double period) {
+    int r = p2p_resident_build(c, maxleaf, bdl, bdr, direct_start);
+    if (r) return r;
+    p2p_dtree* t = c->dtree;
+    double tc[3], tw[3];
+    for (int k = 0; k < 3; k++) { tc[k] = 0.5 * (bdr[k] + bdl[k]); tw[k] = bdr[k] - bdl[k]; }
+    if ((r = p2p_forces_local(c, theta, rcut, period, tc, tw, 1))) return r;
+    if (t->m2l_on) return p2p_midfield_compute(c, nullptr);
+    return 0;
+}
+
+// vel += (P2P + mid-field) * dkh for the resident particles (forces of the last step).  With the M2L lists enabled the
+// mid-field must have been computed (p2p_resident_forces does; a multi-rank step calls p2p_midfield_compute_peers_packed):
+// kicking with the P2P part alone would silently drop the pairs the walk handed to the expansions.
 int p2p_resident_kick(p2p_ctx* c, double dkh) {
     USE(c);
     p2p_dtree* t = c->dtree;
     if (!t || !t->stepping || !t->valid) return fail(P2P_ERR_STATE, "no forces computed for the resident particles");
-    p2p::dt::kick_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(c->acc.p, t->resident, dkh, t->v[0].p, t->v[1].p, t->v[2].p);
+    if (t->m2l_on && !t->mid_valid) return fail(P2P_ERR_STATE, "the M2L lists are enabled but the mid-field of this step was not computed");
+    if (t->mid_valid)
+        p2p::dt::kick_mid_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(c->acc.p, t->acc_mid.p, t->resident, dkh, t->v[0].p, t->v[1].p, t->v[2].p);
+    else
+        p2p::dt::kick_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(c->acc.p, t->resident, dkh, t->v[0].p, t->v[1].p, t->v[2].p);
     CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- multi-rank resident stepping: after the drift the particles migrate to the ranks that own them, WITH their
+// velocities and ids (domain_decomposition every step, 1_Indexing/src/domains.c:298-377) ---------------------------------
+// partition of the resident particles by the rank kd-tree; velocities and ids follow
+int p2p_resident_partition(p2p_ctx* c, int nproc, const double* split, int* sendcount) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping || t->resident < 1) return fail(P2P_ERR_STATE, "p2p_resident_load first");
+    p2p::dt::iota_kernel<<<blocks(t->resident, 256), 256, 0, c->stream>>>(t->perm.p, t->resident);
+    int r = p2p_route_partition(c, nproc, split, sendcount);
+    if (r) return r;
+    return resident_carry(c, t);
+}
+// copies of / into the resident state; DEVICE pointers of the caller: 6 double arrays (x, y, z, vx, vy, vz), ids int32
+int p2p_resident_export(p2p_ctx* c, void* const d_xv[6], void* d_id) {
+    USE(c);
+    p2p_dtree* t = c->dtree;
+    if (!t || !t->stepping) return fail(P2P_ERR_STATE, "p2p_resident_load first");
+    const size_t n = (size_t)t->resident;
+    if (n == 0) return 0;
+    for (int k = 0; k < 3; k++) {
+        CU(cudaMemcpyAsync(d_xv[k], t->x[k].p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_xv[3 + k], t->v[k].p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(d_id, t->gid.p, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int p2p_resident_import(p2p_ctx* c, const void* const d_xv[6], const void* d_id, int64_t n) {
+    USE(c);
+    if (n < 1 || n > 0x7fffffffLL || !d_xv || !d_id) return fail(P2P_ERR_ARG, "bad arrays");
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    cudaStream_t st = c->stream;
+    t->valid = false; t->resident = 0;
+    for (int k = 0; k < 3; k++) {
+        CU(t->x[k].reserve((size_t)n, st)); CU(t->v[k].reserve((size_t)n, st)); CU(t->vtmp[k].reserve((size_t)n, st));
+        CU(cudaMemcpyAsync(t->x[k].p, d_xv[k], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(t->v[k].p, d_xv[3 + k], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(t->perm.reserve((size_t)n, st)); CU(t->seg.reserve((size_t)n, st)); CU(t->gid.reserve((size_t)n, st)); CU(t->gidtmp.reserve((size_t)n, st));
+    CU(cudaMemcpyAsync(t->gid.p, d_id, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    t->resident = n; t->perm_is_local = false; t->stepping = true;
     return 0;
 }
 

@@ -770,6 +770,15 @@ __global__ void kick_kernel(const float4* __restrict__ acc, long long n, double 
     const float4 a = acc[i];
     vx[i] += (double)a.x * dkh; vy[i] += (double)a.y * dkh; vz[i] += (double)a.z * dkh;
 }
+// the same with the mid-field part of the short-range force (fp64, tree order) added: the reference kicks with the sum
+// of P2P and M2L / L2L / L2P (1_Indexing/src/photoNs.c:161-180 after fmm_task / fmm_ext)
+__global__ void kick_mid_kernel(const float4* __restrict__ acc, const double* __restrict__ mid, long long n, double dkh,
+                                double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = acc[i];
+    vx[i] += ((double)a.x + mid[3 * i]) * dkh; vy[i] += ((double)a.y + mid[3 * i + 1]) * dkh; vz[i] += ((double)a.z + mid[3 * i + 2]) * dkh;
+}
 // pos += vel * dd, then wrapped into [0, box) exactly as the reference's while loops do (photoNs.c:182-208)
 __global__ void drift_kernel(long long n, double dd, double box, const double* __restrict__ vx, const double* __restrict__ vy,
                              const double* __restrict__ vz, double* __restrict__ x, double* __restrict__ y, double* __restrict__ z) {
@@ -1034,7 +1043,7 @@ __host__ __device__ __forceinline__ ull item(int im, int jm, int peer, int sh) {
 // walk_task_p2p_ext on the image prepare_sendtree2 would have sent, whose cut nodes are recognised on the fly.
 // Output slots are claimed per warp.  counters[0] = items written to `out`, counters[1] = tasks emitted so far;
 // writes beyond the capacities are dropped (the host sees the counts, grows the buffers and repeats the level).
-__global__ void __launch_bounds__(256) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
+__global__ void __launch_bounds__(256, 4) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
                                                          ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
                                                          ull cap_task, WalkParams P) {
     __shared__ int s_cnt[3][8];

@@ -142,9 +142,9 @@ int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P) {
 }
 
 // Second-generation kernel (p2p_rows2_kernel): one pass per row, near and far slice bodies.
-template <int NSRC, bool TRUNC, int MINB>
+template <int NSRC, bool TRUNC, int MINB, int DBG = 0>
 int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
-    auto kern = p2p::p2p_rows2_kernel<NSRC, kStage, TRUNC, MINB>;
+    auto kern = p2p::p2p_rows2_kernel<NSRC, kStage, TRUNC, MINB, DBG>;
     const int smem = 4 * (int)sizeof(p2p::WarpSmem2<kStage>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
@@ -161,6 +161,7 @@ int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
 template <bool TRUNC>
 int launch_cfg2(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb) {
     if constexpr (TRUNC) {
+        if (nsrc == 9) return launch_rows2<1, true, 2, 1>(c, P);          // error-budget variant: fp64 force factor (pair_exact2)
         if (nsrc == 2) return launch_rows2<2, true, 3>(c, P);
         return minb == 4 ? launch_rows2<1, true, 4>(c, P) : launch_rows2<1, true, 3>(c, P);
     } else {
@@ -291,7 +292,7 @@ int p2p_set_box(p2p_ctx* c, const double origin[3], double extent) {
 
 int p2p_set_tuning(p2p_ctx* c, int tt, int nsrc, int minb) {
     // tt 0 / 32: second-generation kernel (nsrc 1 / 2, min_blocks 3 / 4); tt 8 / 16: first-generation kernel in its final tuning
-    if (!c || (tt && tt != 8 && tt != 16 && tt != 32) || (nsrc != 0 && nsrc != 1 && nsrc != 2) || (minb != 0 && minb != 3 && minb != 4))
+    if (!c || (tt && tt != 8 && tt != 16 && tt != 32) || (nsrc != 0 && nsrc != 1 && nsrc != 2 && nsrc != 9) || (minb != 0 && minb != 3 && minb != 4))
         return fail(P2P_ERR_ARG, "bad tuning (targets_per_pass 0/32 or 8/16, sources_per_lane 1/2, min_blocks 3/4)");
     c->tune_tt = tt; c->tune_nsrc = nsrc; c->tune_minb = minb;
     return 0;

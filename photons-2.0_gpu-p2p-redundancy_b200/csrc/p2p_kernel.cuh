@@ -527,6 +527,26 @@ __device__ __forceinline__ void pair_far2(const KernelParams& P, float2 sx, floa
     az = __ffma2_rn(dz, f, az);
 }
 
+// error-budget variant (development aid, tests/tools/error_distribution.py): the same FP32 separations, the force factor
+// in fp64 with libm's erfc / exp -- what remains of the error is coordinate rounding and FP32 accumulation
+__device__ __forceinline__ void pair_exact2(const KernelParams& P, float2 sx, float2 sy, float2 sz, float2 tx, float2 ty, float2 tz,
+                                            float2& ax, float2& ay, float2& az) {
+    const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
+    float f[2];
+    const float ddx[2] = {dx.x, dx.y}, ddy[2] = {dy.x, dy.y}, ddz[2] = {dz.x, dz.y};
+    for (int k = 0; k < 2; k++) {
+        const double q2 = (double)ddx[k] * ddx[k] + (double)ddy[k] * ddy[k] + (double)ddz[k] * ddz[k];
+        const double r = sqrt(q2), rc = fmax(r, sqrt((double)P.eps2));
+        const double u = r * 0.8325546111576977;                // kernel length unit -> u = r / 2 r_s: 1 / sqrt(log2 e)
+        const double g = erfc(u) + 1.1283791670955126 * u * exp(-u * u);
+        f[k] = (float)(q2 < 1.0e5 ? g / (rc * rc * rc) : 0.0);
+    }
+    const float2 ff = make_float2(f[0], f[1]);
+    ax = __ffma2_rn(dx, ff, ax);
+    ay = __ffma2_rn(dy, ff, ay);
+    az = __ffma2_rn(dz, ff, az);
+}
+
 constexpr int kRowTargets = 32;         // = P2P_MAX_LEAF
 
 template <int STAGE>
@@ -552,7 +572,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 }
 
 // All chunks and slices of the columns [e, e_end) of one row against the first 2 K targets, with the NEAR or the FAR body.
-template <int K, bool FAR, int NSRC, int STAGE, bool TRUNC>
+template <int K, bool FAR, int NSRC, int STAGE, bool TRUNC, int DBG>
 __device__ __forceinline__ void run_range2(const KernelParams& P, WarpSmem2<STAGE>& S, const int4 c4, long long e, const long long e_end,
                                            const int lane, uint32_t& phase0, uint32_t& phase1, float2 (&ax)[kRowTargets / 2],
                                            float2 (&ay)[kRowTargets / 2], float2 (&az)[kRowTargets / 2]) {
@@ -574,7 +594,10 @@ __device__ __forceinline__ void run_range2(const KernelParams& P, WarpSmem2<STAG
             const float2 tz = S.tgt[p].z;
 #pragma unroll
             for (int q = 0; q < NSRC; q++) {
-                if (FAR)
+                if (DBG)
+                    pair_exact2(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]), make_float2(txy.x, txy.y),
+                                make_float2(txy.z, txy.w), tz, ax[p], ay[p], az[p]);
+                else if (FAR)
                     pair_far2(P, make_float2(sx[q], sx[q]), make_float2(sy[q], sy[q]), make_float2(sz[q], sz[q]), make_float2(txy.x, txy.y),
                               make_float2(txy.z, txy.w), tz, ax[p], ay[p], az[p]);
                 else
@@ -640,7 +663,7 @@ __device__ __forceinline__ void run_range2(const KernelParams& P, WarpSmem2<STAG
     }
 }
 
-template <int NSRC, int STAGE, bool TRUNC, int MINB>
+template <int NSRC, int STAGE, bool TRUNC, int MINB, int DBG = 0>
 __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -691,8 +714,8 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
         switch ((nt + 1) >> 1) {                              // target pairs of this row (warp-uniform)
 #define P2P_CASE(k)                                                                                                             \
     case k:                                                                                                                     \
-        if (e_mid > e_begin) run_range2<k, false, NSRC, STAGE, TRUNC>(P, S, c4, e_begin, e_mid, lane, phase0, phase1, ax, ay, az); \
-        if (TRUNC && e_end > e_mid) run_range2<k, true, NSRC, STAGE, TRUNC>(P, S, c4, e_mid, e_end, lane, phase0, phase1, ax, ay, az); \
+        if (e_mid > e_begin) run_range2<k, false, NSRC, STAGE, TRUNC, DBG>(P, S, c4, e_begin, e_mid, lane, phase0, phase1, ax, ay, az); \
+        if (TRUNC && e_end > e_mid) run_range2<k, true, NSRC, STAGE, TRUNC, DBG>(P, S, c4, e_mid, e_end, lane, phase0, phase1, ax, ay, az); \
         break;
             P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
             P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)

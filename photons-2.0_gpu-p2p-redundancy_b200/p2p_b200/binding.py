@@ -84,7 +84,11 @@ def load_library():
     L.p2p_route_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.p2p_tree_build_resident.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
     L.p2p_download_index.argtypes = [C.c_void_p, _lp]
-    L.p2p_resident_load.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, C.c_int64]
+    L.p2p_resident_load.argtypes = [C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int64]
+    L.p2p_resident_build.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+    L.p2p_resident_partition.argtypes = [C.c_void_p, C.c_int, _dp, _ip]
+    L.p2p_resident_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.p2p_resident_import.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]
     L.p2p_resident_forces.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double]
     L.p2p_resident_kick.argtypes = [C.c_void_p, C.c_double]
     L.p2p_resident_drift.argtypes = [C.c_void_p, C.c_double, C.c_double]
@@ -412,7 +416,7 @@ class P2PContext:
         self._chk(self._L.p2p_tree_build_resident(self._h, int(maxleaf), bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start)))
         info = self.tree_info()
         self.nleaf = info["nleaf"]
-        self.npart = self._resident
+        self.npart = self.resident_count()
 
     def download_index(self, out=None):
         idx = np.zeros(self.npart, np.int64) if out is None else out
@@ -421,12 +425,33 @@ class P2PContext:
         return idx
 
     # ---- device-resident stepping
-    def resident_load(self, pos, vel=None):
+    def resident_load(self, pos, vel=None, first_id=0):
         pos = _f64(pos)
         v = _f64(vel) if vel is not None else None
         self._chk(self._L.p2p_resident_load(self._h, pos.ctypes.data_as(_dp), pos.shape[1], v.ctypes.data_as(_dp) if v is not None else None,
-                                            v.shape[1] if v is not None else 3, pos.shape[0]))
+                                            v.shape[1] if v is not None else 3, pos.shape[0], int(first_id)))
         self.npart = pos.shape[0]
+
+    def resident_build(self, maxleaf, bdl, bdr, direct_start=0):
+        bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)
+        self._chk(self._L.p2p_resident_build(self._h, int(maxleaf), bl.ctypes.data_as(_dp), br.ctypes.data_as(_dp), int(direct_start)))
+        self.nleaf = self.tree_info()["nleaf"]
+        self.npart = self.resident_count()
+
+    def resident_partition(self, nproc, split):
+        split = _f64(split)
+        send = np.zeros(nproc, np.int32)
+        self._chk(self._L.p2p_resident_partition(self._h, int(nproc), split.ctypes.data_as(_dp), send.ctypes.data_as(_ip)))
+        return send
+
+    def resident_export(self, d_xv, d_id):
+        arr = (C.c_void_p * 6)(*[C.c_void_p(int(p)) for p in d_xv])
+        self._chk(self._L.p2p_resident_export(self._h, arr, C.c_void_p(int(d_id))))
+
+    def resident_import(self, d_xv, d_id, n):
+        arr = (C.c_void_p * 6)(*[C.c_void_p(int(p)) for p in d_xv])
+        self._chk(self._L.p2p_resident_import(self._h, arr, C.c_void_p(int(d_id)), int(n)))
+        self.npart = int(n)
 
     def resident_forces(self, maxleaf, bdl, bdr, theta, rcut, period, direct_start=0):
         bl, br = np.ascontiguousarray(bdl, np.float64), np.ascontiguousarray(bdr, np.float64)

@@ -281,3 +281,68 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
                        comm_ms=comm_ms, remote_walk_ms=remote_walk_ms, chunks=st["chunks"],
                        ghost_particles=nbody, remote_tasks=nt_r, topology_bytes=topo_bytes)
     return ntask, npairs
+
+
+class ResidentRun:
+    """Multi-rank device-resident stepping (SURVEY 8f N4 + row a12): positions, velocities and ids stay in HBM on every
+    rank across steps.  Each step: the particles migrate to the ranks that own them after the last drift (device partition
+    by the rank kd-tree, all-to-all-v of the seven state arrays as device buffers -- domain_decomposition,
+    1_Indexing/src/domains.c:298-377), the tree is built from the arrived order, forces as in lists_halo_forces, then kick
+    and drift with the reference's arithmetic (1_Indexing/src/photoNs.c:161-208).  Nothing crosses PCIe per step."""
+
+    def __init__(self, ctx, npart_total, box, maxleaf, nside, mass, theta=0.4, truncated=True, midfield=False, group=None):
+        self.ctx, self.group = ctx, group
+        self.P, self.me = dist.get_world_size(group), dist.get_rank(group)
+        self.box, self.maxleaf, self.theta, self.midfield = box, maxleaf, theta, midfield
+        self.rs, self.rcut, self.eps = host.derived_params(box, nside, npart_total)
+        ctx.set_physics(mass, self.eps, self.rs if truncated else 0.0)
+        ctx.set_box([0.0, 0.0, 0.0], box)
+        self.split = host.domain_setup(self.P, box)[0]
+        self.S = _streams_of(ctx)
+
+    def load(self, slab_pos, slab_vel, first_index):
+        """the slab of the global arrays this rank starts from (global ids first_index ...)"""
+        with torch.cuda.stream(self.S.main):
+            self.ctx.resident_load(slab_pos, slab_vel, first_index)
+
+    def _migrate(self):
+        ctx, P, dev = self.ctx, self.P, self.S.dev
+        n = ctx.resident_count()
+        send = ctx.resident_partition(P, self.split)
+        if P == 1:
+            return n
+        bufs = [torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(6)]
+        ids = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ctx.resident_export([b.data_ptr() for b in bufs], ids.data_ptr())
+        recv = _gather_host_ints(send, self.group, dev)[:, self.me]
+        s, r = [int(v) for v in send], [int(v) for v in recv]
+        got = [_all_to_all_v(b[:n], s, r, self.group) for b in bufs]
+        gid = _all_to_all_v(ids[:n], s, r, self.group)
+        nloc = int(recv.sum())
+        ctx.resident_import([g.data_ptr() for g in got], gid.data_ptr(), nloc)
+        return nloc
+
+    def step(self, dkh, dd, timings=None, overlap=True):
+        """migrate -> build -> forces -> kick (vel += acc dkh) -> drift (pos += vel dd, wrapped).  Returns (ntask, npairs)."""
+        ctx = self.ctx
+        with torch.cuda.stream(self.S.main):
+            self._migrate()
+            center, width, direct = host.domain_boxes(self.P, self.box, self.split)
+            dom = host.domain_of_rank(self.P, self.me)
+            bdl, bdr = center[dom] - 0.5 * width[dom], center[dom] + 0.5 * width[dom]
+            ctx.midfield_enable(self.midfield, False)
+            ctx.resident_build(self.maxleaf, bdl, bdr, int(direct[dom]))
+            out = lists_halo_forces(ctx, self.rcut, self.box, bdl, bdr, self.theta, True, self.group, timings, self.midfield, True, overlap)
+            ctx.resident_kick(dkh)
+            ctx.resident_drift(dd, self.box)
+        return out
+
+    def relax(self, work):
+        """the reference's work-weighted split relaxation (1_Indexing/src/photoNs.c:295-306); takes effect at the next migration"""
+        w_all = _gather_host_ints([int(work)], self.group, self.S.dev)[:, 0].astype(np.float64)
+        self.split = host.domain_relax(self.P, self.box, self.split, w_all)
+
+    def download(self):
+        """(positions, velocities, ids) of this rank's particles, in the resident order"""
+        with torch.cuda.stream(self.S.main):
+            return self.ctx.resident_download()

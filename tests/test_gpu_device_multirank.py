@@ -198,3 +198,85 @@ def test_device_multirank_midfield_matches_the_reference(demo_pos):
         want[ref[r]["part_orig_index"]] = ref[r]["acc_mid"].reshape(-1, 3)
     assert np.abs(want).max() > 0
     assert np.linalg.norm(acc - want, axis=1).max() < 1e-10 * np.linalg.norm(want, axis=1).mean()
+
+
+def _resident_worker(rank, world, port, pos, vel0, q):
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "photons-2.0_gpu-p2p-redundancy_b200")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import p2p_b200
+    from p2p_b200 import dist as pdist
+    from p2p_b200 import dist_device, host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    n, maxleaf, nstep = pos.shape[0], 16, 3
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    cell = DEMO_BOX / DEMO_NSIDE
+    dkh, dd = 7.5e4 * cell, 0.4               # mean |a| of the demo is 6.7e-6: a kick adds ~0.5 cell per unit time
+    split = host.domain_setup(world, DEMO_BOX)[0]
+    center, width, direct = host.domain_boxes(world, DEMO_BOX, split)
+    dom = host.domain_of_rank(world, rank)
+    bdl, bdr = center[dom] - 0.5 * width[dom], center[dom] + 0.5 * width[dom]
+    # ---- resident path: nothing returns to the host between the steps
+    a = p2p_b200.P2PContext(0)
+    R = dist_device.ResidentRun(a, n, DEMO_BOX, maxleaf, DEMO_NSIDE, DEMO_MASS, THETA)
+    R.load(pos[lo:hi].copy(), vel0[lo:hi].copy(), lo)
+    counts = [R.step(dkh, dd) for _ in range(nstep)]
+    pa, va, ia = R.download()
+    # ---- host mirror around the one-step device path: host routing (pinned bit-exactly to the reference's
+    # domain_decomposition), exchange over gloo, forces, numpy kick / drift / wrap, arrays carried in tree order
+    b = p2p_b200.P2PContext(0)
+    p, v, ids = pos[lo:hi].copy(), vel0[lo:hi].copy(), np.arange(lo, hi, dtype=np.int64)
+    mirror_counts = []
+    for _ in range(nstep):
+        lidx = np.arange(len(p), dtype=np.int64)
+        send = host.domain_route(world, split, p, lidx)
+        v, ids = v[lidx], ids[lidx]
+        off = np.concatenate([[0], np.cumsum(send)])
+        rc = pdist._a2a_counts(send.reshape(world, 1), None)[:, 0]
+        p = np.concatenate(pdist._a2a_v([p[off[d]:off[d + 1]] for d in range(world)], rc, 3, np.float64, None))
+        v = np.concatenate(pdist._a2a_v([v[off[d]:off[d + 1]] for d in range(world)], rc, 3, np.float64, None))
+        ids = np.concatenate(pdist._a2a_v([ids[off[d]:off[d + 1]].reshape(-1, 1) for d in range(world)], rc, 1, np.int64, None))[:, 0]
+        acc, nt, npr = dist_device.run_device_step(b, p, n, DEMO_BOX, maxleaf, DEMO_NSIDE, DEMO_MASS, bdl, bdr, int(direct[dom]), THETA)
+        mirror_counts.append((nt, npr))
+        D = b.tree_download()
+        perm = D["perm"]
+        p, v, ids = D["pos"], v[perm] + acc[perm] * dkh, ids[perm]
+        p = p + v * dd
+        for k in range(3):
+            col = p[:, k]
+            while (col < 0.0).any():
+                col[col < 0.0] += DEMO_BOX
+            while (col >= DEMO_BOX).any():
+                col[col >= DEMO_BOX] -= DEMO_BOX
+    moved = float(np.abs(pa - pos[ia]).max())
+    q.put((rank, bool(np.array_equal(ia, ids)), bool(np.array_equal(va, v)), bool(np.array_equal(pa, p)), counts == mirror_counts, ia, moved))
+    dist.barrier()
+    a.close()
+    b.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multirank_resident_steps_equal_host_mirror(demo_pos, world):
+    """positions, velocities and ids resident across three steps on every rank, migration as device buffers: bit for bit
+    the host mirror (host routing + one-step device path + numpy integrator), every particle owned exactly once"""
+    rng = np.random.default_rng(6)
+    vel0 = rng.normal(0.0, 0.2 * DEMO_BOX / DEMO_NSIDE, demo_pos.shape)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_resident_worker, args=(r, world, port, demo_pos, vel0, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=900) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same_ids, same_vel, same_pos, same_counts, ia, moved in got:
+        assert same_ids and same_vel and same_pos and same_counts, (rank, same_ids, same_vel, same_pos, same_counts)
+        assert moved > 0.05 * DEMO_BOX / DEMO_NSIDE
+    assert sorted(np.concatenate([g[5] for g in got]).tolist()) == list(range(len(demo_pos)))

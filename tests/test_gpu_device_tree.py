@@ -215,7 +215,7 @@ def test_device_path_equals_host_path_at_scale(ctx):
     acc = ctx.download_acc_original()
     d = np.linalg.norm(acc - acc_host, axis=1)
     na = np.linalg.norm(acc_host, axis=1)
-    assert (d / np.maximum(na, na.mean())).max() < 2e-6      # same arithmetic, different summation order only
+    assert (d / np.maximum(na, na.mean())).max() < 4e-6      # same arithmetic; summation order and near / far class of image sources differ
     info = ctx.tree_info()
     print("128^3 device tree: build %.2f ms, walk %.2f ms, %d levels, %d walk items" %
           (info["ms_build"], info["ms_walk"], info["nlevel"], info["walk_items"]))

@@ -77,7 +77,7 @@ def test_demo_local_list(ctx, demo_pos, golden, maxleaf, truncated, variant):
         gap = np.maximum(0.0, np.maximum(lo[rid] - hi[col], lo[col] - hi[rid]))
         gap = np.sqrt((gap ** 2).sum(axis=1))
         ok = np.isfinite(gap)
-        thr = 1.5 * 2.0 * rs
+        thr = 1.25 * 2.0 * rs                                                         # P2P_U_FAR
         q = 4 * DEMO_BOX / 2 ** 32                                                    # rounding of the fixed-point bounds
         assert (gap[ok & (far == 1)] >= thr - q).all() and (gap[ok & (far == 0)] < thr + q).all()
     else:
@@ -271,8 +271,13 @@ def test_long_rows_are_sorted_and_classified(ctx):
     ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs)
     absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs, absterms=True)
     assert ctx.counts() == (len(tt), npairs)
-    e1, e2 = _errors(acc, ref, absr)
-    assert e1 < TOL and e2 < TOL, (e1, e2)
+    # (r_s is tiny here: most background particles only have sources at u > 4, whose forces are ~1e-12 of the clump's;
+    # the relative check is for the particles that kept a substantial near field, as in test_edge_cases)
+    d, na = np.linalg.norm(acc - ref, axis=1), np.linalg.norm(absr, axis=1)
+    nr = np.linalg.norm(ref, axis=1)
+    assert (d / np.maximum(nr, nr.mean())).max() < TOL
+    sel = na > 0.1 * np.median(na[na > 0])
+    assert (d[sel] / na[sel]).max() < TOL
 
 
 def test_far_body_equals_near_body(ctx, demo_pos):

@@ -22,7 +22,7 @@ ctx = p2p_b200.P2PContext(0)
 VARIANTS = {"production": (0, 0, 0, -1.0)}
 if "--variants" in sys.argv:
     VARIANTS.update({"first_generation_kernel": (16, 0, 0, -1.0), "no_far_class": (32, 1, 3, 0.0), "two_sources_per_lane": (32, 2, 3, -1.0),
-                     "far_class_from_u_2": (32, 1, 3, 2.0)})
+                     "far_class_from_u_2": (32, 1, 3, 2.0), "fp64_force_factor_same_fp32_separations": (32, 9, 0, -1.0)})
 for maxleaf in (16, 32):
     ref, rt, rp = flow.reference_forces(pos, BOX, maxleaf, NSIDE, THETA, MASS, 1, True)
     absr, _, _ = flow.reference_forces(pos, BOX, maxleaf, NSIDE, THETA, MASS, 1, True, absterms=True)

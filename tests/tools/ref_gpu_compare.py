@@ -24,7 +24,7 @@ out = {"input": "demo IC 32^3, MAXLEAF 16, theta 0.4, local list (381377 tasks, 
 with tempfile.TemporaryDirectory() as td:
     pf, of = os.path.join(td, "pos.f64"), os.path.join(td, "acc.f64")
     pos.tofile(pf)
-    for name in ("ref_gpu", "ref_dropin"):
+    for name in ("ref_gpu", "ref_gpu_r64", "ref_dropin"):
         exe = os.path.join(ROOT, "oracle", "_ref", name)
         if not os.path.isfile(exe):
             out[name] = "not built"
@@ -37,6 +37,24 @@ with tempfile.TemporaryDirectory() as td:
             {"rc": r.returncode, "stderr": r.stderr[-400:]}
         if m and g:
             out[name].update(copyMemGPU_s=float(g.group(1)), launch_sync_s=float(g.group(2)), readResultsGPU_s=float(g.group(3)))
+        if name == "ref_gpu_r64" and os.path.isfile(of):
+            # the reference kernel's own numbers (fp64, plain Newtonian, D4) against the oracle's restatement of the same
+            # arithmetic on the same list: task 0 is never computed and its result slot is never initialised (D1), so the
+            # oracle leaves task 0 out and the particles of task 0's target leaf are not compared
+            import oracle
+            T = oracle.Tree(pos, MAXLEAF, [0, 0, 0], [BOX] * 3, 0)
+            rs_, rcut_, eps_ = oracle.derived_params(BOX, NSIDE, len(pos))
+            tt, ts = T.walk_p2p(THETA, rcut_)
+            want_t, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt[1:], ts[1:], MASS, eps_, 0.0)
+            want = np.zeros_like(want_t)
+            want[T.perm] = want_t
+            got = np.fromfile(of).reshape(-1, 3)
+            keep = np.ones(len(pos), bool)
+            keep[T.perm[T.leaf_ipart[tt[0]]:T.leaf_ipart[tt[0]] + T.leaf_npart[tt[0]]]] = False
+            d = np.linalg.norm(got - want, axis=1)[keep]
+            na = np.linalg.norm(want, axis=1)[keep]
+            out[name]["kernel_vs_oracle_plain"] = {"max_rel_to_mean_force": float(d.max() / na.mean()), "nonzero_fraction": float((np.abs(got).sum(axis=1) > 0).mean()),
+                                                   "particles_compared": int(keep.sum()), "note": "fp64 both sides; task 0 left out (D1)"}
 # this repository, same input: host-list path (tree + walk on the host cores) and device-resident path
 rs, rcut, eps = host.derived_params(BOX, NSIDE, len(pos))
 ctx = p2p_b200.P2PContext(0)
