@@ -103,6 +103,24 @@ int p2p_domain_relax(int nproc, double box, double* split, const double* work);
 /* boxes (center_toptree, 1_Indexing/src/toptree.c:150-182) of the 2P-1 rank-tree nodes for given splits */
 int p2p_domain_boxes(int nproc, double box, const double* split, double* center, double* width, int* direct_of_node);
 
+/* Gadget-2 (format 1) snapshots (read_GadgetHeader / read_Particle_Gadget2 / write_Particle_Gadget2,
+ * 1_Indexing/src/snapshot.c:5-22,211-293,397-503): float32 positions and velocities on disk, all particle types
+ * concatenated, velocities scaled by a^(3/2) on input and back on output; ids are not stored (as in the reference). */
+typedef struct {
+    int64_t npart[6];           /* particles of each type in this file */
+    int64_t nfile;              /* their sum */
+    uint32_t npart_total[6];    /* of the whole snapshot */
+    double mass[6];
+    double time, redshift, box, omega0, omega_lambda, hubble;
+    int num_files;
+} p2p_snapshot_info;
+int p2p_snapshot_header(const char* path, p2p_snapshot_info* info);
+/* particles [n_start, n_start + n_count) of the file's order -> rows of doubles (pos / vel may be NULL) */
+int p2p_snapshot_read(const char* path, int64_t n_start, int64_t n_count, double* pos, int64_t pos_stride, double* vel, int64_t vel_stride);
+/* n_count particles as type 1 with info->mass[1], box, cosmology and redshift from info (vel NULL: zeros) */
+int p2p_snapshot_write(const char* path, const p2p_snapshot_info* info, int64_t n_count, const double* pos, int64_t pos_stride,
+                       const double* vel, int64_t vel_stride);
+
 int p2p_host_max_threads(void);
 
 #ifdef __cplusplus

@@ -555,7 +555,8 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     int r = reserve_csr(c, L, n, st);
     if (r) return r;
     const double far2 = far_threshold2(c);
-    if (far2 > 0.0) {
+    const bool v2 = c->variant != P2P_KERNEL_SCALAR && (c->tune_tt == 0 || c->tune_tt == 32);
+    if (far2 > 0.0 || v2) {                                // near / far classes, and the row reference points of the force kernel
         if ((r = leaf_bounds_fixed(c, st))) return r;
         CU(cudaStreamWaitEvent(st, c->ev_bounds, 0));      // bounds of earlier leaves may have been computed on another stream
     }
@@ -640,30 +641,42 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     P.counter = L.d_counter; P.n_active = L.d_counter + 2; P.row_order = L.order->p; P.nrow = c->nleaf;
     P.row_mid = L.row_mid->p; P.err = c->d_bad + 1; P.rows_per_warp = c->rows_per_warp;
     const bool trunc = c->rs > 0.0;
-    // kernel length unit: 2 r_s / sqrt(log2 e) for the truncated kernel (then exp(-u^2) = 2^(-r'^2) and the
-    // polynomial argument is r' = u sqrt(log2 e)), the box extent otherwise
+    const bool packed = c->variant != P2P_KERNEL_SCALAR;
+    const bool v2 = packed && (c->tune_tt == 0 || c->tune_tt == 32);
+    // kernel length unit.  Truncated kernel: L* = 2 r_s / sqrt(log2 e) makes exp(-u^2) = 2^(-r'^2); the second-generation
+    // kernel takes the power-of-two fraction of the frame nearest to it, L0 = extent / 2^p, so that the fixed-point step is
+    // 2^(p - 32) units EXACTLY, and carries kappa = (L0 / L*)^2 in its coefficients.  Plain kernel: the frame itself.
     const double sl2e = sqrt(1.4426950408889634);
-    const double unit = trunc ? 2.0 * c->rs / sl2e : (c->extent > 0.0 ? c->extent : 1.0);
+    double unit = trunc ? 2.0 * c->rs / sl2e : (c->extent > 0.0 ? c->extent : 1.0);
+    double kappa = 1.0;
+    if (trunc && v2 && c->extent > 0.0) {
+        const double lstar = unit;
+        unit = c->extent * exp2(-round(log2(c->extent / lstar)));
+        kappa = (unit / lstar) * (unit / lstar);
+    }
     P.k_fix = (float)(c->extent / 4294967296.0 / unit);
     P.eps2 = (float)((c->eps / unit) * (c->eps / unit));
     P.neps2 = -P.eps2;
+    P.nkappa = (float)-kappa;
+    P.u_scale = (float)(sqrt(kappa) / sl2e);
     if (trunc) {
-        // rinv' Q(u) = rinv' + v (c0 + c1 v + ...), v = r' : c_j = q_{j+2} / sl2e^(j+2)
-        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] / pow(sl2e, j + 2));
+        // rinv' Q(u) = rinv' + v (c0 + c1 v + ...), v = r / L*: c_j = q_{j+2} / sl2e^(j+2); in units of L0: c_j kappa^(1 + j/2)
+        for (int j = 0; j < p2p::kPolyTerms; j++) P.c[j] = (float)(P2P_GCOEF_10[j + 2] / pow(sl2e, j + 2) * pow(kappa, 1.0 + 0.5 * j));
         static_assert(p2p::kFarDegree == P2P_FAR_DEGREE, "far-field polynomial degree");
-        for (int j = 0; j < p2p::kFarTerms; j++) P.cf[j] = (float)P2P_GFAR[j];
-        P.far_shift = (float)P2P_FAR_SHIFT;
+        // far field: kappa^(3/2) 2^(-kappa w') H(t), t = t' / kappa, t' = 1 / (w' + shift / kappa)
+        for (int j = 0; j < p2p::kFarTerms; j++) P.cf[j] = (float)(P2P_GFAR[j] * pow(kappa, 1.5 - j));
+        P.far_s0 = (float)P2P_FAR_SHIFT;
+        P.far_shift = (float)(P2P_FAR_SHIFT / kappa);
         // dummy (padding) source: 2^(-r^2) flushes to exactly 0 there while r^8 still fits FP32, whatever the extent of the target leaf
         P.far_coord = 1000.0f * (float)sl2e;
     } else {
         P.far_coord = 1.0e18f;
     }
+    P.lbounds = (v2 && c->bounds_n >= c->nleaf && c->nleaf > 0) ? c->lbounds.p : nullptr;
     P.out_scale = (float)(c->mass / (unit * unit));
     CU(cudaMemsetAsync(L.d_counter, 0, sizeof(unsigned int), st));
     int r = 0;
     if (c->nleaf > 0 && ntask > 0) {
-        const bool packed = c->variant != P2P_KERNEL_SCALAR;
-        const bool v2 = packed && (c->tune_tt == 0 || c->tune_tt == 32);
         cudaStream_t keep = c->stream;
         c->stream = st;                                         // the launchers use c->stream
         if (v2) {

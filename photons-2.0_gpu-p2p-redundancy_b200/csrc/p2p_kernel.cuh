@@ -68,7 +68,15 @@ struct KernelParams {
     unsigned int* err;       // sticky error flag (a source leaf larger than the stage was skipped)
     int rows_per_warp;       // 0: persistent warps; k: a warp retires after k rows (second-generation kernel)
     float cf[kFarTerms];     // far-field polynomial H(t), t = 1 / (r'^2 + far_shift) (tools/fit_gfactor.py)
-    float far_shift;
+    float far_shift;         // shift in the kernel's length unit, far_s0 = nkappa * -far_shift (the shift of the fit)
+    float far_s0;
+    // Second-generation kernel: the length unit is extent / 2^p (p integer), so that k_fix is a POWER OF TWO and the
+    // conversion of a fixed-point offset costs one rounding (int -> float) instead of two; exp(-u^2) = 2^(-kappa r'^2) with
+    // kappa in [1/2, 2) absorbed into the polynomial coefficients and into the multiply that negates the exponent.
+    float nkappa;            // -kappa
+    float u_scale;           // u = r' u_scale (error-budget variant only)
+    const int4* lbounds;     // LeafBounds of the leaves (csr_pack.cuh) or nullptr: the row's reference point is the CENTRE of its
+                             // targets' bounds (offsets half as large as from the first target: half the rounding of the separations)
 };
 
 // MUFU.RSQ / MUFU.EX2.  The file is compiled with --use_fast_math, under which rsqrtf / exp2f ARE the bare
@@ -487,7 +495,7 @@ __device__ __forceinline__ void pair_near2(const KernelParams& P, float2 sx, flo
     const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
     float2 f;
     if (TRUNC) {
-        const float2 a = __fmul2_rn(r2, make_float2(-1.f, -1.f));
+        const float2 a = __fmul2_rn(r2, make_float2(P.nkappa, P.nkappa));
         const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
         const float2 v = __fmul2_rn(r2, rinv);
         // (a Newton step on rinv, 3 more instructions, changed the measured force error by 2 %: MUFU.RSQ is not what limits it)
@@ -515,7 +523,7 @@ __device__ __forceinline__ void pair_far2(const KernelParams& P, float2 sx, floa
     const float2 dx = __fadd2_rn(sx, tx), dy = __fadd2_rn(sy, ty), dz = __fadd2_rn(sz, tz);
     const float2 sh = make_float2(P.far_shift, P.far_shift);
     const float2 ws = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __ffma2_rn(dx, dx, sh)));     // w + shift
-    const float2 a = __ffma2_rn(ws, make_float2(-1.f, -1.f), sh);                         // -w
+    const float2 a = __ffma2_rn(ws, make_float2(P.nkappa, P.nkappa), make_float2(P.far_s0, P.far_s0));   // -kappa w
     const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
     const float2 t = make_float2(rcp_approx(ws.x), rcp_approx(ws.y));
     float2 p = make_float2(P.cf[kFarDegree], P.cf[kFarDegree]);
@@ -537,7 +545,7 @@ __device__ __forceinline__ void pair_exact2(const KernelParams& P, float2 sx, fl
     for (int k = 0; k < 2; k++) {
         const double q2 = (double)ddx[k] * ddx[k] + (double)ddy[k] * ddy[k] + (double)ddz[k] * ddz[k];
         const double r = sqrt(q2), rc = fmax(r, sqrt((double)P.eps2));
-        const double u = r * 0.8325546111576977;                // kernel length unit -> u = r / 2 r_s: 1 / sqrt(log2 e)
+        const double u = r * (double)P.u_scale;                  // kernel length unit -> u = r / 2 r_s
         const double g = erfc(u) + 1.1283791670955126 * u * exp(-u * u);
         f[k] = (float)(q2 < 1.0e5 ? g / (rc * rc * rc) : 0.0);
     }
@@ -548,6 +556,7 @@ __device__ __forceinline__ void pair_exact2(const KernelParams& P, float2 sx, fl
 }
 
 constexpr int kRowTargets = 32;         // = P2P_MAX_LEAF
+constexpr int kBlockLeaves = 128;       // source leaves per summation block of a row (4 staging chunks)
 
 template <int STAGE>
 struct alignas(128) WarpSmem2 {
@@ -696,8 +705,8 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
         const long long e_end = __ldg(P.row_ptr + row + 1);
         if (nt <= 0 || e_begin >= e_end) continue;
         const long long e_mid = TRUNC ? e_begin + __ldg(P.row_mid + row) : e_end;
-        // reference point of the row: its first target particle (fixed-point)
-        const int4 c4 = __ldg(P.part + tl.x);
+        // reference point of the row (fixed point): the centre of its targets' bounds, else its first target particle
+        const int4 c4 = P.lbounds ? __ldg(P.lbounds + 2 * row) : __ldg(P.part + tl.x);
         {   // targets -> shared: negated, relative to c4; padding slots repeat the first target
             const int4 t4 = __ldg(P.part + tl.x + (lane < nt ? lane : 0));
             float* base = reinterpret_cast<float*>(&S.tgt[lane >> 1]);
@@ -707,33 +716,43 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
         }
         __syncwarp();
 
-        float2 ax[TP], ay[TP], az[TP];
+        // BLOCKED SUMMATION.  A row's sources arrive in kd order, i.e. as a spatial sweep: the running sum of a lane swings to
+        // a large fraction of sum |terms| before the other side of the target cancels it, and every FP32 addition rounds
+        // relative to that swing (at z = 49 the net force is 1.4 % of sum |terms|).  The row is therefore consumed in blocks
+        // of at most kBlockLeaves source leaves, near and far columns apart; each block starts from zero accumulators and is
+        // reduced over the warp into the per-target totals of lane j (a handful of additions at the top level).
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        for (int far = 0; far < (TRUNC ? 2 : 1); far++) {
+            const long long c_end = far ? e_end : e_mid;
+            for (long long lo = far ? e_mid : e_begin; lo < c_end; lo += kBlockLeaves) {
+                const long long hi = lo + kBlockLeaves < c_end ? lo + kBlockLeaves : c_end;
+                float2 ax[TP], ay[TP], az[TP];
 #pragma unroll
-        for (int j = 0; j < TP; j++) ax[j] = ay[j] = az[j] = make_float2(0.f, 0.f);
-
-        switch ((nt + 1) >> 1) {                              // target pairs of this row (warp-uniform)
-#define P2P_CASE(k)                                                                                                             \
-    case k:                                                                                                                     \
-        if (e_mid > e_begin) run_range2<k, false, NSRC, STAGE, TRUNC, DBG>(P, S, c4, e_begin, e_mid, lane, phase0, phase1, ax, ay, az); \
-        if (TRUNC && e_end > e_mid) run_range2<k, true, NSRC, STAGE, TRUNC, DBG>(P, S, c4, e_mid, e_end, lane, phase0, phase1, ax, ay, az); \
+                for (int j = 0; j < TP; j++) ax[j] = ay[j] = az[j] = make_float2(0.f, 0.f);
+                switch ((nt + 1) >> 1) {                      // target pairs of this row (warp-uniform)
+#define P2P_CASE(k)                                                                                                           \
+    case k:                                                                                                                   \
+        if (far) run_range2<k, TRUNC, NSRC, STAGE, TRUNC, DBG>(P, S, c4, lo, hi, lane, phase0, phase1, ax, ay, az);           \
+        else run_range2<k, false, NSRC, STAGE, TRUNC, DBG>(P, S, c4, lo, hi, lane, phase0, phase1, ax, ay, az);               \
         break;
-            P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
-            P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
+                    P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
+                    P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
 #undef P2P_CASE
-            default: break;
+                    default: break;
+                }
+                // transposing butterfly: afterwards lane j holds target j's sums of this block
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < TP; j++) { v[2 * j] = ax[j].x; v[2 * j + 1] = ax[j].y; }
+                rx += transpose_reduce32(v, lane);
+#pragma unroll
+                for (int j = 0; j < TP; j++) { v[2 * j] = ay[j].x; v[2 * j + 1] = ay[j].y; }
+                ry += transpose_reduce32(v, lane);
+#pragma unroll
+                for (int j = 0; j < TP; j++) { v[2 * j] = az[j].x; v[2 * j + 1] = az[j].y; }
+                rz += transpose_reduce32(v, lane);
+            }
         }
-
-        // transposing butterfly: afterwards lane j holds target j's sums
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < TP; j++) { v[2 * j] = ax[j].x; v[2 * j + 1] = ax[j].y; }
-        const float rx = transpose_reduce32(v, lane);
-#pragma unroll
-        for (int j = 0; j < TP; j++) { v[2 * j] = ay[j].x; v[2 * j + 1] = ay[j].y; }
-        const float ry = transpose_reduce32(v, lane);
-#pragma unroll
-        for (int j = 0; j < TP; j++) { v[2 * j] = az[j].x; v[2 * j + 1] = az[j].y; }
-        const float rz = transpose_reduce32(v, lane);
         if (lane < nt) {
             float4* dst = P.acc + tl.x + lane;
             float4 a = *dst;
