@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (sizes whose positions do not fit pinned host memory)")
     ap.add_argument("--no-overlap", action="store_true", help="remote phase on the compute stream (A/B of the halo overlap)")
+    ap.add_argument("--no-launch-count", action="store_true", help="skip the CUPTI kernel count (it cannot run under ncu)")
     ap.add_argument("--relax", type=int, default=0, help="work-weighted split relaxations before the timed region (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -359,7 +360,7 @@ def main():
         assert abs(np2 - npairs) <= 1e-6 * npairs, ((nt2, np2), (ntask, npairs))
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    launches, nccl_launches = count_kernels(resident_step)
+    launches, nccl_launches = (None, None) if args.no_launch_count else count_kernels(resident_step)
 
     # ---------------------------------------------------------------- reduce over ranks
     if world > 1:

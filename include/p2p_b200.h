@@ -134,9 +134,9 @@ int p2p_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
 int p2p_accumulated_counts(p2p_ctx* ctx, int64_t* ntask, int64_t* npairs);
 /* copies of the device CSR for parity tests: row_ptr[nleaf+1] (int64), col[ntask] (int32) */
 int p2p_download_csr(p2p_ctx* ctx, int64_t* row_ptr, int* col);
-/* near / far class of every CSR column (1 = far, evaluated by the far-field body) and the number of near columns of
- * every row (a row's near columns come first); NULL skips */
-int p2p_download_csr_class(p2p_ctx* ctx, unsigned char* is_far, int* row_near);
+/* class of every CSR column (1 = far, evaluated by the far-field body) and the number of far columns of every row (a
+ * row's far columns come first, each class in ascending order); NULL skips */
+int p2p_download_csr_class(p2p_ctx* ctx, unsigned char* is_far, int* row_far);
 /* milliseconds spent by the last p2p_compute / p2p_build_csr launch sequence (CUDA events) */
 int p2p_last_timings(p2p_ctx* ctx, float* ms_compute, float* ms_csr);
 

@@ -152,8 +152,10 @@ __device__ __forceinline__ double bounds_gap2(const LeafBounds& a, const LeafBou
 }
 
 // Scatter into the CSR rows.  With far2 > 0 (truncated kernel) every column is classified on the way: a source leaf whose
-// bounds are at least sqrt(far2) fixed-point steps from the target leaf's gets bit 31 (the force kernel's cheap far body
-// is valid for every particle pair of such a leaf pair); the unsigned row sort then puts the far columns last.
+// bounds are at least sqrt(far2) fixed-point steps from the target leaf's is FAR (the force kernel's cheap far body is valid
+// for every particle pair of such a leaf pair), every other column is NEAR and carries bit 31, so the unsigned row sort puts
+// the far columns FIRST: the kernel sums the many small far terms before the few large near ones (FP32 rounding is
+// relative to the running sum).
 __global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
                                    unsigned long long* __restrict__ cursor, int* __restrict__ col, const LeafBounds* __restrict__ lb,
                                    double far2) {
@@ -162,10 +164,10 @@ __global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __rest
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
         if ((unsigned)t >= (unsigned)nrow || (unsigned)s >= (unsigned)nsrc) continue;
-        unsigned v = (unsigned)s;
+        unsigned v = (unsigned)s | 0x80000000u;            // bit 31: NEAR class (every column when no classes are wanted)
         if (far2 > 0.0) {
             const LeafBounds a = lb[t], b = lb[s];
-            if (bounds_gap2(a, b) >= far2) v |= 0x80000000u;
+            if (bounds_gap2(a, b) >= far2) v = (unsigned)s;
         }
         unsigned long long p = atomicAdd(cursor + t, 1ull);
         col[p] = (int)v;
@@ -178,7 +180,7 @@ constexpr int kSortCap = 2048;
 __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __restrict__ row_ptr, int nrow,
                                                             int* __restrict__ col_, unsigned int* __restrict__ unsorted) {
     __shared__ unsigned int sh[4][kSortCap];
-    unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);     // unsigned order: far columns (bit 31) last
+    unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);     // unsigned order: near columns (bit 31) last
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned int* a = sh[w];
     for (int row = blockIdx.x * 4 + w; row < nrow; row += gridDim.x * 4) {
@@ -273,16 +275,16 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
         const long long b = row_ptr[row], e = row_ptr[row + 1];
         const unsigned long long nt = (unsigned long long)leaf[row].y;
         unsigned long long ns = 0;
-        int near = 0;                                    // columns without the far bit: the row's leading part after the sort
+        int nfar = 0;                                    // columns without the near bit: the row's leading part after the sort
         for (long long i = b + lane; i < e; i += 32) {
             const unsigned int c = (unsigned int)col[i];
             ns += (unsigned long long)leaf[c & 0x7fffffffu].y;
-            near += (c >> 31) == 0;
+            nfar += (c >> 31) == 0;
         }
-        for (int d = 16; d >= 1; d >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, d); near += __shfl_xor_sync(0xffffffffu, near, d); }
+        for (int d = 16; d >= 1; d >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, d); nfar += __shfl_xor_sync(0xffffffffu, nfar, d); }
         const unsigned long long w = nt * ns;
         if (lane == 0) {
-            row_mid[row] = near;
+            row_mid[row] = nfar;
             row_work[row] = w;
             if (w) atomicAdd(hist + (row / band_rows) * kWorkBuckets + min((int)nt, kWorkBuckets - 1), 1u);
             s += w;

@@ -105,8 +105,8 @@ int get_tree(p2p_ctx* c, p2p_dtree** out) {
         c->dtree = t;
         CU(cudaMalloc(&t->d_scalar, 4 * sizeof(int)));
         CU(cudaMallocHost(&t->h_scalar, 4 * sizeof(int)));
-        CU(cudaMalloc(&t->d_wcount, 4 * sizeof(ull)));
-        CU(cudaMallocHost(&t->h_wcount, 4 * sizeof(ull)));
+        CU(cudaMalloc(&t->d_wcount, p2p::dt::kWalkCounters * sizeof(ull)));
+        CU(cudaMallocHost(&t->h_wcount, p2p::dt::kWalkCounters * sizeof(ull)));
         CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
         CU(cudaMalloc(&t->d_maxw, sizeof(int)));
         CU(cudaEventCreate(&t->e0));
@@ -746,63 +746,59 @@ namespace {
 // breadth-first walk from the given items; appends the tasks to the context's list
 int walk_impl(p2p_ctx* c, p2p_dtree* t, p2p::dt::WalkParams P, const std::vector<ull>& init, size_t task_guess) {
     cudaStream_t st = c->stream;
+    constexpr int NC = p2p::dt::kWalkCounters;
     // the M2L list ACCUMULATES over the walks of one tree (target chunks, local then remote phase); a tree build empties it
     const size_t m0 = (size_t)t->nm2l;
     t->mid_valid = false; t->walk_period = P.period;
-    if (t->m2l_on) {
-        const size_t mcap = m0 + std::max<size_t>(task_guess, 1 << 16);
-        CU(t->mt.reserve(mcap, st, m0)); CU(t->ms.reserve(mcap, st, m0)); CU(t->mq.reserve(mcap, st, m0));
-    }
-    size_t fcap = std::max<size_t>(task_guess / 2, 1 << 16);
+    size_t mcap = m0 + std::max<size_t>(task_guess / 8, 1 << 16);
+    size_t fcap = std::max<size_t>(std::max<size_t>(task_guess / 2, 1 << 16), init.size());
     size_t tcap = std::max<size_t>(task_guess, 1 << 16);
-    CU(t->frontier[0].reserve(std::max(fcap, init.size()), st)); CU(t->frontier[1].reserve(fcap, st));
-    CU(c->tt.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
-    CU(c->ts.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
     CU(cudaEventRecord(t->e0, st));
-    CU(cudaMemcpyAsync(t->frontier[0].p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(t->d_wcount, 0, 4 * sizeof(ull), st));
-    ull n_in = init.size(), ntask = 0, nm2l = 0, nviol = 0, items = 0;
-    int cur = 0, levels = 0;
-    while (n_in) {
-        if (++levels > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
-        for (int attempt = 0;; attempt++) {
-            if (attempt > 4) return fail(P2P_ERR_CUDA, "dual-tree walk: a level still overflows its buffers after %d attempts", attempt);
-            const ull cap_out = t->frontier[cur ^ 1].cap;
-            const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
-            const unsigned grid = (unsigned)std::min<ull>((n_in + 255) / 256, (ull)c->num_sm * 16);
-            P.mt = t->m2l_on ? t->mt.p + m0 : nullptr; P.ms = t->ms.p + m0; P.mq = t->mq.p + m0;
-            P.cap_m2l = t->m2l_on ? std::min(t->mt.cap, std::min(t->ms.cap, t->mq.cap)) - m0 : 0;
-            p2p::dt::walk_level_kernel<<<grid, 256, 0, st>>>(t->frontier[cur].p, n_in, t->frontier[cur ^ 1].p, cap_out, t->d_wcount,
-                                                             c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, P);
+    const int batch0 = 2 * (t->built_here ? t->nlevel : 24) + 8;      // the walk descends one tree level per step on either side
+    ull* h = t->h_wcount;
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 8) return fail(P2P_ERR_CUDA, "dual-tree walk: buffers still overflow after %d attempts", attempt);
+        if (t->m2l_on) { CU(t->mt.reserve(mcap, st, m0)); CU(t->ms.reserve(mcap, st, m0)); CU(t->mq.reserve(mcap, st, m0)); }
+        CU(t->frontier[0].reserve(fcap, st)); CU(t->frontier[1].reserve(fcap, st));
+        CU(c->tt.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
+        CU(c->ts.reserve((size_t)c->ntask + tcap, st, (size_t)c->ntask));
+        const ull cap_f = std::min(t->frontier[0].cap, t->frontier[1].cap);
+        const ull cap_task = std::min(c->tt.cap, c->ts.cap) - (size_t)c->ntask;
+        P.mt = t->m2l_on ? t->mt.p + m0 : nullptr; P.ms = t->ms.p + m0; P.mq = t->mq.p + m0;
+        P.cap_m2l = t->m2l_on ? std::min(t->mt.cap, std::min(t->ms.cap, t->mq.cap)) - m0 : 0;
+        CU(cudaMemcpyAsync(t->frontier[0].p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < NC; k++) h[k] = 0;
+        h[0] = init.size();
+        CU(cudaMemcpyAsync(t->d_wcount, h, NC * sizeof(ull), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));                     // h is reused for the read-back below
+        int level = 0;
+        bool done = false, overflow = false;
+        while (!done && !overflow) {
+            if (level > 4096) return fail(P2P_ERR_CUDA, "dual-tree walk did not terminate");
+            const int nb = level == 0 ? batch0 : 8;
+            for (int k = 0; k < nb; k++, level++)
+                p2p::dt::walk_level_kernel<<<c->num_sm * 8, 256, 0, st>>>(t->frontier[level & 1].p, cap_f, t->frontier[(level + 1) & 1].p, cap_f, t->d_wcount,
+                                                                          c->tt.p + c->ntask, c->ts.p + c->ntask, cap_task, level, P);
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(t->h_wcount, t->d_wcount, 4 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h, t->d_wcount, NC * sizeof(ull), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            const ull n_out = t->h_wcount[0], nt = t->h_wcount[1], nm = t->h_wcount[2];
-            if (n_out <= cap_out && nt <= cap_task && nm <= P.cap_m2l) { items += n_in; n_in = n_out; ntask = nt; nm2l = nm; nviol = t->h_wcount[3]; break; }
-            if (nm > P.cap_m2l) {
-                const size_t want = m0 + (size_t)(nm + nm / 2);
-                CU(t->mt.reserve(want, st, m0 + (size_t)nm2l)); CU(t->ms.reserve(want, st, m0 + (size_t)nm2l)); CU(t->mq.reserve(want, st, m0 + (size_t)nm2l));
-            }
-            // a buffer was too small: grow it and repeat this level from the same input
-            if (n_out > cap_out) CU(t->frontier[cur ^ 1].reserve((size_t)(n_out + n_out / 4), st));
-            if (nt > cap_task) {
-                const size_t want = (size_t)c->ntask + (size_t)(nt + nt / 2);
-                CU(c->tt.reserve(want, st, (size_t)(c->ntask + ntask)));
-                CU(c->ts.reserve(want, st, (size_t)(c->ntask + ntask)));
-            }
-            const ull reset[4] = {0, ntask, nm2l, nviol};
-            CU(cudaMemcpyAsync(t->d_wcount, reset, sizeof reset, cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));
+            overflow = h[6] != 0;
+            done = h[level % 3] == 0;
         }
-        cur ^= 1;
-        CU(cudaMemsetAsync(t->d_wcount, 0, sizeof(ull), st));
+        t->walk_levels = level;
+        if (!overflow) break;
+        // a buffer was too small somewhere: grow what overflowed (the counters kept counting past the capacities) and redo
+        if (h[6] & 1) fcap = std::max<size_t>(2 * fcap, (size_t)std::max(h[0], std::max(h[1], h[2])) + (1 << 16));
+        if (h[6] & 2) tcap = std::max<size_t>(tcap + tcap / 2, (size_t)h[3] + (size_t)h[3] / 8);
+        if (h[6] & 4) mcap = m0 + std::max<size_t>(2 * (mcap - m0), (size_t)h[4] + (size_t)h[4] / 8);
     }
+    const ull ntask = h[3], nm2l = h[4], nviol = h[5], items = h[7];
     CU(cudaEventRecord(t->e1, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&t->ms_walk, t->e0, t->e1));
     c->ntask += (long long)ntask;
     c->csr_valid = false;
-    t->walk_tasks = (long long)ntask; t->walk_items = (long long)items; t->walk_levels = levels;
+    t->walk_tasks = (long long)ntask; t->walk_items = (long long)items;
     t->nm2l = (long long)(m0 + nm2l);
     if (nviol)
         return fail(P2P_ERR_ARG, "%llu listed leaf pair(s) span half the period or more: the periodic box is too small for minimal-image "

@@ -1041,16 +1041,28 @@ __host__ __device__ __forceinline__ ull item(int im, int jm, int peer, int sh) {
 // either emits a leaf-leaf task, opens one side (2 items), opens both (self pair, 4 items) or dies.  The local
 // tree against itself without displacement follows walk_task_p2p; every other (rank, image) combination follows
 // walk_task_p2p_ext on the image prepare_sendtree2 would have sent, whose cut nodes are recognised on the fly.
-// Output slots are claimed per warp.  counters[0] = items written to `out`, counters[1] = tasks emitted so far;
-// writes beyond the capacities are dropped (the host sees the counts, grows the buffers and repeats the level).
-__global__ void __launch_bounds__(256, 4) walk_level_kernel(const ull* __restrict__ in, ull n_in, ull* __restrict__ out, ull cap_out,
-                                                         ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
-                                                         ull cap_task, WalkParams P) {
+//
+// The levels run WITHOUT host round-trips: the frontier sizes live in a ring of three device counters (level L reads
+// ring[L % 3], appends to ring[(L + 1) % 3] and clears ring[(L + 2) % 3] for the level after), the host enqueues a batch
+// of levels back to back (an exhausted frontier makes the remaining launches no-ops) and reads the counters once.
+// counters: [0..2] ring, [3] tasks, [4] M2L tasks, [5] minimal-image violations, [6] overflow flags, [7] items processed.
+// Writes beyond a capacity are dropped and flagged (the host grows the buffers and repeats the walk).
+constexpr int kWalkCounters = 8;
+__global__ void __launch_bounds__(256, 4) walk_level_kernel(const ull* __restrict__ in, ull cap_in, ull* __restrict__ out, ull cap_out,
+                                                            ull* __restrict__ counters, int* __restrict__ tt, int* __restrict__ ts,
+                                                            ull cap_task, int level, WalkParams P) {
     __shared__ int s_cnt[3][8];
     __shared__ ull s_base[3];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const ull stride = (ull)gridDim.x * blockDim.x;
+    ull n_in = counters[level % 3];
+    if (n_in > cap_in) n_in = cap_in;                     // an overflowed level: what was dropped is flagged already
+    // the slot the NEXT level appends to is cleared by every level, also by the no-op launches behind an exhausted frontier
+    // (it still holds the input count of the level before this one)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[(level + 2) % 3] = 0; counters[7] += n_in; }
+    if (n_in == 0) return;
+    ull* const c_out = counters + (level + 1) % 3;
     const ull n_round = (n_in + 255) & ~255ull;           // whole blocks iterate together (block-wide slot claims)
     for (ull idx = (ull)blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
         int nchild = 0;
@@ -1090,7 +1102,7 @@ __global__ void __launch_bounds__(256, 4) walk_level_kernel(const ull* __restric
                             const double d = fmax(bi[3 + k] - (bj[k] + disp), (bj[3 + k] + disp) - bi[k]);
                             bad |= !(d < 0.5 * P.period);
                         }
-                    if (bad) atomicAdd(&counters[3], 1ull);
+                    if (bad) atomicAdd(&counters[5], 1ull);
                 }
             } else {
                 const double* bi = P.box + 6 * (size_t)im;
@@ -1164,7 +1176,11 @@ __global__ void __launch_bounds__(256, 4) walk_level_kernel(const ull* __restric
         if (threadIdx.x < 3) {
             int run = 0;
             for (int w = 0; w < 8; w++) { const int v = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = run; run += v; }
-            s_base[threadIdx.x] = run ? atomicAdd(&counters[threadIdx.x], (ull)run) : 0ull;
+            ull* const ctr = threadIdx.x == 0 ? c_out : counters + 2 + threadIdx.x;          // frontier, tasks [3], M2L tasks [4]
+            const ull cap = threadIdx.x == 0 ? cap_out : (threadIdx.x == 1 ? cap_task : P.cap_m2l);
+            const ull b = run ? atomicAdd(ctr, (ull)run) : 0ull;
+            if (run && b + (ull)run > cap) atomicOr(&counters[6], 1ull << threadIdx.x);
+            s_base[threadIdx.x] = b;
         }
         __syncthreads();
         if (nchild) {

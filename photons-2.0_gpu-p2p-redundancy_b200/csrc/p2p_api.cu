@@ -640,6 +640,11 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = L.row_ptr->p; P.col = L.col->p; P.acc = c->acc.p;
     P.counter = L.d_counter; P.n_active = L.d_counter + 2; P.row_order = L.order->p; P.nrow = c->nleaf;
     P.row_mid = L.row_mid->p; P.err = c->d_bad + 1; P.rows_per_warp = c->rows_per_warp;
+    {
+        static int blk = 0;                         // sweeps only: P2P_B200_BLOCK_LEAVES overrides the block size
+        if (!blk) { const char* e = getenv("P2P_B200_BLOCK_LEAVES"); blk = e ? atoi(e) : p2p::kBlockLeaves; if (blk < 1) blk = p2p::kBlockLeaves; }
+        P.block_leaves = blk;
+    }
     const bool trunc = c->rs > 0.0;
     const bool packed = c->variant != P2P_KERNEL_SCALAR;
     const bool v2 = packed && (c->tune_tt == 0 || c->tune_tt == 32);
@@ -796,11 +801,11 @@ int p2p_download_csr(p2p_ctx* c, int64_t* row_ptr, int* col) {
     if (row_ptr) CU(cudaMemcpyAsync(row_ptr, c->row_ptr.p, ((size_t)c->nleaf + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     if (col && c->ntask) CU(cudaMemcpyAsync(col, c->col.p, (size_t)c->ntask * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (col) for (long long i = 0; i < c->ntask; i++) col[i] &= 0x7fffffff;       // bit 31: near / far class of the column
+    if (col) for (long long i = 0; i < c->ntask; i++) col[i] &= 0x7fffffff;       // bit 31: class of the column
     return 0;
 }
 
-int p2p_download_csr_class(p2p_ctx* c, unsigned char* is_far, int* row_near) {
+int p2p_download_csr_class(p2p_ctx* c, unsigned char* is_far, int* row_far) {
     USE(c);
     if (!c->csr_valid) return fail(P2P_ERR_STATE, "no CSR built");
     if (is_far && c->ntask) {
@@ -808,13 +813,13 @@ int p2p_download_csr_class(p2p_ctx* c, unsigned char* is_far, int* row_near) {
         if (!tmp) return fail(P2P_ERR_ARG, "out of host memory");
         cudaError_t e = cudaMemcpyAsync(tmp, c->col.p, (size_t)c->ntask * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e == cudaSuccess) for (long long i = 0; i < c->ntask; i++) is_far[i] = (unsigned char)((unsigned)tmp[i] >> 31);
+        if (e == cudaSuccess) for (long long i = 0; i < c->ntask; i++) is_far[i] = (unsigned char)(((unsigned)tmp[i] >> 31) ^ 1u);
         free(tmp);
         CU(e);
     }
-    if (row_near && c->nleaf) {
-        if (c->ntask) CU(cudaMemcpyAsync(row_near, c->row_mid.p, (size_t)c->nleaf * 4, cudaMemcpyDeviceToHost, c->stream));
-        else memset(row_near, 0, (size_t)c->nleaf * 4);
+    if (row_far && c->nleaf) {
+        if (c->ntask) CU(cudaMemcpyAsync(row_far, c->row_mid.p, (size_t)c->nleaf * 4, cudaMemcpyDeviceToHost, c->stream));
+        else memset(row_far, 0, (size_t)c->nleaf * 4);
     }
     CU(cudaStreamSynchronize(c->stream));
     return 0;

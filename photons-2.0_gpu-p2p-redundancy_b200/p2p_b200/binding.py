@@ -255,7 +255,7 @@ class P2PContext:
         return nt.value, npairs.value
 
     def download_csr(self, raw=False):
-        """(row_ptr, col) of the packed list.  On the device a row holds its near source leaves first, then its far ones
+        """(row_ptr, col) of the packed list.  On the device a row holds its far source leaves first, then its near ones
         (download_csr_class), each class in ascending order; raw=False returns the canonical form (whole rows ascending)."""
         nt, _ = self.counts()
         row = np.zeros(self.nleaf + 1, np.int64)
@@ -268,12 +268,12 @@ class P2PContext:
         return row, col
 
     def download_csr_class(self):
-        """(is_far per CSR column, number of near columns per row): the near / far split the force kernel uses"""
+        """(is_far per CSR column, number of far columns per row -- they come first): the split the force kernel uses"""
         nt, _ = self.counts()
         far = np.zeros(max(nt, 1), np.uint8)
-        near = np.zeros(max(self.nleaf, 1), np.int32)
-        self._chk(self._L.p2p_download_csr_class(self._h, far.ctypes.data_as(C.POINTER(C.c_ubyte)), near.ctypes.data_as(_ip)))
-        return far[:nt], near[:self.nleaf]
+        nfar = np.zeros(max(self.nleaf, 1), np.int32)
+        self._chk(self._L.p2p_download_csr_class(self._h, far.ctypes.data_as(C.POINTER(C.c_ubyte)), nfar.ctypes.data_as(_ip)))
+        return far[:nt], nfar[:self.nleaf]
 
     def last_timings(self):
         a, b = C.c_float(), C.c_float()

@@ -62,12 +62,12 @@ def test_demo_local_list(ctx, demo_pos, golden, maxleaf, truncated, variant):
     row, col = ctx.download_csr(raw=True)
     order = np.lexsort((ts, tt))
     assert np.array_equal(row, np.searchsorted(tt[order], np.arange(T.nleaf + 1)))
-    far, near = ctx.download_csr_class()
+    far, nfar = ctx.download_csr_class()
     rid = np.repeat(np.arange(T.nleaf), np.diff(row))
-    # CSR == the list: every row holds exactly its sources, near ones first, each class in ascending order
+    # CSR == the list: every row holds exactly its sources, far ones first, each class in ascending order
     assert np.array_equal(col[np.lexsort((col, rid))], ts[order])
-    assert np.array_equal(np.lexsort((col, far, rid)), np.arange(len(col)))
-    assert np.array_equal(np.bincount(rid[far == 0], minlength=T.nleaf), near)
+    assert np.array_equal(np.lexsort((col, 1 - far.astype(np.int64), rid)), np.arange(len(col)))
+    assert np.array_equal(np.bincount(rid[far == 1], minlength=T.nleaf), nfar)
     if truncated and variant == p2p_b200.binding.KERNEL_PACKED:
         # classification: exactly the leaf pairs whose particles are ALL at least 2 r_s u_far apart (tight bounds, fixed point)
         assert 0.3 < far.mean() < 0.9
@@ -253,7 +253,7 @@ def test_chunk_pipelined_host_step(demo_pos):
 
 def test_long_rows_are_sorted_and_classified(ctx):
     """A dense clump: rows with more sources than the shared-memory row sort holds (2048) go through the global-memory
-    network; the result must still be near-then-far, ascending, bit-reproducible, and equal to the oracle."""
+    network; the result must still be far-then-near, ascending, bit-reproducible, and equal to the oracle."""
     rng = np.random.default_rng(5)
     box = 64.0
     pos = np.concatenate([rng.uniform(0, box, (4000, 3)), 32.0 + rng.normal(0, 0.4, (20000, 3))]) % box
@@ -264,9 +264,9 @@ def test_long_rows_are_sorted_and_classified(ctx):
     assert np.bincount(tt).max() > 2048
     acc = _run(ctx, T, tt, ts, mass, eps, rs, p2p_b200.binding.KERNEL_PACKED, box)
     row, col = ctx.download_csr(raw=True)
-    far, near = ctx.download_csr_class()
+    far, nfar = ctx.download_csr_class()
     rid = np.repeat(np.arange(T.nleaf), np.diff(row))
-    assert np.array_equal(np.lexsort((col, far, rid)), np.arange(len(col)))
+    assert np.array_equal(np.lexsort((col, 1 - far.astype(np.int64), rid)), np.arange(len(col)))
     assert far.any() and not far.all()
     ctx.zero_acc(); ctx.compute()
     assert np.array_equal(acc, ctx.download_acc())

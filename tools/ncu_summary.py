@@ -40,10 +40,17 @@ def launches(path, out):
 
 def traffic(path, key, pattern):
     sel = {}
-    for r in rows(path):
-        if not re.search(pattern, r["Kernel Name"]):
-            continue
-        sel.setdefault(r["ID"], {})[r["Metric Name"]] = (r["Metric Value"].replace(",", ""), r.get("Metric Unit", ""))
+    table = rows(path)
+    if table and "Metric Name" not in table[0]:
+        # `--page raw` is wide: one row per launch, one column per metric, and the first data row holds the units
+        units = table[0]
+        for r in table[1:]:
+            if re.search(pattern, r["Kernel Name"]):
+                sel[r["ID"]] = {k: (v.replace(",", ""), units.get(k, "")) for k, v in r.items() if v not in (None, "")}
+    else:
+        for r in table:
+            if re.search(pattern, r["Kernel Name"]):
+                sel.setdefault(r["ID"], {})[r["Metric Name"]] = (r["Metric Value"].replace(",", ""), r.get("Metric Unit", ""))
     if not sel:
         raise SystemExit(f"no launch matches {pattern}")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -52,7 +59,10 @@ def traffic(path, key, pattern):
         if name not in d:
             return None
         v, u = d[name]
-        return float(v) * (units or {}).get(u, 1.0)
+        try:
+            return float(v) * (units or {}).get(u, 1.0)
+        except ValueError:
+            return None
     out = []
     for lid, d in sel.items():
         rd, wr = get(d, "dram__bytes_read.sum", scale), get(d, "dram__bytes_write.sum", scale)
