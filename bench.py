@@ -324,6 +324,8 @@ def main():
     force_ms = float(np.mean(kernel_ms))
     breakdown = {k: tm[k] for k in ("build_ms", "walk_ms", "csr_ms", "force_ms", "comm_ms", "remote_walk_ms", "force_local_ms", "force_remote_ms")}
     ghost_particles, chunks = tm["ghost_particles"], tm["chunks"]
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    hbm_used_gb = round((total_b - free_b) / 1e9, 2)
 
     # ---------------------------------------------------------------- e2e: host buffers through the public call
     e2e_ms, e2e_tm, h2d, d2h = None, {}, 0, 0
@@ -393,7 +395,7 @@ def main():
                            pairs_per_step=all_pairs, imbalance=imbalance, ghost_particles=all_ghost, chunks=chunks,
                            halo_overlap=bool(overlap and world > 1), relaxations=len(history),
                            step="resident particles -> tree build + walk + [topology / halo exchange] + packing + forces",
-                           setup_s=round(t_setup, 3), generate_and_upload_s=round(t_gen, 3)),
+                           setup_s=round(t_setup, 3), generate_and_upload_s=round(t_gen, 3), hbm_used_gb_rank0=hbm_used_gb),
             "step_breakdown_ms": breakdown,
             "gpu_launches": (launches * args.steps) if launches is not None else None,
             "gpu_launches_per_step": launches, "nccl_kernels_per_step": nccl_launches,

@@ -15,14 +15,16 @@
 namespace p2p {
 
 // Counts tasks per target leaf.  Task ids are validated HERE (the host never walks the list): a task
-// outside [0,nrow) x [0,nsrc) raises *bad and is dropped by the scatter as well.
-__global__ void csr_count_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
+// outside [row0, row0 + nrow) x [0,nsrc) raises *bad and is dropped by the scatter as well.  (row0, nrow) is the row
+// window of the list: the whole leaf table, or the target range of one chunk of a chunked step -- every per-row pass of
+// the packing then touches that window only.
+__global__ void csr_count_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int row0, int nrow, int nsrc,
                                  unsigned int* __restrict__ cnt, unsigned int* __restrict__ bad) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
-        if ((unsigned)t < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) atomicAdd(cnt + t, 1u);
+        if ((unsigned)(t - row0) < (unsigned)nrow && (unsigned)s < (unsigned)nsrc) atomicAdd(cnt + t, 1u);
         else atomicAdd(bad, 1u);
     }
 }
@@ -156,14 +158,14 @@ __device__ __forceinline__ double bounds_gap2(const LeafBounds& a, const LeafBou
 // for every particle pair of such a leaf pair), every other column is NEAR and carries bit 31, so the unsigned row sort puts
 // the far columns FIRST: the kernel sums the many small far terms before the few large near ones (FP32 rounding is
 // relative to the running sum).
-__global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int nrow, int nsrc,
+__global__ void csr_scatter_kernel(const int* __restrict__ tt, const int* __restrict__ ts, long long n, int row0, int nrow, int nsrc,
                                    unsigned long long* __restrict__ cursor, int* __restrict__ col, const LeafBounds* __restrict__ lb,
                                    double far2) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const int t = tt[i], s = ts[i];
-        if ((unsigned)t >= (unsigned)nrow || (unsigned)s >= (unsigned)nsrc) continue;
+        if ((unsigned)(t - row0) >= (unsigned)nrow || (unsigned)s >= (unsigned)nsrc) continue;
         unsigned v = (unsigned)s | 0x80000000u;            // bit 31: NEAR class (every column when no classes are wanted)
         if (far2 > 0.0) {
             const LeafBounds a = lb[t], b = lb[s];
@@ -261,8 +263,9 @@ __global__ void band_rows_kernel(const unsigned int* __restrict__ occ, int nrow,
         *band_rows = max(kMinBandRows, (nrow + nband - 1) / nband);
     }
 }
+// (row_ptr, row_work, row_mid are the caller's arrays advanced to the first row of the window; leaf is the whole table)
 __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ col,
-                                                         const int2* __restrict__ leaf, int nrow,
+                                                         const int2* __restrict__ leaf, int row0, int nrow,
                                                          unsigned long long* __restrict__ npairs,
                                                          unsigned long long* __restrict__ row_work,
                                                          unsigned int* __restrict__ hist, const int* __restrict__ band_rows_p,
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const long long* __rest
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int row = warp; row < nrow; row += nwarp) {
         const long long b = row_ptr[row], e = row_ptr[row + 1];
-        const unsigned long long nt = (unsigned long long)leaf[row].y;
+        const unsigned long long nt = (unsigned long long)leaf[row0 + row].y;
         unsigned long long ns = 0;
         int nfar = 0;                                    // columns without the near bit: the row's leading part after the sort
         for (long long i = b + lane; i < e; i += 32) {
@@ -340,12 +343,12 @@ __global__ void __launch_bounds__(1024) work_bucket_offsets_kernel(const unsigne
     if (threadIdx.x == 0) *n_active = carry;
 }
 __global__ void work_order_scatter_kernel(const unsigned long long* __restrict__ row_work, const int2* __restrict__ nt_of,
-                                          int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order, const int* __restrict__ band_rows_p) {
+                                          int row0, int nrow, unsigned int* __restrict__ cursor, int* __restrict__ order, const int* __restrict__ band_rows_p) {
     const int band_rows = *band_rows_p;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row < nrow) {
         const unsigned long long w = row_work[row];
-        if (w) order[atomicAdd(cursor + (row / band_rows) * kWorkBuckets + min(nt_of[row].y, kWorkBuckets - 1), 1u)] = row;
+        if (w) order[atomicAdd(cursor + (row / band_rows) * kWorkBuckets + min(nt_of[row0 + row].y, kWorkBuckets - 1), 1u)] = row0 + row;
     }
 }
 

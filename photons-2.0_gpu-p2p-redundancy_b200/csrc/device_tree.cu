@@ -1145,9 +1145,12 @@ int p2p_forces_local(p2p_ctx* c, double theta, double rcut, double period, const
         if (r) return r;
         t->sum_walk += t->ms_walk;
         CU(cudaEventRecord(t->chunk_ev[4 * ch], c->stream));
-        if ((r = p2p_build_csr(c))) return r;
+        if (nchunk > 1) { c->row_lo = lo; c->row_hi = hi; }      // the chunk's tasks have their targets in [lo, hi): pack those rows only
+        r = hi > lo || nchunk == 1 ? p2p_build_csr(c) : 0;
+        c->row_lo = c->row_hi = 0;
+        if (r) return r;
         CU(cudaEventRecord(t->chunk_ev[4 * ch + 1], c->stream));
-        if (compute && (r = p2p_compute(c))) return r;
+        if (compute && (hi > lo || nchunk == 1) && (r = p2p_compute(c))) return r;
         CU(cudaEventRecord(t->chunk_ev[4 * ch + 2], c->stream));
     }
     return 0;

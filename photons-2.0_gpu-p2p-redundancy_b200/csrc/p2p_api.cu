@@ -551,9 +551,13 @@ int leaf_bounds_fixed(p2p_ctx* c, cudaStream_t st) {
 
 // count -> scan -> scatter (+ near / far classification) -> sort -> pair count of the n tasks in L.tt / L.ts, all on stream st
 int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
-    const int nrow = c->nleaf;
+    const int nleaf = c->nleaf;
     int r = reserve_csr(c, L, n, st);
     if (r) return r;
+    // row window: the whole leaf table, or the target range of the chunk being packed (p2p_forces_local); rows outside the
+    // window keep whatever an earlier packing left and are never scheduled
+    const int row0 = c->row_hi > c->row_lo ? c->row_lo : 0;
+    const int nrow = c->row_hi > c->row_lo ? std::min(c->row_hi, nleaf) - row0 : nleaf;
     const double far2 = far_threshold2(c);
     const bool v2 = c->variant != P2P_KERNEL_SCALAR && (c->tune_tt == 0 || c->tune_tt == 32);
     if (far2 > 0.0 || v2) {                                // near / far classes, and the row reference points of the force kernel
@@ -561,12 +565,12 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
         CU(cudaStreamWaitEvent(st, c->ev_bounds, 0));      // bounds of earlier leaves may have been computed on another stream
     }
     const int ntile = (nrow + p2p::kScanTile - 1) / p2p::kScanTile;
-    CU(cudaMemsetAsync(L.cnt->p, 0, ((size_t)nrow + 1) * 4, st));
+    CU(cudaMemsetAsync(L.cnt->p + row0, 0, ((size_t)nrow + 1) * 4, st));
     CU(cudaMemsetAsync(L.d_counter, 0, 4 * sizeof(unsigned int), st));
     const int nband = nrow / p2p::kMinBandRows + 1;                    // upper bound; the band size itself is chosen on the device
     CU(cudaMemsetAsync(L.whist->p, 0, (2 * (size_t)p2p::kWorkBuckets * nband + 128) * sizeof(unsigned int), st));
     CU(cudaMemsetAsync(L.d_npairs, 0, sizeof(unsigned long long), st));
-    if (nrow == 0) {
+    if (nrow <= 0) {
         CU(cudaMemsetAsync(L.row_ptr->p, 0, sizeof(long long), st));
         if (n > 0) CU(cudaMemsetAsync(c->d_bad, 0xff, sizeof(unsigned int), st));          // every task is out of range
         return 0;
@@ -574,23 +578,24 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     const int G = c->num_sm * 8;
     const int nsrc = c->nleaf + c->nghostleaf;
     if (n) {
-        p2p::csr_count_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cnt->p, c->d_bad);
+        p2p::csr_count_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, row0, nrow, nsrc, L.cnt->p, c->d_bad);
         CU(cudaGetLastError());
     }
-    p2p::scan_tile_sums_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p);
+    p2p::scan_tile_sums_kernel<<<ntile, 256, 0, st>>>(L.cnt->p + row0, nrow, L.tile->p);
     p2p::scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(L.tile->p, ntile);
-    p2p::scan_apply_kernel<<<ntile, 256, 0, st>>>(L.cnt->p, nrow, L.tile->p, L.row_ptr->p, L.cursor->p);
+    p2p::scan_apply_kernel<<<ntile, 256, 0, st>>>(L.cnt->p + row0, nrow, L.tile->p, L.row_ptr->p + row0, L.cursor->p + row0);
     CU(cudaGetLastError());
     if (n) {
-        p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, nrow, nsrc, L.cursor->p, L.col->p,
+        p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, row0, nrow, nsrc, L.cursor->p, L.col->p,
                                                    reinterpret_cast<const p2p::LeafBounds*>(c->lbounds.p), far2);
-        p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p, nrow, L.col->p, L.d_counter + 1);
-        p2p::csr_sort_long_rows_kernel<<<c->num_sm * 2, 256, 0, st>>>(L.row_ptr->p, nrow, L.col->p);
+        p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p + row0, nrow, L.col->p, L.d_counter + 1);
+        p2p::csr_sort_long_rows_kernel<<<c->num_sm * 2, 256, 0, st>>>(L.row_ptr->p + row0, nrow, L.col->p);
         int* d_band = reinterpret_cast<int*>(L.whist->p + 2 * (size_t)p2p::kWorkBuckets * nband);
         p2p::band_rows_kernel<<<1, 32, 0, st>>>(c->d_occ, nrow, c->num_sm * 16, band_rows(), d_band);
-        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p, L.col->p, c->leaf.p, nrow, L.d_npairs, L.row_work->p, L.whist->p, d_band, L.row_mid->p);
+        p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p + row0, L.col->p, c->leaf.p, row0, nrow, L.d_npairs, L.row_work->p + row0, L.whist->p,
+                                                  d_band, L.row_mid->p + row0);
         p2p::work_bucket_offsets_kernel<<<1, 1024, 0, st>>>(L.whist->p, L.whist->p + p2p::kWorkBuckets * nband, nband, L.d_counter + 2);
-        p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p, c->leaf.p, nrow,
+        p2p::work_order_scatter_kernel<<<(nrow + 255) / 256, 256, 0, st>>>(L.row_work->p + row0, c->leaf.p, row0, nrow,
                                                                           L.whist->p + p2p::kWorkBuckets * nband, L.order->p, d_band);
         CU(cudaGetLastError());
     }

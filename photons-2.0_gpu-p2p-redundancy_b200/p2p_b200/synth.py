@@ -15,6 +15,7 @@ DEMO_NSIDE = 32
 DEMO_MASS = 211.75382579190332
 SEED = 20250101
 BLOCK = 1 << 20         # particles per random stream
+MAX_CLUMP = 1 << 21     # particles in the largest clump of the clustered box (binds from 1024^3 on)
 
 
 def box_for(nside_particles):
@@ -95,6 +96,13 @@ class HaloCatalogue:
         self.nhalo = max(1, nh_part // 2000)
         occ = rng.pareto(1.0, self.nhalo) + 1.0
         self.weight = occ / occ.sum()
+        # the Pareto tail can hand one clump most of the box (the 1024^3 draw: 71 %); no clump holds more than 2^21 particles
+        cap = MAX_CLUMP / max(nh_part, 1)
+        while self.weight.max() > cap * (1 + 1e-9) and cap * self.nhalo > 1.0:
+            w = np.minimum(self.weight, cap)
+            free = w < cap
+            w[free] *= (1.0 - cap * np.count_nonzero(~free)) / w[free].sum()
+            self.weight = w
         self.cdf = np.cumsum(self.weight)
         self.cdf[-1] = 1.0
         self.centers = rng.uniform(0, box, size=(self.nhalo, 3))
