@@ -87,9 +87,10 @@ int p2p_set_stream(p2p_ctx* ctx, void* cuda_stream);
  * one set, on a second stream, while the force kernel still consumes the local list in the other
  * (replaces the ping-pong task buffers of 1_Indexing/src/fmm.c:365-400). */
 int p2p_swap_lists(p2p_ctx* ctx);
-/* force kernel blocks: 0 = persistent warps (default); k > 0 = a warp retires after k rows, so that kernels of
- * higher-priority streams (NCCL, the halo walk) get SM slots while the force kernel runs */
-int p2p_set_force_blocks(p2p_ctx* ctx, int rows_per_warp);
+/* force kernel blocks: 0 = persistent warps (default); k > 0 = a warp retires once it has run for k x 2^17 SM cycles
+ * (about k x 70 us; at least one row), so that kernels of higher-priority streams (NCCL, the halo walk) get SM slots while
+ * the force kernel runs; one last wave of blocks is persistent and finishes the schedule */
+int p2p_set_force_blocks(p2p_ctx* ctx, int budget);
 /* room for ghost leaves / particles behind the local ones, reserved BEFORE a force kernel is in flight (growing the
  * particle array later would have to wait for it) */
 int p2p_reserve_ghosts(p2p_ctx* ctx, int nghostleaf, int64_t nghost);

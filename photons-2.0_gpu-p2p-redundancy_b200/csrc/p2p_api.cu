@@ -152,8 +152,12 @@ int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
     if (per_sm < 1) return fail(P2P_ERR_CUDA, "force kernel does not fit on an SM (smem %d)", smem);
     long long want = ((long long)P.nrow + 3) / 4;
     long long grid = std::min<long long>((long long)c->num_sm * per_sm, std::max<long long>(want, 1));
-    if (P.rows_per_warp > 0) grid = std::max<long long>((want + P.rows_per_warp - 1) / P.rows_per_warp, 1);   // every row finds a warp
-    kern<<<(unsigned)grid, 128, smem, c->stream>>>(P);
+    p2p::KernelParams Q = P;
+    Q.persist_blocks = (int)grid;
+    // non-persistent mode: budgeted blocks in front of one persistent wave; a budgeted block handles at least four rows, blocks
+    // that find the schedule exhausted leave at once
+    if (P.rows_per_warp > 0) grid += want / 2;
+    kern<<<(unsigned)grid, 128, smem, c->stream>>>(Q);
     CU(cudaGetLastError());
     c->last_blocks_per_sm = per_sm;
     return 0;

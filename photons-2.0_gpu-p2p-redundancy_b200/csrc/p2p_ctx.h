@@ -63,9 +63,9 @@ struct p2p_ctx {
     // multi-rank step is walked and packed while the force kernel still consumes the local list
     long long ntask_b = 0, npairs_b = -1;
     bool csr_valid_b = false;
-    int rows_per_warp = 0;                  // force kernel: 0 = persistent warps, k = a warp retires after k rows (lets kernels of
+    int rows_per_warp = 0;                  // force kernel: 0 = persistent warps, k = a warp retires after k x 2^17 cycles (lets kernels
+                                            // of higher-priority streams -- NCCL, the halo walk -- in between)
     int row_lo = 0, row_hi = 0;             // row window of the next packing (row_hi <= row_lo: the whole leaf table), set per chunk by p2p_forces_local
-                                            // higher-priority streams -- NCCL, the halo walk -- in between)
     int nleaf = 0, nghostleaf = 0, max_target_leaf = 0;
     bool csr_valid = false;
     DevBuf<int4> part;

@@ -518,8 +518,9 @@ class P2PContext:
     def swap_lists(self):
         self._chk(self._L.p2p_swap_lists(self._h))
 
-    def set_force_blocks(self, rows_per_warp=0):
-        self._chk(self._L.p2p_set_force_blocks(self._h, int(rows_per_warp)))
+    def set_force_blocks(self, budget=0):
+        """0: persistent force-kernel warps; k: warps retire after k x 2^17 cycles (slots for higher-priority streams)"""
+        self._chk(self._L.p2p_set_force_blocks(self._h, int(budget)))
 
     def reserve_ghosts(self, nghostleaf, nghost):
         self._chk(self._L.p2p_reserve_ghosts(self._h, int(nghostleaf), int(nghost)))

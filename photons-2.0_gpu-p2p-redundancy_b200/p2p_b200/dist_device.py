@@ -205,7 +205,7 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
     built.record(A)
     # ---- local phase: my tree against itself and its own periodic images (walk, packing, force kernel; in target chunks
     # when the list would not fit)
-    ctx.set_force_blocks(1 if (P > 1 and overlap) else 0)
+    ctx.set_force_blocks(4 if (P > 1 and overlap) else 0)        # warps retire after ~0.3 ms
     ctx.forces_local(theta, rcut, period, tc, tw, p2p)
     ctx.set_force_blocks(0)
     t2 = time.perf_counter()

@@ -134,6 +134,38 @@ def test_edge_cases(ctx):
             assert (d[sel] / na[sel]).max() < TOL, (maxleaf, variant)
 
 
+def test_softened_pairs_deviate_by_less_than_the_analytic_bound(ctx):
+    """Inside the softening length the reference replaces r by eps in 1/r^3 only -- erfc / exp still see the true r
+    (2_Redundant/src/photoNs_CUDA.cu:432-450) -- while the kernel clamps r^2 once for both.  With u = r / 2 r_s and
+    g'(u) = -(4/sqrt(pi)) u^2 exp(-u^2) the truncation factors differ by |g(u) - g(u_eps)| <= 4 / (3 sqrt(pi)) u_eps^3.
+    A clump whose every pair is softened, with eps / 2 r_s = 0.2 so that the deviation (6e-3) towers over FP32 rounding:
+    the result must sit within the bound of the oracle (which implements the reference's form), and must sit within
+    FP32 rounding of the clamped form -- i.e. the deviation is this and nothing else."""
+    from math import erfc, exp, pi, sqrt
+    rng = np.random.default_rng(5)
+    box, eps, rs, mass = 64.0, 0.4, 1.0, 2.0
+    n = 64
+    pos = (np.full(3, 20.0) + rng.uniform(-0.1, 0.1, (n, 3))).astype(np.float32).astype(np.float64)   # all separations < 0.35 < eps
+    T = oracle.Tree(pos, 32, [0, 0, 0], [box] * 3, 0)
+    tt, ts = T.walk_p2p(THETA, 4.5 * rs)
+    u_eps = eps / (2 * rs)
+    bound = 4.0 / (3.0 * sqrt(pi)) * u_eps ** 3
+    g_eps = erfc(u_eps) + 2 * u_eps / sqrt(pi) * exp(-u_eps * u_eps)
+    d = T.pos[None, :, :] - T.pos[:, None, :]                       # d[i, j] = x_j - x_i
+    assert np.linalg.norm(d, axis=2).max() < eps
+    clamped = mass * g_eps / eps ** 3 * d.sum(axis=1)               # every source at the clamped radius
+    for variant in (1, 2):
+        acc = _run(ctx, T, tt, ts, mass, eps, rs, variant, box)
+        ref, npairs = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs)
+        absr, _ = oracle.p2p(T.pos, T.leaf_npart, T.leaf_ipart, T.pos, T.leaf_npart, T.leaf_ipart, tt, ts, mass, eps, rs, absterms=True)
+        assert npairs == n * n
+        na = np.linalg.norm(absr, axis=1)
+        dev = np.linalg.norm(acc - ref, axis=1) / na
+        assert dev.max() < bound, (variant, dev.max(), bound)
+        assert dev.max() > 0.05 * bound                             # the test does see the deviation it is about
+        assert (np.linalg.norm(acc - clamped, axis=1) / na).max() < 5e-6, variant
+
+
 def test_empty_inputs(ctx):
     ctx.set_physics(1.0, 0.1, 1.0)
     ctx.upload_particles(np.zeros((0, 3)))
