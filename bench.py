@@ -403,6 +403,8 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_source,
                          "kernel": "p2p_rows2_kernel<NSRC=1,STAGE=384,trunc,3 blocks/SM> (one pass per row, near + far bodies, FFMA2)",
                          "kernel_ms": force_ms, "flop_per_pair": FLOP_PER_PAIR,
+                         "note": "kernel_ms = sum of the force-kernel launches of one step inside the timed region; with the halo overlap "
+                                 "(N > 1) the local kernel shares the SMs with the walk / packing / NCCL kernels of the comm stream",
                          "peak_source": f"{props.multi_processor_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peaks_kind}); "
                                         "the file holds no FP32 figure, SURVEY.md section 8d defines this peak",
                          "hbm": {"algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (force_ms * 1e-3) / 1e9,

@@ -204,6 +204,14 @@ int p2p_tree_walk_range(p2p_ctx* ctx, double theta, double rcut, double period, 
  * step, p2p_counts / p2p_download_csr only see the last chunk. */
 int p2p_forces_local(p2p_ctx* ctx, double theta, double rcut, double period, const double tcenter[3], const double twidth[3], int compute);
 int p2p_set_chunk_tasks(p2p_ctx* ctx, int64_t max_tasks);
+/* Chunk pipeline: a single-rank p2p_forces_local (no p2p_set_rank with nranks > 1) of at least 4096 x min_chunks leaves is cut
+ * into at least min_chunks target chunks, and walk + packing of chunk k + 1 run on a second, high-priority stream into the
+ * other list set while the force kernel of chunk k runs (the reference's ping-pong task buffers, 1_Indexing/src/fmm.c:365-400,
+ * 947-1024, on the device).  Results are bit-identical to the unchunked step.  Default 0 = off: measured on B200 it gains
+ * nothing at 256^3 and 1.4 % at 512^3 -- each of the ~50 dependent launches of a walk waits for force-kernel warps to
+ * retire.  While it runs the context alternates its two list sets itself, so p2p_swap_lists must not be
+ * used to hold a list across the call. */
+int p2p_set_chunk_pipeline(p2p_ctx* ctx, int min_chunks);
 /* device milliseconds of the last step: tree build, walks, packing and force kernels (summed over the chunks) */
 int p2p_step_timings(p2p_ctx* ctx, float* ms_build, float* ms_walk, float* ms_csr, float* ms_force, int* nchunk);
 /* number of sources listed twice in a row of the packed list (0 unless the periodic box is too small) */

@@ -68,6 +68,11 @@ struct p2p_dtree {
     int last_chunks = 0;
     long long max_chunk_tasks = 1LL << 29;
     std::vector<cudaEvent_t> chunk_ev;
+    // chunk pipeline of p2p_forces_local: walk + packing of chunk k + 1 on pipe_stream while the force kernel of chunk k runs
+    int pipe_chunks = 0;         // chunks a single-rank step is cut into at least (<= 1: no pipeline)
+    int nranks = 1;              // p2p_set_rank; the pipeline is for single-rank steps (a multi-rank step overlaps its remote phase)
+    cudaStream_t pipe_stream = nullptr;
+    cudaEvent_t ev_pipe_built = nullptr, ev_pack_done[2] = {nullptr, nullptr}, ev_force_done[2] = {nullptr, nullptr};
 };
 
 void p2p_dtree_release(p2p_dtree* t) {
@@ -94,6 +99,9 @@ void p2p_dtree_release(p2p_dtree* t) {
     if (t->e0) cudaEventDestroy(t->e0);
     if (t->e1) cudaEventDestroy(t->e1);
     for (cudaEvent_t e : t->chunk_ev) cudaEventDestroy(e);
+    if (t->pipe_stream) cudaStreamDestroy(t->pipe_stream);
+    for (cudaEvent_t e : {t->ev_pipe_built, t->ev_pack_done[0], t->ev_pack_done[1], t->ev_force_done[0], t->ev_force_done[1]})
+        if (e) cudaEventDestroy(e);
     delete t;
 }
 
@@ -879,7 +887,7 @@ int p2p_set_rank(p2p_ctx* c, int rank, int nranks) {
     p2p_dtree* t;
     int r = get_tree(c, &t);
     if (r) return r;
-    t->self_rank = rank;
+    t->self_rank = rank; t->nranks = nranks;
     return 0;
 }
 
@@ -1125,6 +1133,62 @@ int p2p_midfield_download(p2p_ctx* c, double* leaf_M, double* node_M, double* le
 // force kernel, in TARGET CHUNKS (ranges of leaves) sized so that one chunk's list stays below max_chunk_tasks
 // (p2p_set_chunk_tasks): the task list of 1024^3 particles on one GPU would take 6.7e9 x 12 bytes.  The accelerations
 // accumulate; p2p_accumulated_counts gives the totals, p2p_step_timings the device times summed over the chunks.
+}  // extern "C"
+
+namespace {
+// The chunks of p2p_forces_local as a two-stage pipeline: walk and packing of chunk k + 1 run on a second, high-priority
+// stream into the other list set while the force kernel of chunk k runs on the caller's stream with retiring warps (so that
+// the small latency-bound kernels of the walk and the packing find SM slots).  Replaces the ping-pong task buffers of the
+// reference (1_Indexing/src/fmm.c:365-400, 947-1024: walk into one buffer while the other is computed -- serialised in this
+// fork).  Every row still lives in exactly one chunk and is summed in the same order: results are bit-identical.
+int forces_local_pipelined(p2p_ctx* c, p2p_dtree* t, int nchunk, double theta, double rcut, double period, const double tcenter[3],
+                           const double twidth[3], int compute, cudaStream_t A, int user_budget) {
+    if (!t->pipe_stream) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&t->pipe_stream, cudaStreamNonBlocking, greatest));
+        CU(cudaEventCreateWithFlags(&t->ev_pipe_built, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            CU(cudaEventCreateWithFlags(&t->ev_pack_done[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&t->ev_force_done[k], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t W = t->pipe_stream;
+    const int nleaf = t->nleaf;
+    CU(cudaEventRecord(t->ev_pipe_built, A));            // tree, particles, zeroed accelerations
+    CU(cudaStreamWaitEvent(W, t->ev_pipe_built, 0));
+    int r;
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int lo = (int)((long long)nleaf * ch / nchunk), hi = (int)((long long)nleaf * (ch + 1) / nchunk);
+        const int set = ch & 1;
+        if (ch > 0 && (r = p2p_swap_lists(c))) return r;
+        c->stream = W;
+        if (ch >= 2) CU(cudaStreamWaitEvent(W, t->ev_force_done[set], 0));      // the kernel that consumed this set two chunks ago
+        if ((r = p2p_clear_tasks(c))) return r;
+        t->ms_walk = 0.f;
+        if (hi > lo && (r = p2p_tree_walk_range(c, theta, rcut, period, tcenter, twidth, lo, hi))) return r;
+        t->sum_walk += t->ms_walk;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch], W));
+        c->row_lo = lo; c->row_hi = hi;
+        r = hi > lo ? p2p_build_csr(c) : 0;
+        c->row_lo = c->row_hi = 0;
+        if (r) return r;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 1], W));
+        CU(cudaEventRecord(t->ev_pack_done[set], W));
+        c->stream = A;
+        CU(cudaStreamWaitEvent(A, t->ev_pack_done[set], 0));
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 3], A));
+        c->rows_per_warp = ch + 1 < nchunk ? std::max(user_budget, 4) : user_budget;    // the last kernel has nothing to make room for
+        if (compute && hi > lo && (r = p2p_compute(c))) return r;
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 2], A));
+        CU(cudaEventRecord(t->ev_force_done[set], A));
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int p2p_forces_local(p2p_ctx* c, double theta, double rcut, double period, const double tcenter[3], const double twidth[3], int compute) {
     USE(c);
     p2p_dtree* t = c->dtree;
@@ -1133,10 +1197,20 @@ int p2p_forces_local(p2p_ctx* c, double theta, double rcut, double period, const
     const long long est = (long long)nleaf * (period > 0.0 ? 200 : 170);
     int nchunk = (int)std::min<long long>((est + t->max_chunk_tasks - 1) / t->max_chunk_tasks, std::max(nleaf, 1));
     if (nchunk < 1) nchunk = 1;
+    // single-rank steps of a useful size are cut into at least pipe_chunks chunks and pipelined
+    const bool pipe = t->pipe_chunks > 1 && t->nranks <= 1 && compute && nleaf >= 4096 * t->pipe_chunks;
+    if (pipe) nchunk = std::max(nchunk, t->pipe_chunks);
     while ((int)t->chunk_ev.size() < 4 * nchunk) { cudaEvent_t e; CU(cudaEventCreate(&e)); t->chunk_ev.push_back(e); }
     t->sum_walk = t->sum_csr = t->sum_force = 0.f;
     t->last_chunks = nchunk;
     int r;
+    if (pipe) {
+        cudaStream_t A = c->stream;
+        const int user_budget = c->rows_per_warp;
+        r = forces_local_pipelined(c, t, nchunk, theta, rcut, period, tcenter, twidth, compute, A, user_budget);
+        c->stream = A; c->rows_per_warp = user_budget; c->row_lo = c->row_hi = 0;
+        return r;
+    }
     for (int ch = 0; ch < nchunk; ch++) {
         const int lo = (int)((long long)nleaf * ch / nchunk), hi = (int)((long long)nleaf * (ch + 1) / nchunk);
         if ((r = p2p_clear_tasks(c))) return r;
@@ -1150,9 +1224,22 @@ int p2p_forces_local(p2p_ctx* c, double theta, double rcut, double period, const
         c->row_lo = c->row_hi = 0;
         if (r) return r;
         CU(cudaEventRecord(t->chunk_ev[4 * ch + 1], c->stream));
+        CU(cudaEventRecord(t->chunk_ev[4 * ch + 3], c->stream));
         if (compute && (hi > lo || nchunk == 1) && (r = p2p_compute(c))) return r;
         CU(cudaEventRecord(t->chunk_ev[4 * ch + 2], c->stream));
     }
+    return 0;
+}
+
+// chunks a single-rank p2p_forces_local is cut into at least, pipelined (walk + packing of the next chunk beside the force
+// kernel of the current one); 0 or 1 = off
+int p2p_set_chunk_pipeline(p2p_ctx* c, int min_chunks) {
+    USE(c);
+    p2p_dtree* t;
+    int r = get_tree(c, &t);
+    if (r) return r;
+    if (min_chunks < 0 || min_chunks > 64) return fail(P2P_ERR_ARG, "bad chunk count");
+    t->pipe_chunks = min_chunks;
     return 0;
 }
 
@@ -1177,7 +1264,7 @@ int p2p_step_timings(p2p_ctx* c, float* ms_build, float* ms_walk, float* ms_csr,
     for (int ch = 0; ch < t->last_chunks && 4 * ch + 2 < (int)t->chunk_ev.size(); ch++) {
         float a = 0.f, b = 0.f;
         if (cudaEventElapsedTime(&a, t->chunk_ev[4 * ch], t->chunk_ev[4 * ch + 1]) == cudaSuccess) csr += a;
-        if (cudaEventElapsedTime(&b, t->chunk_ev[4 * ch + 1], t->chunk_ev[4 * ch + 2]) == cudaSuccess) force += b;
+        if (cudaEventElapsedTime(&b, t->chunk_ev[4 * ch + 3], t->chunk_ev[4 * ch + 2]) == cudaSuccess) force += b;
     }
     cudaGetLastError();
     if (ms_build) *ms_build = t->ms_build;

@@ -142,9 +142,9 @@ int launch_cfg(p2p_ctx* c, const p2p::KernelParams& P) {
 }
 
 // Second-generation kernel (p2p_rows2_kernel): one pass per row, near and far slice bodies.
-template <int NSRC, bool TRUNC, int MINB, int DBG = 0>
-int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
-    auto kern = p2p::p2p_rows2_kernel<NSRC, kStage, TRUNC, MINB, DBG>;
+template <int NSRC, bool TRUNC, int MINB, int DBG, bool BLOCKED, bool RETIRE>
+int launch_rows2_inst(p2p_ctx* c, const p2p::KernelParams& P) {
+    auto kern = p2p::p2p_rows2_kernel<NSRC, kStage, TRUNC, MINB, DBG, BLOCKED, RETIRE>;
     const int smem = 4 * (int)sizeof(p2p::WarpSmem2<kStage>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
@@ -156,20 +156,34 @@ int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P) {
     Q.persist_blocks = (int)grid;
     // non-persistent mode: budgeted blocks in front of one persistent wave; a budgeted block handles at least four rows, blocks
     // that find the schedule exhausted leave at once
-    if (P.rows_per_warp > 0) grid += want / 2;
+    if (RETIRE && P.rows_per_warp > 0) grid += want / 2;
     kern<<<(unsigned)grid, 128, smem, c->stream>>>(Q);
     CU(cudaGetLastError());
     c->last_blocks_per_sm = per_sm;
     return 0;
 }
+// the shipped configuration comes in four builds (blocked summation x retiring warps, both compile-time); the tuning and
+// debug variants only in the general one
+template <int NSRC, bool TRUNC, int MINB, int DBG = 0, bool ALL = false>
+int launch_rows2(p2p_ctx* c, const p2p::KernelParams& P, bool blocked) {
+    const bool retire = P.rows_per_warp > 0;
+    if constexpr (ALL) {
+        if (!blocked && !retire) return launch_rows2_inst<NSRC, TRUNC, MINB, DBG, false, false>(c, P);
+        if (!blocked && retire) return launch_rows2_inst<NSRC, TRUNC, MINB, DBG, false, true>(c, P);
+        if (blocked && !retire) return launch_rows2_inst<NSRC, TRUNC, MINB, DBG, true, false>(c, P);
+    }
+    p2p::KernelParams Q = P;
+    if (!blocked) Q.block_leaves = 0x3fffffff;       // the general build: one block per class
+    return launch_rows2_inst<NSRC, TRUNC, MINB, DBG, true, true>(c, Q);
+}
 template <bool TRUNC>
-int launch_cfg2(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb) {
+int launch_cfg2(p2p_ctx* c, const p2p::KernelParams& P, int nsrc, int minb, bool blocked) {
     if constexpr (TRUNC) {
-        if (nsrc == 9) return launch_rows2<1, true, 2, 1>(c, P);          // error-budget variant: fp64 force factor (pair_exact2)
-        if (nsrc == 2) return launch_rows2<2, true, 3>(c, P);
-        return minb == 4 ? launch_rows2<1, true, 4>(c, P) : launch_rows2<1, true, 3>(c, P);
+        if (nsrc == 9) return launch_rows2<1, true, 2, 1>(c, P, blocked);          // error-budget variant: fp64 force factor (pair_exact2)
+        if (nsrc == 2) return launch_rows2<2, true, 3>(c, P, blocked);
+        return minb == 4 ? launch_rows2<1, true, 4>(c, P, blocked) : launch_rows2<1, true, 3, 0, true>(c, P, blocked);
     } else {
-        return launch_rows2<1, false, 3>(c, P);
+        return launch_rows2<1, false, 3>(c, P, blocked);
     }
 }
 
@@ -611,7 +625,8 @@ int p2p_build_csr(p2p_ctx* c) {
     USE(c);
     CU(cudaEventRecord(c->ev2, c->stream));
     const ListSet L = list_set(c, 0);
-    CU(cudaMemsetAsync(c->d_bad, 0, 2 * sizeof(unsigned int), c->stream));
+    // (only the list flag: a force kernel consuming the other list set may be raising the kernel flag d_bad[1] right now)
+    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(unsigned int), c->stream));
     int r = pack_csr(c, L, c->ntask, c->stream);
     if (r) return r;
     CU(cudaMemcpyAsync(c->h_flags + 2, c->d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
@@ -635,6 +650,7 @@ static int check_flags(p2p_ctx* c) {
     }
     if (c->h_flags[3] != 0) {
         c->h_flags[3] = 0;
+        cudaMemsetAsync(c->d_bad + 1, 0, sizeof(unsigned int), c->stream);       // reported once
         return fail(P2P_ERR_ARG, "a source leaf holds more than %d particles (ghost leaf table not validated?): its pairs were skipped", kStage);
     }
     return 0;
@@ -649,11 +665,11 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
     P.part = c->part.p; P.leaf = c->leaf.p; P.row_ptr = L.row_ptr->p; P.col = L.col->p; P.acc = c->acc.p;
     P.counter = L.d_counter; P.n_active = L.d_counter + 2; P.row_order = L.order->p; P.nrow = c->nleaf;
     P.row_mid = L.row_mid->p; P.err = c->d_bad + 1; P.rows_per_warp = c->rows_per_warp;
-    {
-        static int blk = 0;                         // sweeps only: P2P_B200_BLOCK_LEAVES overrides the block size
-        if (!blk) { const char* e = getenv("P2P_B200_BLOCK_LEAVES"); blk = e ? atoi(e) : p2p::kBlockLeaves; if (blk < 1) blk = p2p::kBlockLeaves; }
-        P.block_leaves = blk;
-    }
+    // blocked summation of long classes: off unless P2P_B200_BLOCK_LEAVES names a block size (experiments)
+    static int blk = -1;
+    if (blk < 0) { const char* e = getenv("P2P_B200_BLOCK_LEAVES"); blk = e ? atoi(e) : 0; if (blk < 0) blk = 0; }
+    P.block_leaves = blk > 0 ? blk : p2p::kBlockLeaves;
+    const bool blocked = blk > 0;
     const bool trunc = c->rs > 0.0;
     const bool packed = c->variant != P2P_KERNEL_SCALAR;
     const bool v2 = packed && (c->tune_tt == 0 || c->tune_tt == 32);
@@ -696,7 +712,7 @@ int launch_force(p2p_ctx* c, const ListSet& L, long long ntask, cudaStream_t st)
         if (v2) {
             const int nsrc = c->tune_nsrc ? c->tune_nsrc : kDefaultNsrc;
             const int minb = c->tune_minb ? c->tune_minb : kDefaultMinBlocks;
-            r = trunc ? launch_cfg2<true>(c, P, nsrc, minb) : launch_cfg2<false>(c, P, nsrc, minb);
+            r = trunc ? launch_cfg2<true>(c, P, nsrc, minb, blocked) : launch_cfg2<false>(c, P, nsrc, minb, blocked);
         } else {
             const int tt = (c->tune_tt == 8 || c->tune_tt == 16) ? c->tune_tt : (c->max_target_leaf <= 8 ? 8 : 16);
             if (tt == 8) {

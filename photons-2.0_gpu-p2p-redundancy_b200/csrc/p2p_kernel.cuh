@@ -674,7 +674,10 @@ __device__ __forceinline__ void run_range2(const KernelParams& P, WarpSmem2<STAG
     }
 }
 
-template <int NSRC, int STAGE, bool TRUNC, int MINB, int DBG = 0>
+// BLOCKED: classes are summed in blocks of P.block_leaves source leaves (off in the shipped configuration: it costs 2.5 %
+// and buys nothing measurable); RETIRE: the time-budgeted non-persistent mode of a multi-rank step.
+// Both are compile-time: carried as run-time options they cost the plain kernel 2.6 ms of 59.5 at 256^3.
+template <int NSRC, int STAGE, bool TRUNC, int MINB, int DBG = 0, bool BLOCKED = false, bool RETIRE = false>
 __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -695,11 +698,11 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
     // of each other whatever the rows cost (a fixed row count left three warps of a block idle behind the one that drew a
     // dense-clump row: 0.42 instead of 0.58 of peak on the clustered 1024^3 box).  The last persist_blocks blocks never retire,
     // so the grid finishes the schedule however many rows the budgeted blocks leave.
-    const bool retiring = P.rows_per_warp > 0 && (int)blockIdx.x < (int)gridDim.x - P.persist_blocks;
-    const long long t_retire = clock64() + ((long long)P.rows_per_warp << 17);
+    const bool retiring = RETIRE && P.rows_per_warp > 0 && (int)blockIdx.x < (int)gridDim.x - P.persist_blocks;
+    const long long t_retire = RETIRE ? clock64() + ((long long)P.rows_per_warp << 17) : 0;
 
     for (bool first = true;; first = false) {
-        if (retiring && !first && clock64() > t_retire) break;
+        if (RETIRE && retiring && !first && clock64() > t_retire) break;
         int row = -1;
         if (lane == 0) {
             const unsigned int idx = atomicAdd(P.counter, 1u);
@@ -728,8 +731,8 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
         // large fraction of sum |terms| before the other side of the target cancels it, and every FP32 addition rounds relative
         // to that swing (at z = 49 the net force is 1.4 % of sum |terms|).  The FAR columns come first: their many small terms
         // are summed among themselves before the few large near terms arrive (demo box: median error 2.7e-6 -> 1.9e-6 of the
-        // mean force, for free).  Classes longer than block_leaves source leaves (dense clumps) are consumed in blocks, each
-        // reduced over the warp into the per-target totals of lane j and restarted from zero.
+        // mean force, for free).  BLOCKED: classes longer than block_leaves source leaves (dense clumps) are consumed in blocks,
+        // each reduced over the warp into the per-target totals of lane j and restarted from zero.
         float rx = 0.f, ry = 0.f, rz = 0.f;
         float2 ax[TP], ay[TP], az[TP];
 #pragma unroll
@@ -749,22 +752,29 @@ __global__ void __launch_bounds__(128, MINB) p2p_rows2_kernel(const KernelParams
 #pragma unroll
             for (int j = 0; j < TP; j++) ax[j] = ay[j] = az[j] = make_float2(0.f, 0.f);
         };
-        for (int cls = 0; cls < 2; cls++) {                   // 0: far columns [e_begin, e_mid), 1: near columns [e_mid, e_end)
-            const long long c_end = cls ? e_end : e_mid;
-            for (long long lo = cls ? e_mid : e_begin; lo < c_end; lo += P.block_leaves) {
-                const long long hi = lo + P.block_leaves < c_end ? lo + P.block_leaves : c_end;
-                switch ((nt + 1) >> 1) {                      // target pairs of this row (warp-uniform)
+        auto run_class = [&](int cls, long long lo, long long hi) {
+            switch ((nt + 1) >> 1) {                          // target pairs of this row (warp-uniform)
 #define P2P_CASE(k)                                                                                                           \
     case k:                                                                                                                   \
         if (cls) run_range2<k, false, NSRC, STAGE, TRUNC, DBG>(P, S, c4, lo, hi, lane, phase0, phase1, ax, ay, az);           \
         else run_range2<k, TRUNC, NSRC, STAGE, TRUNC, DBG>(P, S, c4, lo, hi, lane, phase0, phase1, ax, ay, az);               \
         break;
-                    P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
-                    P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
+                P2P_CASE(1) P2P_CASE(2) P2P_CASE(3) P2P_CASE(4) P2P_CASE(5) P2P_CASE(6) P2P_CASE(7) P2P_CASE(8)
+                P2P_CASE(9) P2P_CASE(10) P2P_CASE(11) P2P_CASE(12) P2P_CASE(13) P2P_CASE(14) P2P_CASE(15) P2P_CASE(16)
 #undef P2P_CASE
-                    default: break;
+                default: break;
+            }
+        };
+        for (int cls = 0; cls < 2; cls++) {                   // 0: far columns [e_begin, e_mid), 1: near columns [e_mid, e_end)
+            const long long c_begin = cls ? e_mid : e_begin, c_end = cls ? e_end : e_mid;
+            if constexpr (BLOCKED) {
+                for (long long lo = c_begin; lo < c_end; lo += P.block_leaves) {
+                    const long long hi = lo + P.block_leaves < c_end ? lo + P.block_leaves : c_end;
+                    run_class(cls, lo, hi);
+                    if (hi < c_end) flush();                  // a further block of this class follows
                 }
-                if (hi < c_end) flush();                      // a further block of this class follows
+            } else {
+                if (c_begin < c_end) run_class(cls, c_begin, c_end);
             }
         }
         flush();

@@ -7,7 +7,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libp2p_b200.so")
+LIB_PATH = os.environ.get("P2P_B200_LIB") or os.path.join(LIB_DIR, "libp2p_b200.so")     # the override serves kernel A/B builds (tools/README.md)
 
 KERNEL_AUTO, KERNEL_SCALAR, KERNEL_PACKED = 0, 1, 2
 
@@ -101,6 +101,7 @@ def load_library():
     L.p2p_resident_count.argtypes = [C.c_void_p, _lp]
     L.p2p_forces_local.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _dp, C.c_int]
     L.p2p_set_chunk_tasks.argtypes = [C.c_void_p, C.c_int64]
+    L.p2p_set_chunk_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.p2p_step_timings.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 4 + [_ip]
     L.p2p_swap_lists.argtypes = [C.c_void_p]
     L.p2p_set_force_blocks.argtypes = [C.c_void_p, C.c_int]
@@ -508,6 +509,10 @@ class P2PContext:
 
     def set_chunk_tasks(self, max_tasks):
         self._chk(self._L.p2p_set_chunk_tasks(self._h, int(max_tasks)))
+
+    def set_chunk_pipeline(self, min_chunks=0):
+        """single-rank forces_local: at least min_chunks target chunks, walk + packing of the next beside the forces of the current (0: off)"""
+        self._chk(self._L.p2p_set_chunk_pipeline(self._h, int(min_chunks)))
 
     def step_timings(self):
         v = [C.c_float() for _ in range(4)]

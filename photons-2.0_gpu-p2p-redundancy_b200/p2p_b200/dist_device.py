@@ -205,9 +205,12 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
     built.record(A)
     # ---- local phase: my tree against itself and its own periodic images (walk, packing, force kernel; in target chunks
     # when the list would not fit)
+    nvtx = torch.cuda.nvtx
+    nvtx.range_push("p2p/local phase: walk + pack + forces")
     ctx.set_force_blocks(4 if (P > 1 and overlap) else 0)        # warps retire after ~0.3 ms
     ctx.forces_local(theta, rcut, period, tc, tw, p2p)
     ctx.set_force_blocks(0)
+    nvtx.range_pop()
     t2 = time.perf_counter()
     local_done = torch.cuda.Event()
     local_done.record(A)
@@ -222,6 +225,7 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
             ctx.swap_lists()
             ctx.clear_tasks()
             ev["c0"].record(B)
+            nvtx.range_push("p2p/remote phase: topology all-gather")
             stride = ctx.topology_stride(nlmax, nnmax)
             mine = torch.empty(stride, dtype=torch.uint8, device=dev)
             ctx.tree_export_packed(mine.data_ptr(), nlmax, nnmax)
@@ -232,10 +236,14 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
                 ctx.midfield_multipoles(M_mine.data_ptr())
                 M_all = _all_gather_blocks(M_mine, P, group)
             ev["c1"].record(B)
+            nvtx.range_pop()
+            nvtx.range_push("p2p/remote phase: walk against the peers' trees")
             ev["w0"].record(B)
             ctx.tree_walk_peers_packed(theta, rcut, period, tc, tw, me, nls, nns, topo.data_ptr(), nlmax, nnmax, 0)
             remote_walk_ms = ctx.tree_info()["ms_walk"]
             ev["w1"].record(B)
+            nvtx.range_pop()
+            nvtx.range_push("p2p/remote phase: halo plan + exchange")
             ev["c2"].record(B)
             marks = torch.empty(max(G, 1), dtype=torch.uint8, device=dev)
             need = ctx.halo_plan_need(topo.data_ptr(), me, nls, nlmax, nnmax, marks.data_ptr())
@@ -253,6 +261,8 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
             ctx.halo_set_particles(ghosts.data_ptr() if nbody else None, nbody)
             S.ghost_guess = max(S.ghost_guess, int(1.25 * nbody))
             ev["c3"].record(B)
+            nvtx.range_pop()
+            nvtx.range_push("p2p/remote phase: pack + forces")
             ctx.build_csr()
             B.wait_event(local_done)        # both force kernels accumulate into the same accelerations
             if p2p:
@@ -261,6 +271,7 @@ def lists_halo_forces(ctx, rcut, box, bdl, bdr, theta, periodic, group, timings=
                 ctx.midfield_compute_peers_packed(P, topo.data_ptr(), nlmax, nnmax, M_all.data_ptr())
             remote_done = torch.cuda.Event()
             remote_done.record(B)
+            nvtx.range_pop()
         A.wait_event(remote_done)
         ctx.set_stream(A.cuda_stream)
         nt_r = ctx.counts()[0]

@@ -299,3 +299,34 @@ def test_target_chunks_reproduce_the_unchunked_step(demo_pos):
     assert np.array_equal(out[0][2], out[1][2])                      # P2P part (FP32, tree order): bit for bit
     # with the mid-field (fp64 atomics: summation order differs)
     assert np.abs(out[0][4] - out[1][4]).max() < 1e-10 * np.abs(out[0][4]).max()
+
+
+def test_pipelined_chunks_equal_the_unpipelined_step():
+    """The chunk pipeline of p2p_forces_local (walk + packing of chunk k + 1 on a second stream and in the other list set beside
+    the force kernel of chunk k, retiring warps) against the same step in one piece: identical counts, identical M2L list,
+    bit-identical P2P accelerations -- every row lives in exactly one chunk and is summed in the same order."""
+    from p2p_b200 import synth
+    nside = 64
+    pos, box = synth.clustered(nside)
+    rs, rcut, eps = oracle.derived_params(box, nside, len(pos))
+    bdl, bdr = np.zeros(3), np.full(3, box)
+    out = []
+    for pipe in (0, 4, 7):
+        ctx = p2p_b200.P2PContext(0)
+        ctx.set_physics(DEMO_MASS, eps, rs)
+        ctx.set_box([0.0, 0.0, 0.0], box)
+        ctx.set_chunk_pipeline(pipe)
+        ctx.midfield_enable(True, False)
+        for rep in range(2):                                   # the second step reuses buffers, events and the second stream
+            ctx.tree_build(pos, 8, bdl, bdr, 0)
+            ctx.forces_local(THETA, rcut, box, 0.5 * (bdl + bdr), bdr - bdl)
+            nm2l = ctx.midfield_compute()
+            st = ctx.step_timings()
+            res = (ctx.accumulated_counts(), nm2l, ctx.download_acc(), st["chunks"])
+        out.append(res)
+        ctx.close()
+    assert [o[3] for o in out] == [1, 4, 7]
+    for o in out[1:]:
+        assert o[0] == out[0][0] and o[1] == out[0][1]
+        assert np.array_equal(o[2], out[0][2])
+
