@@ -248,3 +248,46 @@ def test_routing_partition_closed_form():
             x = np.sort(rng.random(n))[::-1].copy()
         split = float(rng.choice([0.5, rng.random(), -1.0, 2.0, 1.0, 0.0]))
         assert ref_route_partition(x, split) == model_route_partition(x, split)
+
+
+# ---- register bitonic network of the CSR row sort (csrc/csr_pack.cuh: warp_sort_keys) --------------------------------
+def model_warp_sort(v):
+    """v[e][lane], key i = e * 32 + lane: exchanges at distance j < 32 are a shuffle (lane ^ j), at j >= 32 they pair the
+    registers e and e | (j / 32) of one lane -- the index arithmetic of warp_sort_keys, statement for statement"""
+    E = len(v)
+    lane = np.arange(32)
+    k = 2
+    while k <= 32 * E:
+        j = k >> 1
+        while j > 0:
+            if j >= 32:
+                je = j >> 5
+                for e in range(E):
+                    if (e & je) == 0:
+                        up = ((e << 5) & k) == 0
+                        lo, hi = np.minimum(v[e], v[e | je]), np.maximum(v[e], v[e | je])
+                        v[e], v[e | je] = (lo, hi) if up else (hi, lo)
+            else:
+                lower = (lane & j) == 0
+                for e in range(E):
+                    y = v[e][lane ^ j]
+                    up = (((e << 5) | lane) & k) == 0
+                    v[e] = np.where(lower == up, np.minimum(v[e], y), np.maximum(v[e], y))
+            j >>= 1
+        k <<= 1
+    return v
+
+
+@pytest.mark.parametrize("E", [1, 2, 4, 8, 16])
+def test_register_bitonic_network_sorts(E):
+    rng = np.random.default_rng(E)
+    n = 32 * E
+    for trial in range(150):
+        ln = int(rng.integers(2, n + 1))
+        keys = (rng.integers(0, 50, ln) if trial % 3 == 0 else rng.integers(0, 2 ** 32 - 1, ln, dtype=np.uint64)).astype(np.uint32)
+        if trial % 5 == 0:
+            keys |= np.uint32(0x80000000) * (rng.random(ln) < 0.4).astype(np.uint32)      # class bit: near columns sort last
+        a = np.full(n, 0xffffffff, np.uint32)
+        a[:ln] = keys
+        out = np.concatenate(model_warp_sort([a[e * 32:(e + 1) * 32].copy() for e in range(E)]))
+        assert np.array_equal(out[:ln], np.sort(keys))
