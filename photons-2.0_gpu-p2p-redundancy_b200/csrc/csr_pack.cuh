@@ -224,8 +224,10 @@ __device__ __forceinline__ void warp_sort_row(unsigned int* __restrict__ col, lo
         if (e * 32 + lane < len) col[b + e * 32 + lane] = v[e];
 }
 
+// (rows above kSortCap columns are listed in long_rows[0 .. *unsorted) for csr_sort_long_rows_kernel)
 __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __restrict__ row_ptr, int nrow,
-                                                            int* __restrict__ col_, unsigned int* __restrict__ unsorted) {
+                                                            int* __restrict__ col_, unsigned int* __restrict__ unsorted,
+                                                            int* __restrict__ long_rows) {
     __shared__ unsigned int sh[4][kSortCap];
     unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);     // unsigned order: near columns (bit 31) last
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
         const long long b = row_ptr[row];
         const int len = (int)(row_ptr[row + 1] - b);
         if (len <= 1) continue;
-        if (len > kSortCap) { if (lane == 0) atomicAdd(unsorted, 1u); continue; }
+        if (len > kSortCap) { if (lane == 0) long_rows[atomicAdd(unsorted, 1u)] = row; continue; }
         if (len <= kSortRegCap) {
             if (len <= 32) warp_sort_row<1>(col, b, len, lane);
             else if (len <= 64) warp_sort_row<2>(col, b, len, lane);
@@ -266,12 +268,14 @@ __global__ void __launch_bounds__(128) csr_sort_rows_kernel(const long long* __r
 // Rows above kSortCap columns (dense clumps): one block per row, bitonic network in global memory in the form whose
 // compare-exchanges all put the smaller key at the lower index, so that positions beyond the row's length act as +inf
 // without being stored.
-__global__ void __launch_bounds__(256) csr_sort_long_rows_kernel(const long long* __restrict__ row_ptr, int nrow, int* __restrict__ col_) {
+__global__ void __launch_bounds__(256) csr_sort_long_rows_kernel(const long long* __restrict__ row_ptr, const unsigned int* __restrict__ n_long,
+                                                                 const int* __restrict__ long_rows, int* __restrict__ col_) {
     unsigned int* __restrict__ col = reinterpret_cast<unsigned int*>(col_);
-    for (int row = blockIdx.x; row < nrow; row += gridDim.x) {
+    const int n = (int)*n_long;                           // usually 0: scanning the whole row table for them cost 0.85 ms at 256^3
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const int row = long_rows[r];
         const long long b = row_ptr[row];
         const long long len = row_ptr[row + 1] - b;
-        if (len <= kSortCap) continue;
         long long m = 1;
         while (m < len) m <<= 1;
         for (long long k = 2; k <= m; k <<= 1) {

@@ -61,6 +61,7 @@ struct p2p_dtree {
     int walk_levels = 0;
     int plain_max = p2p::dt::kSeqPlainMax;
     bool block_mode = true;
+    bool node_mode = true;       // deep levels through node_level_kernel
     float ms_build = 0.f, ms_walk = 0.f;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     // p2p_forces_local: sums over its target chunks
@@ -142,7 +143,9 @@ int p2p_tree_set_option(p2p_ctx* c, int seq_sum_plain_max) {
     int r = get_tree(c, &t);
     if (r) return r;
     // -2: default thresholds but every node through the warp kernel (no block-per-node variant);
-    // -3: block-per-node but no speculative chunked evaluation; -4: speculative evaluation for every node above one chunk
+    // -3: block-per-node but no speculative chunked evaluation; -4: speculative evaluation for every node above one chunk;
+    // -5: defaults, but the deep levels through the particle-wide kernels as well (no node-centric levels)
+    t->node_mode = seq_sum_plain_max != -5;
     t->block_mode = seq_sum_plain_max != -2;
     t->spec_min = seq_sum_plain_max == -3 ? 0 : (seq_sum_plain_max == -4 ? 2048 : 32768);
     t->plain_max = seq_sum_plain_max < 0 ? p2p::dt::kSeqPlainMax : seq_sum_plain_max;
@@ -300,20 +303,29 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
             p2p::dt::chunk_transducer_kernel<<<std::min(maxchunks, c->num_sm * 4), p2p::dt::kBlockWarps * 32, 0, st>>>(A, Sp, b, n, dir);
             p2p::dt::chunk_combine_kernel<<<std::min(n, c->num_sm), p2p::dt::kBlockWarps * 32, 0, st>>>(A, Sp, b, n, dir);
         }
-        if (longest > block_min)
-            p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min, spec_min);
+        // deep levels (no node above kNodeMax particles): a warp per node does the whole level (node_level_kernel)
+        const bool node_mode = t->node_mode && longest <= p2p::dt::kNodeMax;
         const int warps = std::min(n, c->num_sm * 64);
-        p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max, block_min);
-        p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
-        p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
-        p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
-        p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
-        p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
+        if (node_mode) {
+            p2p::dt::node_level_kernel<<<blocks((long long)warps * 32, p2p::dt::kNodeWarps * 32), p2p::dt::kNodeWarps * 32, 0, st>>>(
+                A, b, n, dir, maxleaf, t->plain_max, t->child_cnt.p);
+        } else {
+            if (longest > block_min)
+                p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min, spec_min);
+            p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max, block_min);
+            p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
+            p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
+            p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
+            p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
+            p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
+        }
         p2p::dt::child_scan_kernel<<<1, 1024, 0, st>>>(t->child_cnt.p, n, t->d_scalar);
         CU(cudaMemsetAsync(t->d_scalar + 2, 0, sizeof(int), st));
         p2p::dt::children_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p, b + n, (int)ncap, t->d_scalar + 2);
-        p2p::dt::slot_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
-        p2p::dt::swap_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
+        if (!node_mode) {
+            p2p::dt::slot_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
+            p2p::dt::swap_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
+        }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(t->h_scalar, t->d_scalar, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

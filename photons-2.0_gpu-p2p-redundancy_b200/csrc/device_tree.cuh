@@ -711,6 +711,100 @@ __global__ void swap_kernel(BuildArrays A, long long npart) {
     A.perm[j] = pa;
 }
 
+// ---- node-centric level (deep levels: every node of the level holds at most kNodeMax particles) ------------------------
+// One warp does for its node what the particle-wide kernels above do for all nodes together -- split mean, flags, left
+// count, the pairing of the k-th big element of the left zone with the small element of the right zone that has k small
+// elements to its right, the swaps -- with the flags as ballot masks in shared memory instead of a global flag array, a
+// global scan and a slot array: one kernel and one read of the split coordinate per level instead of eight kernels and six
+// passes over all particles.  Same closed form, same special cases (runs of 2 and < 2), same split arithmetic.
+constexpr int kNodeMax = 2048;
+constexpr int kNodeWarps = 4;
+
+struct NodeSmem {
+    unsigned int mask[kNodeMax / 32];        // flag bits (x > split) of the node's particles, 32 per word
+    unsigned short big[kNodeMax / 2];        // left-zone big elements in index order (relative positions)
+    unsigned short small_r[kNodeMax / 2];    // right-zone small elements by the number of small elements to their right
+};
+
+__global__ void __launch_bounds__(kNodeWarps * 32) node_level_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int maxleaf,
+                                                                   int plain_max, int* __restrict__ nchild_nodes) {
+    __shared__ NodeSmem sm_all[kNodeWarps];
+    NodeSmem& sm = sm_all[threadIdx.x >> 5];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const double* __restrict__ X = A.x[dir];
+    for (int n = w; n < lvl_count; n += nw) {
+        const int t = lvl_begin + n;
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t];
+        int np0 = 0;
+        double split = 0.0;
+        if (len == 2) {
+            const double x0 = X[start], x1 = X[start + 1];
+            split = 0.5 * (x0 + x1);
+            np0 = 1;
+            __syncwarp();                                        // every lane has read the pair
+            if (x0 > x1 && lane < 4) {                           // the two are put in ascending order
+                if (lane < 3) { const double a = A.x[lane][start], b = A.x[lane][start + 1]; A.x[lane][start] = b; A.x[lane][start + 1] = a; }
+                else { const int a = A.perm[start], b = A.perm[start + 1]; A.perm[start] = b; A.perm[start + 1] = a; }
+            }
+        } else if (len > 2) {
+            const double ssum = len <= plain_max ? seq_sum_warp_plain(X, start, len) : seq_sum_warp(X, start, len);
+            split = ssum / (double)len;
+            // flags as ballot masks; number of big elements
+            const int nword = (len + 31) >> 5;
+            int nbig = 0;
+            for (int c = 0; c < nword; c++) {
+                const int i = c * 32 + lane;
+                const bool f = i < len && X[start + i] > split;
+                const unsigned m = __ballot_sync(full, f);
+                if (lane == 0) sm.mask[c] = m;
+                nbig += __popc(m);
+            }
+            __syncwarp();
+            np0 = nbig == 0 ? len - 1 : len - nbig;
+            if (nbig > 0) {
+                // every lane walks the words with running counts (uniform), and files its own element of the word
+                int big_before = 0;                              // big elements in the words before c
+                const int nsmall = len - nbig;
+                for (int c = 0; c < nword; c++) {
+                    const unsigned m = sm.mask[c];
+                    const int i = c * 32 + lane;
+                    if (i < len) {
+                        const int bl = big_before + __popc(m & ((1u << lane) - 1u));      // big elements left of i
+                        const bool f = (m >> lane) & 1u;
+                        if (i < np0) { if (f) sm.big[bl] = (unsigned short)i; }
+                        else if (!f) sm.small_r[nsmall - (i - bl) - 1] = (unsigned short)i;  // i - bl small elements left of i
+                    }
+                    big_before += __popc(m);
+                }
+                __syncwarp();
+                // big elements of the left zone = small elements of the right zone = np0 - (small elements of the left zone)
+                int big_left = 0;
+                for (int c = 0; c * 32 < np0; c++) {
+                    const unsigned m = sm.mask[c];
+                    const int rem = np0 - c * 32;
+                    big_left += __popc(rem >= 32 ? m : (m & ((1u << rem) - 1u)));
+                }
+                for (int k = lane; k < big_left; k += 32) {
+                    const long long i = start + sm.big[k], j = start + sm.small_r[k];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { const double a = A.x[d][i], b = A.x[d][j]; A.x[d][i] = b; A.x[d][j] = a; }
+                    const int pa = A.perm[i], pb = A.perm[j];
+                    A.perm[i] = pb; A.perm[j] = pa;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            A.t_split[t] = split;
+            A.t_np0[t] = np0;
+            nchild_nodes[n] = (np0 > maxleaf) + (len - np0 > maxleaf);
+        }
+    }
+}
+
 // ---- particle routing by the rank kd-tree (prepare_body_inOrderOf_domain, 1_Indexing/src/domains.c:163-296) -----------
 // The same level-synchronous partition with GIVEN split values: the reference's bksort_body_inplace is, for runs of three
 // or more, the standard pairing (k-th big element from the left of [0, ns) <-> k-th small one from the right of [ns, len),

@@ -606,8 +606,9 @@ int pack_csr(p2p_ctx* c, const ListSet& L, long long n, cudaStream_t st) {
     if (n) {
         p2p::csr_scatter_kernel<<<G, 256, 0, st>>>(L.tt->p, L.ts->p, n, row0, nrow, nsrc, L.cursor->p, L.col->p,
                                                    reinterpret_cast<const p2p::LeafBounds*>(c->lbounds.p), far2);
-        p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p + row0, nrow, L.col->p, L.d_counter + 1);
-        p2p::csr_sort_long_rows_kernel<<<c->num_sm * 2, 256, 0, st>>>(L.row_ptr->p + row0, nrow, L.col->p);
+        // (the list of long rows borrows the schedule array, which is written only afterwards)
+        p2p::csr_sort_rows_kernel<<<G, 128, 0, st>>>(L.row_ptr->p + row0, nrow, L.col->p, L.d_counter + 1, L.order->p);
+        p2p::csr_sort_long_rows_kernel<<<c->num_sm * 2, 256, 0, st>>>(L.row_ptr->p + row0, L.d_counter + 1, L.order->p, L.col->p);
         int* d_band = reinterpret_cast<int*>(L.whist->p + 2 * (size_t)p2p::kWorkBuckets * nband);
         p2p::band_rows_kernel<<<1, 32, 0, st>>>(c->d_occ, nrow, c->num_sm * 16, band_rows(), d_band);
         p2p::pair_count_kernel<<<G, 256, 0, st>>>(L.row_ptr->p + row0, L.col->p, c->leaf.p, row0, nrow, L.d_npairs, L.row_work->p + row0, L.whist->p,

@@ -291,3 +291,72 @@ def test_register_bitonic_network_sorts(E):
         a[:ln] = keys
         out = np.concatenate(model_warp_sort([a[e * 32:(e + 1) * 32].copy() for e in range(E)]))
         assert np.array_equal(out[:ln], np.sort(keys))
+
+
+# ---- node-centric level (csrc/device_tree.cuh: node_level_kernel): the same closed form from ballot masks ---------------
+def model_node_level(x, mean):
+    """one warp, flags as 32-bit words: the counting and filing of node_level_kernel, statement for statement"""
+    x = np.asarray(x)
+    n = len(x)
+    nword = (n + 31) >> 5
+    mask = []
+    for c in range(nword):
+        m = 0
+        for lane in range(32):
+            i = c * 32 + lane
+            if i < n and x[i] > mean:
+                m |= 1 << lane
+        mask.append(m)
+    nbig = sum(bin(m).count("1") for m in mask)
+    np0 = n - 1 if nbig == 0 else n - nbig
+    idx = list(range(n))
+    if nbig == 0:
+        return idx, np0
+    nsmall = n - nbig
+    big, small_r = {}, {}
+    big_before = 0
+    for c in range(nword):
+        m = mask[c]
+        for lane in range(32):
+            i = c * 32 + lane
+            if i < n:
+                bl = big_before + bin(m & ((1 << lane) - 1)).count("1")
+                f = (m >> lane) & 1
+                if i < np0:
+                    if f:
+                        big[bl] = i
+                elif not f:
+                    small_r[nsmall - (i - bl) - 1] = i
+        big_before += bin(m).count("1")
+    big_left = 0
+    c = 0
+    while c * 32 < np0:
+        rem = np0 - c * 32
+        big_left += bin(mask[c] if rem >= 32 else mask[c] & ((1 << rem) - 1)).count("1")
+        c += 1
+    assert sorted(big) == list(range(big_left)) and sorted(small_r) == list(range(big_left))
+    for k in range(big_left):
+        i, j = big[k], small_r[k]
+        idx[i], idx[j] = idx[j], idx[i]
+    return idx, np0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_node_level_model_equals_reference_partition(seed):
+    rng = np.random.default_rng(100 + seed)
+    for trial in range(500):
+        n = int(rng.integers(3, 200))
+        kind = trial % 5
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = rng.integers(0, 4, n).astype(np.float64)
+        elif kind == 2:
+            x = np.full(n, 3.25)
+        elif kind == 3:
+            x = np.sort(rng.random(n))[::-1].copy()
+        else:
+            x = np.sort(rng.random(n))
+        idx, but, mean = ref_partition(x)
+        midx, np0 = model_node_level(x, mean)
+        assert (midx, np0) == (idx, but)
