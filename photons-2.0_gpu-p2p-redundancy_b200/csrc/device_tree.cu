@@ -51,7 +51,7 @@ struct p2p_dtree {
     ull* h_wcount = nullptr;     // pinned
     unsigned int* d_dup = nullptr;
     int* d_maxw = nullptr;
-    double max_leaf_width = 0.0;
+    double max_leaf_width = 0.0, max_parent_width = -1.0;   // device-built trees; the latter bounds the separations of a local walk
     DevBuf<double> v[3], vtmp[3];     // device-resident stepping: velocities (tree order) and carry scratch
     DevBuf<int> gid, gidtmp;          // ... and the particles' ids
     bool stepping = false;
@@ -117,7 +117,7 @@ int get_tree(p2p_ctx* c, p2p_dtree** out) {
         CU(cudaMalloc(&t->d_wcount, p2p::dt::kWalkCounters * sizeof(ull)));
         CU(cudaMallocHost(&t->h_wcount, p2p::dt::kWalkCounters * sizeof(ull)));
         CU(cudaMalloc(&t->d_dup, sizeof(unsigned int)));
-        CU(cudaMalloc(&t->d_maxw, sizeof(int)));
+        CU(cudaMalloc(&t->d_maxw, 2 * sizeof(int)));
         CU(cudaEventCreate(&t->e0));
         CU(cudaEventCreate(&t->e1));
         static const int shifts[28][3] = {{0, 0, 0},
@@ -268,6 +268,14 @@ int p2p_tree_build(p2p_ctx* c, const double* pos, int64_t stride, int64_t npart,
 
 namespace {
 // build_localtree over the particles resident in t->x / t->perm (current order = the order the reference would start from)
+// levels with at most this many nodes evaluate the split mean with a block (or speculative chunks on all SMs) per node,
+// levels with more nodes with a warp per node (P2P_B200_FEW_NODES overrides, for sweeps)
+int few_nodes(int num_sm) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("P2P_B200_FEW_NODES"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+    return v > 0 ? v : num_sm;
+}
+
 int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const double bdl[3], const double bdr[3], int direct_start) {
     cudaStream_t st = c->stream;
     int r;
@@ -289,7 +297,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
         if (lvl > 256) return fail(P2P_ERR_ARG, "kd-tree deeper than 256 levels (more than maxleaf coincident particles?)");
         const int b = lvl_begin[lvl], n = lvl_count[lvl], dir = (direct_start + lvl) % 3;
         // few, long nodes: chunks on all SMs (speculative binade) or a block each; many nodes: a warp each
-        const bool few = t->block_mode && n <= c->num_sm * 4;
+        const bool few = t->block_mode && n <= few_nodes(c->num_sm);
         const int block_min = few ? 2048 : 0x7fffffff;
         const int spec_min = (few && t->spec_min > 0) ? std::max(t->spec_min, block_min) : 0x7fffffff;
         if (longest > spec_min) {
@@ -356,7 +364,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     O.nleaf = nleaf; O.box = t->box.p; O.son = t->son.p; O.node_npart = t->node_npart.p; O.node_split = t->node_split.p;
     O.leaf_npart = t->leaf_npart.p; O.leaf_ipart = t->leaf_ipart.p; O.max_width = t->d_maxw;
     O.node_leaf0 = t->node_leaf0.p; O.node_nleaf = t->node_nleaf.p;
-    CU(cudaMemsetAsync(t->d_maxw, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(t->d_maxw, 0, 2 * sizeof(int), st));
     for (int lvl = 0; lvl < t->nlevel; lvl++)
         p2p::dt::assign_down_kernel<<<blocks(lvl_count[lvl], 256), 256, 0, st>>>(A, O, lvl_begin[lvl], lvl_count[lvl], (direct_start + lvl) % 3,
                                                                                bdl[0], bdl[1], bdl[2], bdr[0], bdr[1], bdr[2]);
@@ -377,10 +385,11 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     c->max_target_leaf = maxleaf;
     if ((r = p2p_update_occupancy(c))) return r;
     CU(cudaEventRecord(t->e1, st));
-    float wmaxf = 0.f;
-    CU(cudaMemcpyAsync(&wmaxf, t->d_maxw, sizeof wmaxf, cudaMemcpyDeviceToHost, st));
+    float wmaxf[2] = {0.f, 0.f};
+    CU(cudaMemcpyAsync(wmaxf, t->d_maxw, sizeof wmaxf, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    t->max_leaf_width = wmaxf;
+    t->max_leaf_width = wmaxf[0];
+    t->max_parent_width = wmaxf[1];
     CU(cudaEventElapsedTime(&t->ms_build, t->e0, t->e1));
     t->npart = npart; t->maxleaf = maxleaf; t->nleaf = nleaf; t->nnode = nnode; t->cap = cap; t->direct_start = direct_start;
     t->valid = true; t->built_here = true; t->mid_valid = false; t->nm2l = 0;
@@ -878,8 +887,13 @@ int p2p_tree_walk_range(p2p_ctx* c, double theta, double rcut, double period, co
     const int me = t->self_rank;              // 0 unless p2p_set_rank said otherwise: the peer index the M2L tasks carry
     P.sbox = t->box.p; P.sson = t->son.p; P.me = me; P.npeer = me + 1; P.snleaf[me] = nleaf;
     if (period > 0.0) {
-        if ((r = leaf_bounds(c, t))) return r;
+        if ((r = leaf_bounds(c, t))) return r;            // (also what p2p_tree_export_packed ships)
         P.tb = t->tb.p; P.stb = t->tb.p;
+        // A leaf pair enters the frontier from a pair that passed the cutoff test (cell gap < r_cut) with a node that has a leaf
+        // child in the leaf's place, so no listed particle separation exceeds r_cut + 2 (largest such node).  If that is below
+        // half the period the per-pair check of the tight bounds -- two 48-byte gathers for every one of the 1e8 tasks of 256^3 --
+        // cannot fire and is skipped; small boxes (the 32-cell demo after a few steps) keep the exact per-pair check.
+        if (t->built_here && t->max_parent_width >= 0.0 && rcut + 2.0 * t->max_parent_width * (1.0 + 1e-6) < 0.5 * period) P.tb = nullptr;
     }
     if (leaf_hi > 0) { P.node_leaf0 = t->node_leaf0.p; P.node_nleaf = t->node_nleaf.p; P.t_lo = leaf_lo; P.t_hi = leaf_hi; }
     std::vector<ull> init;

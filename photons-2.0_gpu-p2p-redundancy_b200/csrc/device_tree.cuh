@@ -943,7 +943,7 @@ struct TreeOut {
     double* node_split;
     int* leaf_npart;
     int* leaf_ipart;
-    int* max_width;                  // float bits of the largest leaf width (non-negative floats order like integers); informational
+    int* max_width;                  // float bits (non-negative floats order like integers): [0] largest leaf width, [1] largest width of a node with a leaf child
     int* node_leaf0;                 // first leaf and number of leaves of every node's subtree (leaves are numbered left to right),
     int* node_nleaf;                 // for walks restricted to a range of target leaves
 };
@@ -1012,6 +1012,10 @@ __global__ void assign_down_kernel(BuildArrays A, TreeOut O, int lvl_begin, int 
         }
     }
     warp_atomic_max(O.max_width, __float_as_int((float)wmax));
+    // largest cell of a node that has a leaf child: bounds every particle separation a LOCAL walk can list (a leaf pair enters
+    // the frontier from a pair that passed the cutoff test with this node in the leaf's place)
+    const double pmax = wmax > 0.0 ? fmax(nwid[0], fmax(nwid[1], nwid[2])) : 0.0;
+    warp_atomic_max(O.max_width + 1, __float_as_int((float)pmax));
 }
 
 __global__ void soa_from_aos_kernel(const double* __restrict__ pos, long long n, double* __restrict__ x, double* __restrict__ y,
