@@ -14,6 +14,8 @@
 #define fail p2p_fail
 using p2p::dt::ull;
 
+constexpr int kBlockLevelMinNodes = 64;     // a level runs block-centric once it has this many nodes (and none above kBlockNodeMax particles)
+
 struct p2p_dtree {
     // final tree
     long long npart = 0;
@@ -62,6 +64,7 @@ struct p2p_dtree {
     int plain_max = p2p::dt::kSeqPlainMax;
     bool block_mode = true;
     bool node_mode = true;       // deep levels through node_level_kernel
+    int block_level_min = kBlockLevelMinNodes;     // middle levels through block_level_kernel from this many nodes per level on (0: never)
     float ms_build = 0.f, ms_walk = 0.f;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     // p2p_forces_local: sums over its target chunks
@@ -144,8 +147,10 @@ int p2p_tree_set_option(p2p_ctx* c, int seq_sum_plain_max) {
     if (r) return r;
     // -2: default thresholds but every node through the warp kernel (no block-per-node variant);
     // -3: block-per-node but no speculative chunked evaluation; -4: speculative evaluation for every node above one chunk;
-    // -5: defaults, but the deep levels through the particle-wide kernels as well (no node-centric levels)
+    // -5: defaults, but the deep levels through the particle-wide kernels as well (no node-centric and no block-centric levels);
+    // -6: no block-centric levels; -7: block-centric levels from the root on (every node up to kBlockNodeMax particles)
     t->node_mode = seq_sum_plain_max != -5;
+    t->block_level_min = (seq_sum_plain_max == -5 || seq_sum_plain_max == -6) ? 0 : (seq_sum_plain_max == -7 ? 1 : kBlockLevelMinNodes);
     t->block_mode = seq_sum_plain_max != -2;
     t->spec_min = seq_sum_plain_max == -3 ? 0 : (seq_sum_plain_max == -4 ? 2048 : 32768);
     t->plain_max = seq_sum_plain_max < 0 ? p2p::dt::kSeqPlainMax : seq_sum_plain_max;
@@ -293,6 +298,7 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
     // ---- levels
     std::vector<int> lvl_begin{0}, lvl_count{1};
     int total_nodes = 1, longest = (int)npart;
+    bool block_levels = false;
     for (int lvl = 0;; lvl++) {
         if (lvl > 256) return fail(P2P_ERR_ARG, "kd-tree deeper than 256 levels (more than maxleaf coincident particles?)");
         const int b = lvl_begin[lvl], n = lvl_count[lvl], dir = (direct_start + lvl) % 3;
@@ -313,6 +319,11 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
         }
         // deep levels (no node above kNodeMax particles): a warp per node does the whole level (node_level_kernel)
         const bool node_mode = t->node_mode && longest <= p2p::dt::kNodeMax;
+        // middle levels (enough nodes to fill the chip, none above kBlockNodeMax particles): a block per node for everything
+        // but the split mean (block_level_kernel).  Sticky: its levels do not maintain the particle -> node map the
+        // particle-wide kernels need.
+        if (!node_mode && t->block_level_min > 0 && n >= t->block_level_min && longest <= p2p::dt::kBlockNodeMax) block_levels = true;
+        const bool block_lvl = block_levels && !node_mode;
         const int warps = std::min(n, c->num_sm * 64);
         if (node_mode) {
             p2p::dt::node_level_kernel<<<blocks((long long)warps * 32, p2p::dt::kNodeWarps * 32), p2p::dt::kNodeWarps * 32, 0, st>>>(
@@ -321,16 +332,20 @@ int build_core(p2p_ctx* c, p2p_dtree* t, long long npart, int maxleaf, const dou
             if (longest > block_min)
                 p2p::dt::mean_block_kernel<<<std::min(n, c->num_sm * 2), p2p::dt::kBlockWarps * 32, 0, st>>>(A, b, n, dir, block_min, spec_min);
             p2p::dt::mean_kernel<<<blocks((long long)warps * 32, 128), 128, 0, st>>>(A, b, n, dir, t->plain_max, block_min);
-            p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
-            p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
-            p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
-            p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
-            p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
+            if (block_lvl) {
+                p2p::dt::block_level_kernel<<<std::min(n, c->num_sm * 3), p2p::dt::kBlockLevelThreads, 0, st>>>(A, b, n, dir, maxleaf, t->child_cnt.p);
+            } else {
+                p2p::dt::flag_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart, dir);
+                p2p::dt::flag_tile_sums_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p);
+                p2p::dt::flag_tile_offsets_kernel<<<1, 1024, 0, st>>>(t->tile.p, ntile);
+                p2p::dt::flag_scan_apply_kernel<<<ntile, 256, 0, st>>>(A.flag, npart, t->tile.p, A.G);
+                p2p::dt::split_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p);
+            }
         }
         p2p::dt::child_scan_kernel<<<1, 1024, 0, st>>>(t->child_cnt.p, n, t->d_scalar);
         CU(cudaMemsetAsync(t->d_scalar + 2, 0, sizeof(int), st));
         p2p::dt::children_kernel<<<blocks(n, 256), 256, 0, st>>>(A, b, n, maxleaf, t->child_cnt.p, b + n, (int)ncap, t->d_scalar + 2);
-        if (!node_mode) {
+        if (!node_mode && !block_lvl) {
             p2p::dt::slot_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
             p2p::dt::swap_kernel<<<blocks(npart, 256), 256, 0, st>>>(A, npart);
         }

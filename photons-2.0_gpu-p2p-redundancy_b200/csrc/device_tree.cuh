@@ -805,6 +805,94 @@ __global__ void __launch_bounds__(kNodeWarps * 32) node_level_kernel(BuildArrays
     }
 }
 
+// ---- block-centric level (middle levels: enough nodes to fill the chip, none above kBlockNodeMax particles) ------------
+// The same closed form with one BLOCK per node: every warp owns a contiguous range of the node's 32-particle words, counts
+// its big elements in a first sweep (flags kept as ballot masks in shared memory), a scan over the warp counts gives every
+// warp its starting rank, and a second sweep over the masks files the left-zone big elements and the right-zone small
+// elements into two lists (the node's own range of the slot / seg_next arrays, which the particle-wide kernels no longer
+// need once a level runs here: the later levels all run here or in node_level_kernel).  Replaces flag, the three scan
+// kernels, split, slot and swap of a level; the split means come from the mean kernels as before.
+constexpr int kBlockNodeMax = 131072;
+constexpr int kBlockLevelThreads = 512;
+
+__global__ void __launch_bounds__(kBlockLevelThreads) block_level_kernel(BuildArrays A, int lvl_begin, int lvl_count, int dir, int maxleaf,
+                                                                       int* __restrict__ nchild_nodes) {
+    constexpr int NW = kBlockLevelThreads / 32;
+    __shared__ unsigned int mask[kBlockNodeMax / 32];
+    __shared__ int wcnt[NW];
+    __shared__ int s_big_left;
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double* __restrict__ X = A.x[dir];
+    for (int n = blockIdx.x; n < lvl_count; n += gridDim.x) {
+        const int t = lvl_begin + n;
+        const long long start = A.t_start[t];
+        const int len = A.t_len[t];
+        int np0 = 0;
+        if (len == 2) {
+            const double x0 = X[start], x1 = X[start + 1];
+            np0 = 1;
+            __syncthreads();                                     // every thread has read the pair
+            if (x0 > x1 && tid < 4) {                            // the two are put in ascending order
+                if (tid < 3) { const double a = A.x[tid][start], b = A.x[tid][start + 1]; A.x[tid][start] = b; A.x[tid][start + 1] = a; }
+                else { const int a = A.perm[start], b = A.perm[start + 1]; A.perm[start] = b; A.perm[start + 1] = a; }
+            }
+        } else if (len > 2) {
+            const double split = A.t_split[t];
+            const int nword = (len + 31) >> 5;
+            const int w0 = (int)((long long)nword * wid / NW), w1 = (int)((long long)nword * (wid + 1) / NW);
+            int cnt = 0;
+            for (int c = w0; c < w1; c++) {
+                const int i = c * 32 + lane;
+                const bool f = i < len && X[start + i] > split;
+                const unsigned m = __ballot_sync(full, f);
+                if (lane == 0) mask[c] = m;
+                cnt += __popc(m);
+            }
+            if (lane == 0) wcnt[wid] = cnt;
+            if (tid == 0) s_big_left = 0;
+            __syncthreads();
+            int run = 0, nbig = 0;
+            for (int v = 0; v < NW; v++) { const int x = wcnt[v]; if (v < wid) run += x; nbig += x; }
+            np0 = nbig == 0 ? len - 1 : len - nbig;
+            if (nbig > 0) {                                      // uniform over the block
+                const int nsmall = len - nbig;
+                int* __restrict__ big_list = A.slot + start;     // left-zone big elements in index order
+                int* __restrict__ small_list = A.seg_next + start;   // right-zone small elements by the number of small elements to their right
+                int my_left = 0;
+                for (int c = w0; c < w1; c++) {
+                    const unsigned m = mask[c];
+                    const int i = c * 32 + lane;
+                    if (i < len) {
+                        const int bl = run + __popc(m & ((1u << lane) - 1u));      // big elements left of i
+                        const bool f = (m >> lane) & 1u;
+                        if (i < np0) { if (f) big_list[bl] = i; }
+                        else if (!f) small_list[nsmall - (i - bl) - 1] = i;        // i - bl small elements left of i
+                    }
+                    const int rem = np0 - c * 32;
+                    my_left += __popc(rem >= 32 ? m : (rem > 0 ? (m & ((1u << rem) - 1u)) : 0u));
+                    run += __popc(m);
+                }
+                if (lane == 0 && my_left) atomicAdd(&s_big_left, my_left);
+                __syncthreads();                                 // lists complete (global writes of this block are visible to it)
+                const int big_left = s_big_left;
+                for (int k = tid; k < big_left; k += kBlockLevelThreads) {
+                    const long long i = start + big_list[k], j = start + small_list[k];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { const double a = A.x[d][i], b = A.x[d][j]; A.x[d][i] = b; A.x[d][j] = a; }
+                    const int pa = A.perm[i], pb = A.perm[j];
+                    A.perm[i] = pb; A.perm[j] = pa;
+                }
+            }
+        }
+        if (tid == 0) {
+            A.t_np0[t] = np0;
+            nchild_nodes[n] = (np0 > maxleaf) + (len - np0 > maxleaf);
+        }
+        __syncthreads();                                         // masks and counters are reused by the block's next node
+    }
+}
+
 // ---- particle routing by the rank kd-tree (prepare_body_inOrderOf_domain, 1_Indexing/src/domains.c:163-296) -----------
 // The same level-synchronous partition with GIVEN split values: the reference's bksort_body_inplace is, for runs of three
 // or more, the standard pairing (k-th big element from the left of [0, ns) <-> k-th small one from the right of [ns, len),

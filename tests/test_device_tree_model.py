@@ -360,3 +360,73 @@ def test_node_level_model_equals_reference_partition(seed):
         idx, but, mean = ref_partition(x)
         midx, np0 = model_node_level(x, mean)
         assert (midx, np0) == (idx, but)
+
+
+# ---- block-centric level (csrc/device_tree.cuh: block_level_kernel): warps own contiguous word ranges -------------------
+def model_block_level(x, mean, nwarp):
+    """the two sweeps of block_level_kernel with `nwarp` warps: per-warp counts, exclusive scan, ranks from running counts"""
+    x = np.asarray(x)
+    n = len(x)
+    nword = (n + 31) >> 5
+    popc = lambda v: bin(v).count("1")
+    mask = [0] * nword
+    wcnt = [0] * nwarp
+    rng_of = lambda w: (nword * w // nwarp, nword * (w + 1) // nwarp)
+    for w in range(nwarp):
+        for c in range(*rng_of(w)):
+            m = 0
+            for lane in range(32):
+                i = c * 32 + lane
+                if i < n and x[i] > mean:
+                    m |= 1 << lane
+            mask[c] = m
+            wcnt[w] += popc(m)
+    nbig = sum(wcnt)
+    np0 = n - 1 if nbig == 0 else n - nbig
+    idx = list(range(n))
+    if nbig == 0:
+        return idx, np0
+    nsmall = n - nbig
+    big, small, big_left = {}, {}, 0
+    for w in range(nwarp):
+        run = sum(wcnt[:w])
+        for c in range(*rng_of(w)):
+            m = mask[c]
+            for lane in range(32):
+                i = c * 32 + lane
+                if i < n:
+                    bl = run + popc(m & ((1 << lane) - 1))
+                    f = (m >> lane) & 1
+                    if i < np0:
+                        if f:
+                            big[bl] = i
+                    elif not f:
+                        small[nsmall - (i - bl) - 1] = i
+            rem = np0 - c * 32
+            big_left += popc(m if rem >= 32 else (m & ((1 << rem) - 1) if rem > 0 else 0))
+            run += popc(m)
+    assert sorted(big) == list(range(big_left)) and sorted(small) == list(range(big_left))
+    for k in range(big_left):
+        i, j = big[k], small[k]
+        idx[i], idx[j] = idx[j], idx[i]
+    return idx, np0
+
+
+@pytest.mark.parametrize("nwarp", [1, 3, 16])
+def test_block_level_model_equals_reference_partition(nwarp):
+    rng = np.random.default_rng(200 + nwarp)
+    for trial in range(400):
+        n = int(rng.integers(3, 700))
+        kind = trial % 5
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = rng.integers(0, 4, n).astype(np.float64)
+        elif kind == 2:
+            x = np.full(n, 3.25)
+        elif kind == 3:
+            x = np.sort(rng.random(n))[::-1].copy()
+        else:
+            x = np.sort(rng.random(n))
+        idx, but, mean = ref_partition(x)
+        assert model_block_level(x, mean, nwarp) == (idx, but)

@@ -122,12 +122,12 @@ def _inputs(kind, n, seed, box):
     ("uniform", 5000, 8, 0), ("uniform", 40000, 16, 1), ("f32", 30000, 32, 2), ("clumpy", 30000, 16, 0),
     ("grid", 20000, 32, 1), ("uniform", 3, 1, 0), ("uniform", 2, 1, 0), ("uniform", 2, 8, 0), ("uniform", 1, 8, 0), ("uniform", 37, 1, 2),
     ("f32", 300000, 32, 0)])
-@pytest.mark.parametrize("plain_max", [-1, -2, -3, -4, -5, 0, 1 << 30])
+@pytest.mark.parametrize("plain_max", [-1, -2, -3, -4, -5, -6, -7, 0, 1 << 30])
 def test_device_build_is_the_reference_tree(ctx, kind, n, maxleaf, direct, plain_max):
     """plain_max -1: defaults (speculative chunks / block per long node, warp per node, in-order fold for short runs, node-centric
     deep levels); -2: no block variant; -3: no speculative chunks; -4: speculative chunks for every node above 2048 particles;
-    -5: particle-wide kernels for the deep levels too; 0: every split mean through the parallel transducer sum; 1<<30: every
-    one through the in-order fold"""
+    -5: particle-wide kernels for all levels; -6: no block-centric middle levels; -7: block-centric levels from the root on;
+    0: every split mean through the parallel transducer sum; 1<<30: every one through the in-order fold"""
     box = 1000.0
     pos = _inputs(kind, n, 1234 + n, box)
     bdl, bdr = [0.0, 0.0, 0.0], [box, box, box]

@@ -1,7 +1,8 @@
 #!/bin/bash
-# one-GPU session: smoke(), the default bench line, then the ncu launch list of the same bench command
+# one-GPU session: tree-build tests with the block-centric levels, then the resident step timing
 cd /root/repo
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/r2A_smoke.txt; cat gpurun_out/r2A_smoke.txt
-timeout 400 python bench.py > gpurun_out/r2A_bench256_n1.json 2> gpurun_out/r2A_bench256_n1.err; echo rc256 $?
-timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-launch-count > gpurun_out/r2A_plain.json 2> gpurun_out/r2A_plain.err && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2A_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-launch-count > gpurun_out/r2A_ncu.log 2>&1; echo rcncu $?
+timeout 900 python -m pytest tests/test_gpu_device_tree.py tests/test_gpu_resident.py tests/test_gpu_midfield.py -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r2C_pytest.txt; cat gpurun_out/r2C_pytest.txt
+timeout 200 python tools/device_step.py 256 32 3 --resident 2>&1 | tail -1 > gpurun_out/r2C_devstep.txt
+timeout 200 python tools/device_step.py 128 32 3 --resident 2>&1 | tail -1 >> gpurun_out/r2C_devstep.txt
+timeout 200 python tools/device_step.py 128 32 2 --clustered 2>&1 | tail -1 >> gpurun_out/r2C_devstep.txt
+cat gpurun_out/r2C_devstep.txt
