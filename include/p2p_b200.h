@@ -325,7 +325,9 @@ int p2p_midfield_compute_peers_packed(p2p_ctx* ctx, int npeer, const void* d_top
 int p2p_midfield_download(p2p_ctx* ctx, double* leaf_M, double* node_M, double* leaf_L, double* node_L, float* ms);
 
 /* test knob: runs up to this length use the plain in-order fold for the split mean, longer ones the exact parallel
- * evaluation of the same sequential sum (< 0 restores the default) */
+ * evaluation of the same sequential sum.  Negative values select build paths (every one gives the same tree): -1 defaults;
+ * -2 no block-per-node split mean; -3 no speculative chunks; -4 speculative chunks for every node above 2048 particles;
+ * -5 particle-wide kernels for all levels; -6 no block-centric middle levels; -7 block-centric levels from the root on */
 int p2p_tree_set_option(p2p_ctx* ctx, int seq_sum_plain_max);
 
 #ifdef __cplusplus
