@@ -38,7 +38,7 @@ def launches(path, out):
     print(open(out).read())
 
 
-def traffic(path, key, pattern):
+def traffic(path, key, pattern, write=True):
     sel = {}
     table = rows(path)
     if table and "Metric Name" not in table[0]:
@@ -76,6 +76,8 @@ def traffic(path, key, pattern):
                     "inst_executed": get(d, "smsp__inst_executed.sum"),
                     "thread_inst_per_inst": get(d, "smsp__thread_inst_executed_per_inst_executed.ratio")})
     best = max(out, key=lambda o: o["duration_ms"] or 0)
+    if not write:
+        return best
     tab_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     tab = json.load(open(tab_path)) if os.path.isfile(tab_path) else {}
     tab[key] = dict(best, source=f"ncu --set full, {os.path.basename(path)}, launch {best['launch']} of {len(out)} matching {pattern}")
