@@ -88,6 +88,31 @@ def test_demo_local_list(ctx, demo_pos, golden, maxleaf, truncated, variant):
     assert e1 < TOL and e2 < TOL, (e1, e2)
 
 
+@pytest.mark.parametrize("truncated", [True, False])
+def test_device_step_matches_the_golden_force_vectors(demo_pos, truncated):
+    """The one-call device step (tree build + walk + packing + forces on the GPU; local list of the demo, MAXLEAF 16) against
+    the COMMITTED golden force vectors tests/golden/demo_forces.npz -- 4096 sampled particles by original index; the plain
+    vector is the one the reference's own GPU kernel reproduces to 1.2e-15 (tests/golden/make_golden_forces.py)."""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "demo_forces.npz"))
+    rs, rcut, eps = oracle.derived_params(DEMO_BOX, DEMO_NSIDE, len(demo_pos))
+    c = p2p_b200.P2PContext(0)
+    try:
+        c.set_physics(DEMO_MASS, eps, rs if truncated else 0.0)
+        c.set_box([0.0, 0.0, 0.0], DEMO_BOX)
+        acc = c.step_device(demo_pos, 16, [0, 0, 0], [DEMO_BOX] * 3, THETA, rcut, 0.0)        # original particle order
+        assert c.counts() == (381377, 83354950)
+    finally:
+        c.close()
+    name = "trunc" if truncated else "plain"
+    ref, absr = g["acc_" + name], g["abs_" + name]
+    d = np.linalg.norm(acc[g["index"]] - ref, axis=1)
+    na = np.linalg.norm(ref, axis=1)
+    assert (d / np.maximum(na, na.mean())).max() < TOL
+    assert (d / np.linalg.norm(absr, axis=1)).max() < TOL
+
+
 def test_demo_full_step_with_periodic_images(demo_pos):
     """Product host code + ghosts + kernel == oracle's intended whole step (D6 fixed), original particle order."""
     L = step.build_lists(demo_pos, DEMO_BOX, 16, DEMO_NSIDE, THETA, periodic=True)

@@ -45,3 +45,21 @@ def test_multirank_flow_matches_reference_golden(demo_pos, golden, nproc):
         assert [len(r["tt"]) for r in rk["remote"]] == g["remote_tasks"]
         pairs = [int((T.leaf_npart[r["tt"]].astype(np.int64) * r["image"]["npart"][r["ts"]]).sum()) for r in rk["remote"]]
         assert pairs == g["remote_pairs"]
+
+
+def test_oracle_reproduces_the_golden_force_vectors():
+    """tests/golden/demo_forces.npz (made by tests/golden/make_golden_forces.py; its plain vector equals what the reference's
+    own GPU kernel returns on this list to 1.2e-15, profiles/r2_reference_kernel_r64_vs_oracle.json): the oracle still
+    produces it -- same tree, same list, same fp64 arithmetic (libm erfc / exp may differ in the last bits between builds)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_golden_forces", os.path.join(ROOT, "tests", "golden", "make_golden_forces.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    got = m.compute()
+    want = np.load(os.path.join(ROOT, "tests", "golden", "demo_forces.npz"))
+    assert np.array_equal(got["index"], want["index"])
+    assert np.array_equal(got["acc_plain"], want["acc_plain"])                       # sqrt and division only: bit for bit
+    scale = np.linalg.norm(want["acc_trunc"], axis=1).mean()
+    assert np.abs(got["acc_trunc"] - want["acc_trunc"]).max() < 1e-13 * scale
